@@ -1,0 +1,176 @@
+/*
+ * simgan_b200 C ABI  --  the drop-in boundary under the Python classes that mirror the reference's
+ * Policy / PPO / gail.Discriminator / RolloutStorage.
+ *
+ * The reference (jyf588/SimGAN) is pure Python and has no FFI for this path; each entry point below
+ * replaces the eager-PyTorch op sequence of the cited reference function.  Citations are relative to
+ * the reference root; A2C = third_party/a2c_ppo_acktr.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host); no ownership transfer
+ *   - all tensors are dense fp32 in the reference's own layouts (time-major (T,N,D) rollout buffers,
+ *     nn.Linear weights (out,in) row-major); indices are int32 flat sample ids t*N+n
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
+ *   - return value: 0 on success, non-zero on error; sg_last_error() gives the message
+ *   - flat parameter vectors use the segment tables returned by sg_policy_layout / sg_disc_layout
+ *     (every segment starts on a 16-byte boundary)
+ */
+#ifndef SIMGAN_B200_H
+#define SIMGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_OK 0
+#define SG_ERR_INVALID 1
+#define SG_ERR_CUDA 2
+#define SG_ERR_WORKSPACE 3
+
+const char* sg_last_error(void);
+int sg_version(void);
+/* SM count / cooperative-launch capability of the current device (0 if no device). */
+int sg_device_sm_count(void);
+
+/* ---- flat parameter layouts ---------------------------------------------------------------- */
+/* Policy(MLPBase)+DiagGaussian, 13 segments in nn.Module.parameters() order
+ * (A2C/model.py:243-251, A2C/distributions.py:98-104):
+ *   0 actor.0.weight (H,O)  1 actor.0.bias (H)  2 actor.2.weight (H,H)  3 actor.2.bias (H)
+ *   4 critic.0.weight (H,O) 5 critic.0.bias (H) 6 critic.2.weight (H,H) 7 critic.2.bias (H)
+ *   8 critic_linear.weight (1,H) 9 critic_linear.bias (1)
+ *  10 dist.fc_mean.weight (A,H) 11 dist.fc_mean.bias (A) 12 dist.logstd._bias (A,1)
+ * offsets[13] (in floats) receives the segment starts; returns the padded total length. */
+#define SG_POLICY_SEGMENTS 13
+int sg_policy_layout(int obs_dim, int hidden, int act_dim, int* offsets);
+/* Discriminator trunk, 6 segments (A2C/algo/gail.py:40-43):
+ *   0 trunk.0.weight (Hd,F) 1 trunk.0.bias (Hd) 2 trunk.2.weight (Hd,Hd) 3 trunk.2.bias (Hd)
+ *   4 trunk.4.weight (1,Hd) 5 trunk.4.bias (1) */
+#define SG_DISC_SEGMENTS 6
+int sg_disc_layout(int feat_dim, int hidden, int* offsets);
+
+/* ---- rollout buffer ------------------------------------------------------------------------ */
+/* RolloutStorage.compute_returns, all four branches (A2C/storage.py:103-142).
+ * rewards (T,N,1); value_preds/returns/masks/bad_masks (T+1,N,1); next_value (N,1).
+ * GAE branches write value_preds[T] = next_value; the others write returns[T] = next_value.
+ * gamma / gae_lambda are doubles because the reference forms gamma*gae_lambda in Python double
+ * before narrowing to fp32.  Bit-exact with the reference's fp32 op order. */
+int sg_compute_returns(const float* rewards, float* value_preds, const float* masks, const float* bad_masks,
+                       float* returns, const float* next_value, int T, int N, double gamma, double gae_lambda,
+                       int use_gae, int use_proper_time_limits, void* stream);
+
+/* mean and UNBIASED std of (returns - value_preds)[:S] (A2C/algo/ppo.py:66-68).
+ * out_stats: 2 floats {mean, std}. workspace: sg_adv_stats_workspace_bytes(S) bytes. */
+int64_t sg_adv_stats_workspace_bytes(int S);
+int sg_adv_stats(const float* returns, const float* value_preds, int S, float* out_stats, void* workspace,
+                 void* stream);
+
+/* Row gathers of RolloutStorage.feed_forward_generator (A2C/storage.py:169-185): for each of
+ * n_tensors sources, dst[i][j,:] = src[i][idx[j],:] with row width dims[i].  idx is int64 (the
+ * reference's sampler indices), h_src/h_dst/h_dims are HOST arrays of length n_tensors. */
+int sg_gather_rows(const float* const* h_src, float* const* h_dst, const int* h_dims, int n_tensors,
+                   const int64_t* idx, int n_rows, void* stream);
+
+/* RolloutStorage.insert (A2C/storage.py:70-84): nine row-block copies in one launch.
+ * h_src/h_dst/h_count: HOST arrays (n_copies) of device pointers and float counts. */
+int sg_copy_blocks(const float* const* h_src, float* const* h_dst, const int* h_count, int n_copies, void* stream);
+
+/* ---- actor-critic -------------------------------------------------------------------------- */
+/* Policy.act / get_value / evaluate_actions forward (A2C/model.py:89-114).
+ * params: flat policy vector.  obs (B,O).  noise (B,A) standard normal or NULL (deterministic /
+ * evaluate).  actions_in (B,A) or NULL: when given, log-probs are evaluated for it (evaluate_actions)
+ * instead of the sampled action.  Outputs (any may be NULL): value (B,1), action (B,A), logp (B,1),
+ * entropy (1) = batch-mean entropy. */
+int sg_policy_forward(const float* params, int obs_dim, int hidden, int act_dim, const float* obs, int B,
+                      const float* noise, const float* actions_in, float* value, float* action, float* logp,
+                      float* entropy, void* stream);
+
+/* ---- PPO ----------------------------------------------------------------------------------- */
+typedef struct sg_ppo_config {
+    int obs_dim, hidden, act_dim;
+    int T, N;                 /* rollout dims; S = T*N */
+    int ppo_epoch;            /* epochs in this call */
+    int num_mini_batch;       /* minibatches per epoch */
+    int mini_batch_size;      /* rows per minibatch (S / num_mini_batch) */
+    double clip_param, value_loss_coef, entropy_coef, max_grad_norm;   /* Python floats of PPO.__init__ */
+    double beta1, beta2, adam_eps;
+    int use_clipped_value_loss;
+    int first_adam_step;      /* Adam step count of the first minibatch in this call (1-based) */
+    int row_begin, row_end;   /* data-parallel shard: rows [row_begin,row_end) of every minibatch are
+                                 processed locally (0, mini_batch_size on a single GPU) */
+    int mode;                 /* 0 = one persistent cooperative kernel, 1 = one launch per phase */
+} sg_ppo_config;
+
+int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg);
+
+/* PPO.update (A2C/algo/ppo.py:65-157) for cfg->ppo_epoch epochs.
+ *   params/adam_m/adam_v : flat policy vectors (updated in place)
+ *   obs (T+1,N,O), actions (T,N,A), value_preds (T+1,N,1), returns (T+1,N,1), old_logp (T,N,1)
+ *   adv_stats {mean,std} from sg_adv_stats
+ *   perm  int32 (ppo_epoch, S): the reference sampler's torch.randperm(S) per epoch (A2C/storage.py:158-162)
+ *   step_size / bc2_sqrt: device float arrays (n_steps) of Adam lr/(1-beta1^t) and sqrt(1-beta2^t),
+ *     formed on the host in double like torch.optim.Adam does
+ *   trace (n_steps,4) {value_loss, action_loss, entropy, grad_norm} per optimizer step
+ * In mode 1 with allreduce_cb != NULL the callback is invoked on the host between the gradient
+ * reduction and the clip+Adam epilogue of every step with (grad_ptr, n_floats, user) and must
+ * enqueue an in-place sum-allreduce on `stream` (data-parallel minibatch sharding). */
+typedef int (*sg_allreduce_fn)(float* grad, int n_floats, void* user);
+int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float* adam_v, const float* obs,
+                  const float* actions, const float* value_preds, const float* returns, const float* old_logp,
+                  const float* adv_stats, const int32_t* perm, const float* step_size, const float* bc2_sqrt,
+                  float* trace, void* workspace, sg_allreduce_fn allreduce_cb, void* allreduce_user, void* stream);
+
+/* ---- GAIL discriminator -------------------------------------------------------------------- */
+typedef struct sg_disc_config {
+    int feat_dim, hidden;
+    int batch_size;           /* rows per minibatch (gail_batch_size) */
+    int n_steps;              /* zipped minibatches in this call */
+    double gp_lambda;         /* 10.0 (A2C/algo/gail.py:70) */
+    double beta1, beta2, adam_eps;
+    int first_adam_step;
+    int row_begin, row_end;   /* data-parallel shard of every minibatch */
+    int mode;                 /* 0 persistent, 1 launch per phase */
+} sg_disc_config;
+
+int64_t sg_disc_workspace_bytes(const sg_disc_config* cfg);
+
+/* Discriminator.update_gail_dyn (A2C/algo/gail.py:154-193) for cfg->n_steps minibatches.
+ *   expert (N_exp,F) expert rows; policy_feat = obs_feat[1:] viewed (S,F)
+ *   expert_idx / policy_idx int32 (n_steps, batch): DataLoader / sampler index streams
+ *   alpha (n_steps, batch): the torch.rand(B,1) mixup draws (gail.py:72)
+ *   trace (n_steps,3) {total loss, expert loss, policy loss} */
+int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, float* adam_v, const float* expert,
+                   const float* policy_feat, const int32_t* expert_idx, const int32_t* policy_idx,
+                   const float* alpha, const float* step_size, const float* bc2_sqrt, float* trace,
+                   void* workspace, sg_allreduce_fn allreduce_cb, void* allreduce_user, void* stream);
+
+/* Discriminator.predict_reward_combined (A2C/algo/gail.py:201-210) for one (N,F) block:
+ * reward = log(s+1e-7)-log(1-s+1e-7)+offset; returns = has_returns ? returns*gamma*masks+reward : reward. */
+int sg_disc_predict_reward(const float* params, int feat_dim, int hidden, const float* d_in, int n_rows,
+                           double gamma, const float* masks, double offset, int has_returns, float* reward,
+                           float* returns, void* stream);
+
+/* Whole-rollout reward relabel = the T-step loop of A2C/main_gail_dyn_ppo.py:275-297 with the
+ * RunningMeanStd update (A2C/baselines/common/running_mean_std.py:33-56) kept on the device.
+ *   obs_feat (T+1,N,F), masks (T+1,N,1), rewards (T,N,1) out
+ *   disc_returns (N): the discriminator's persistent running return (in/out); has_returns as above
+ *   rms_state: 3 doubles {mean, var, count} (in/out)
+ *   mean_returns (T): per-step torch.mean(returns) (the caller's gail_rewards deque)
+ *   workspace: sg_relabel_workspace_bytes(T,N) */
+int64_t sg_relabel_workspace_bytes(int T, int N);
+int sg_disc_relabel(const float* params, int feat_dim, int hidden, const float* obs_feat, const float* masks,
+                    float* rewards, int T, int N, double gamma, double offset, float* disc_returns, int has_returns,
+                    double* rms_state, float* mean_returns, void* workspace, void* stream);
+
+/* The device-resident tail of the relabel alone (steps after the discriminator forward): running
+ * return scan, numpy-order float32 batch moments, float64 RunningMeanStd merge, normalise + clip.
+ * raw_reward (T,N) is what predict_reward_combined returns as `reward`.  Bit-exact with the reference. */
+int sg_relabel_normalize(const float* raw_reward, const float* masks, float* rewards, int T, int N, double gamma,
+                         float* disc_returns, int has_returns, double* rms_state, float* mean_returns, void* workspace,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMGAN_B200_H */

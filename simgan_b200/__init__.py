@@ -1,0 +1,14 @@
+"""simgan_b200 -- B200-native PPO+GAIL inner loop behind the reference's Python surface.
+
+Classes mirror third_party/a2c_ppo_acktr of jyf588/SimGAN (Policy, PPO, gail.Discriminator,
+RolloutStorage); the minibatch math runs in hand-written sm_100a kernels behind the C ABI declared
+in include/simgan_b200.h (loaded by simgan_b200._lib).
+"""
+from .model import Policy, MLPBase  # noqa: F401
+from .storage import RolloutStorage  # noqa: F401
+from .running_mean_std import RunningMeanStd  # noqa: F401
+from . import algo  # noqa: F401
+from .algo import PPO  # noqa: F401
+from .algo.gail import Discriminator  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,291 @@
+"""GAIL discriminator with the reference's surface (third_party/a2c_ppo_acktr/algo/gail.py:34-217).
+
+``update_gail_dyn`` / ``predict_reward_combined`` keep their signatures and return types; the
+minibatch loop (gather expert + policy rows, three trunk forwards, two BCE-with-logits terms, the
+gradient penalty with a hand-derived double backward, Adam) runs in the sm_100a kernel behind
+``sg_disc_update``.  Index streams and the mixup alphas are drawn on the host from the CPU default
+generator in exactly the order ``zip(DataLoader, feed_forward_generator)`` consumes it
+(SURVEY.md section 8g-2), then shipped to the device once per epoch.
+
+``relabel_rollout`` is the whole-rollout form of the caller's T-step relabel loop
+(main_gail_dyn_ppo.py:275-297): one device pass instead of T launches with three host syncs each.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..running_mean_std import RunningMeanStd
+from .adam import FusedAdam
+
+
+class Discriminator(nn.Module):
+    def __init__(self, input_dim, hidden_dim, device):
+        super().__init__()
+        self.device = device
+        # default nn.Linear init, three layers in this order (gail.py:40-43)
+        self.trunk = nn.Sequential(nn.Linear(input_dim, hidden_dim), nn.Tanh(),
+                                   nn.Linear(hidden_dim, hidden_dim), nn.Tanh(),
+                                   nn.Linear(hidden_dim, 1)).to(device)
+        self.trunk.train()
+        self.optimizer = FusedAdam(self.trunk.parameters())       # Adam defaults lr 1e-3, eps 1e-8 (gail.py:48)
+        self.returns = None
+        self.ret_rms = RunningMeanStd(shape=())
+        self.kernel_mode = 0
+        self.dp = None
+        self.last_trace = None
+        self.__dict__["_ws"] = None
+
+    # ---- flat parameter buffer ---------------------------------------------------------------------------
+    @property
+    def feat_dim(self):
+        return self.trunk[0].in_features
+
+    @property
+    def hidden_dim(self):
+        return self.trunk[0].out_features
+
+    def hot_path_parameters(self):
+        t = self.trunk
+        return [t[0].weight, t[0].bias, t[2].weight, t[2].bias, t[4].weight, t[4].bias]
+
+    def flat_params(self):
+        ps = self.hot_path_parameters()
+        dev = ps[0].device
+        if dev.type != "cuda":
+            raise _lib.SgError("the GAIL discriminator hot path needs a CUDA device (got %s); no CPU fallback" % dev)
+        offs, total = _lib.disc_layout(self.feat_dim, self.hidden_dim)
+        flat = self.__dict__.get("_flat")
+        bound = (flat is not None and flat.device == dev and flat.numel() == total and
+                 all(p.dtype == torch.float32 and p.is_contiguous() and p.data_ptr() == flat.data_ptr() + 4 * o
+                     for p, o in zip(ps, offs)))
+        if not bound:
+            flat = torch.zeros(total, device=dev, dtype=torch.float32)
+            for p, o in zip(ps, offs):
+                n = p.numel()
+                flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = flat[o:o + n].view(p.shape)
+            self.__dict__["_flat"] = flat
+        return flat
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state.pop("_flat", None)
+        state["_ws"] = None
+        return state
+
+    # ---- update --------------------------------------------------------------------------------------------
+    @staticmethod
+    def draw_epoch_indices(n_expert, batch_size, drop_last, n_rollout):
+        """Host RNG emulation of one ``zip(expert_loader, feed_forward_generator)`` pass.
+
+        Order of CPU-default-generator draws (torch 2.x): DataLoader base seed (one int64 random_()),
+        RandomSampler seed (one int64 random_()), expert permutation on a PRIVATE generator, the rollout
+        sampler's randperm(S), then one rand(B,1) per zipped minibatch (gail.py:72).
+        Returns (expert_idx (n,B) int64, policy_idx (n,B) int64, alpha (n,B) fp32)."""
+        torch.empty((), dtype=torch.int64).random_()
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        gen = torch.Generator()
+        gen.manual_seed(seed)
+        e_perm = torch.randperm(n_expert, generator=gen)
+        n_e = n_expert // batch_size
+        if not drop_last and n_expert % batch_size:
+            raise NotImplementedError(
+                "expert set of %d rows with gail_batch_size=%d and drop_last=False yields a ragged expert batch that "
+                "the reference's mixup pairs with a full policy batch (SURVEY.md section 8g-1); not a runnable "
+                "configuration" % (n_expert, batch_size))
+        if n_e == 0:
+            raise ZeroDivisionError("no full expert minibatch (gail.py:193 divides by n=0)")
+        p_perm = torch.randperm(n_rollout)
+        n = min(n_e, n_rollout // batch_size)
+        if n == 0:
+            raise ZeroDivisionError("rollout smaller than gail_batch_size (gail.py:193 divides by n=0)")
+        alpha = torch.rand(n * batch_size)          # == n consecutive torch.rand(B,1) draws (tests pin this)
+        return (e_perm[:n * batch_size].view(n, batch_size), p_perm[:n * batch_size].view(n, batch_size),
+                alpha.view(n, batch_size))
+
+    def _run_update(self, expert, policy_feat, e_idx, p_idx, alpha):
+        flat = self.flat_params()
+        dev = flat.device
+        n, B = e_idx.shape
+        opt = self.optimizer
+        m, v = opt.ensure_state(flat)
+        g = opt.param_groups[0]
+        cfg = _lib.DiscConfig()
+        cfg.feat_dim, cfg.hidden, cfg.batch_size, cfg.n_steps = self.feat_dim, self.hidden_dim, B, n
+        cfg.gp_lambda = 10.0
+        cfg.beta1, cfg.beta2, cfg.adam_eps = g["betas"][0], g["betas"][1], g["eps"]
+        cfg.first_adam_step = opt.step_count + 1
+        cfg.row_begin, cfg.row_end = (0, B) if self.dp is None else self.dp.shard(B)
+        cfg.mode = self.kernel_mode if self.dp is None else 1
+        lib = _lib.lib()
+        need = lib.sg_disc_workspace_bytes(C.byref(cfg))
+        if need < 0:
+            _lib.check(1, "sg_disc_workspace_bytes")
+        ws = self.__dict__.get("_ws")
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+            self.__dict__["_ws"] = ws
+        # one pinned staging block: [expert_idx | policy_idx] int32 and alpha fp32
+        stage_i = torch.empty(2, n, B, dtype=torch.int32).pin_memory()
+        stage_i[0].copy_(e_idx)
+        stage_i[1].copy_(p_idx)
+        idx_dev = stage_i.to(dev, non_blocking=True)
+        alpha_dev = alpha.contiguous().pin_memory().to(dev, non_blocking=True)
+        sched = torch.from_numpy(opt.schedule(n)).to(dev)
+        trace = torch.empty(n, 3, device=dev)
+        cb, user = _lib.NULL_ALLREDUCE, None
+        if self.dp is not None:
+            cb = self.dp.make_callback(ws)
+        rc = lib.sg_disc_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(expert),
+                                _lib.ptr(policy_feat), _lib.ptr(idx_dev[0]), _lib.ptr(idx_dev[1]), _lib.ptr(alpha_dev),
+                                _lib.ptr(sched[0]), _lib.ptr(sched[1]), _lib.ptr(trace), _lib.ptr(ws), cb, user,
+                                _lib.current_stream())
+        _lib.check(rc, "sg_disc_update")
+        opt.step_count += n
+        tr = trace.cpu()
+        if not bool(torch.isfinite(tr).all()):
+            raise _lib.SgError("sg_disc_update produced non-finite losses (grid barrier timeout or diverged update)")
+        self.last_trace = tr
+        lt = le = lp = 0.0
+        for row in tr.tolist():
+            lt += row[0]
+            le += row[1]
+            lp += row[2]
+        return lt / n, le / n, lp / n
+
+    def update_gail_dyn(self, expert_loader, rollouts, replay=None):
+        """gail.py:154-193.  ``expert_loader`` is the caller's DataLoader over TensorDataset(expert (N_exp,F))
+        (main_gail_dyn_ppo.py:165-175); its dataset tensor is used in place on the device and its
+        batch_size / drop_last drive the index emulation.  ``replay`` = (expert_idx, policy_idx, alpha)
+        bypasses the generator (parity tests)."""
+        self.train()
+        expert = expert_loader.dataset.tensors[0]
+        if not expert.is_cuda or not rollouts.obs_feat.is_cuda:
+            raise _lib.SgError("update_gail_dyn needs the expert set and the rollout buffer on the CUDA device")
+        expert = expert if (expert.dtype == torch.float32 and expert.is_contiguous()) else expert.float().contiguous()
+        T, N = rollouts.rewards.shape[:2]
+        S = T * N
+        F = rollouts.obs_feat.shape[-1]
+        assert expert.shape[1] == F == self.feat_dim
+        policy_feat = rollouts.obs_feat[1:].reshape(S, F)       # next_obs_feat rows (storage.py:172, gail.py:166)
+        if replay is None:
+            e_idx, p_idx, alpha = self.draw_epoch_indices(expert.shape[0], expert_loader.batch_size,
+                                                          bool(expert_loader.drop_last), S)
+        else:
+            e_idx, p_idx, alpha = [torch.as_tensor(x) for x in replay]
+        return self._run_update(expert, policy_feat, e_idx, p_idx, alpha)
+
+    def update(self, expert_loader, rollouts, obsfilt=None, is_gail_dyn=False, a_dim=None):
+        """Legacy (state, action)-split variant (gail.py:91-152): the D input is cat([state, action]) on
+        both sides, so it maps onto the same kernel over concatenated row matrices."""
+        if obsfilt is not None:
+            raise NotImplementedError("obsfilt (VecNormalize observation filter) is not used by the GAIL-dyn path")
+        self.train()
+        es, ea = expert_loader.dataset.tensors[:2]
+        expert = torch.cat([es, ea], dim=1).float().contiguous()
+        T, N = rollouts.rewards.shape[:2]
+        S = T * N
+        fr = rollouts.flat_rows()
+        if not is_gail_dyn:
+            policy_feat = torch.cat([fr["obs"], fr["actions"]], dim=1).contiguous()
+        else:
+            policy_feat = torch.cat([fr["obs_feat"], fr["obs"][:, -a_dim:], fr["next_obs_feat"]], dim=1).contiguous()
+        assert expert.shape[1] == policy_feat.shape[1] == self.feat_dim
+        e_idx, p_idx, alpha = self.draw_epoch_indices(expert.shape[0], expert_loader.batch_size,
+                                                      bool(expert_loader.drop_last), S)
+        return self._run_update(expert, policy_feat, e_idx, p_idx, alpha)
+
+    # ---- differentiable penalty (API completeness; the update kernels derive it by hand) -------------------
+    def compute_grad_pen_combined(self, expert_combined, policy_combined, lambda_=10.):
+        alpha = torch.rand(expert_combined.size(0), 1).expand_as(expert_combined).to(expert_combined.device)
+        mix = (alpha * expert_combined + (1 - alpha) * policy_combined).detach().requires_grad_(True)
+        out = self.trunk(mix)
+        (grad,) = torch.autograd.grad(out, mix, torch.ones_like(out), create_graph=True, retain_graph=True)
+        return lambda_ * (grad.norm(2, dim=1) - 1).pow(2).mean()
+
+    def compute_grad_pen(self, expert_state, expert_action, policy_state, policy_action, lambda_=10.):
+        return self.compute_grad_pen_combined(torch.cat([expert_state, expert_action], dim=1),
+                                              torch.cat([policy_state, policy_action], dim=1), lambda_)
+
+    # ---- rewards ---------------------------------------------------------------------------------------------
+    def predict_reward_combined(self, d_in, gamma, masks, offset=0.0):
+        """gail.py:201-210: (reward (N,1), running returns (N,1)); ``self.returns`` persists across calls."""
+        flat = self.flat_params()
+        x = d_in.detach()
+        if not x.is_cuda:
+            raise _lib.SgError("predict_reward_combined needs CUDA tensors")
+        if x.dtype != torch.float32 or not x.is_contiguous():
+            x = x.float().contiguous()
+        n = x.shape[0]
+        reward = torch.empty(n, 1, device=x.device)
+        has = self.returns is not None
+        if not has:
+            self.returns = torch.empty(n, 1, device=x.device)
+        else:
+            self.returns = self.returns.clone()     # the reference rebinds a fresh tensor each call
+        mk = masks.detach().float().contiguous()
+        rc = _lib.lib().sg_disc_predict_reward(_lib.ptr(flat), self.feat_dim, self.hidden_dim, _lib.ptr(x), n,
+                                               float(gamma), _lib.ptr(mk), float(offset), int(has), _lib.ptr(reward),
+                                               _lib.ptr(self.returns), _lib.current_stream())
+        _lib.check(rc, "sg_disc_predict_reward")
+        return reward, self.returns
+
+    def predict_reward(self, state, action, gamma, masks, offset=0.0):
+        self.eval()
+        return self.predict_reward_combined(torch.cat([state, action], dim=1), gamma, masks, offset)
+
+    def predict_prob_single_step(self, state, action):
+        with torch.no_grad():
+            self.eval()
+            return torch.sigmoid(self.trunk(torch.cat([state, action], dim=1)))
+
+    def relabel_rollout(self, rollouts, gamma, offset, ret_rms, sync=True):
+        """The caller's whole relabel loop (main_gail_dyn_ppo.py:275-297) in one device pass:
+        for every step t, reward_t = predict_reward_combined(obs_feat[t+1], gamma, masks[t], offset),
+        ret_rms.update(returns_t), rewards[t] = clip(reward_t / sqrt(ret_rms.var + 1e-7), +-10).
+        Updates ``rollouts.rewards``, ``self.returns`` and (when ``sync``) ``ret_rms`` in place and returns the
+        (T,) device tensor of per-step mean(returns) -- what the caller appends to ``gail_rewards``."""
+        flat = self.flat_params()
+        if not rollouts.obs_feat.is_cuda:
+            raise _lib.SgError("relabel_rollout needs the rollout buffer on the CUDA device")
+        dev = flat.device
+        T, N = rollouts.rewards.shape[:2]
+        has = self.returns is not None
+        if not has:
+            self.returns = torch.zeros(N, 1, device=dev)
+        lib = _lib.lib()
+        ws = torch.empty(int(lib.sg_relabel_workspace_bytes(T, N)), dtype=torch.uint8, device=dev)
+        rms_dev = torch.tensor([float(ret_rms.mean), float(ret_rms.var), float(ret_rms.count)], dtype=torch.float64,
+                               device=dev)
+        mean_returns = torch.empty(T, device=dev)
+        rc = lib.sg_disc_relabel(_lib.ptr(flat), self.feat_dim, self.hidden_dim, _lib.ptr(rollouts.obs_feat),
+                                 _lib.ptr(rollouts.masks), _lib.ptr(rollouts.rewards), T, N, float(gamma), float(offset),
+                                 _lib.ptr(self.returns), int(has), _lib.ptr(rms_dev), _lib.ptr(mean_returns),
+                                 _lib.ptr(ws), _lib.current_stream())
+        _lib.check(rc, "sg_disc_relabel")
+        self.__dict__["_rms_dev"] = rms_dev
+        if sync:
+            self.sync_rms(ret_rms)
+        return mean_returns
+
+    def sync_rms(self, ret_rms):
+        """Copy the device-side running statistics of the last relabel back into the host object."""
+        st = self.__dict__.get("_rms_dev")
+        if st is not None:
+            mean, var, count = st.cpu().tolist()
+            ret_rms.mean = np.array(mean, dtype=np.float64)
+            ret_rms.var = np.array(var, dtype=np.float64)
+            ret_rms.count = count
+
+
+def alive_bonus_offset(masks, num_steps, num_processes, gail_tar_length, no_alive_bonus=False):
+    """r_sa of main_gail_dyn_ppo.py:258-271; the relabel is called with offset=-r_sa."""
+    if no_alive_bonus:
+        return 0.0
+    n_done = (1.0 - masks).sum().cpu().numpy() + num_processes / 2
+    n_expert_done = (num_steps * num_processes) / gail_tar_length
+    d_sa = 1 - n_done / (n_done + n_expert_done)
+    return float(np.log(d_sa) - np.log(1 - d_sa))

@@ -1,0 +1,133 @@
+"""PPO with the reference's surface (third_party/a2c_ppo_acktr/algo/ppo.py:29-157).
+
+``update(rollouts)`` keeps the reference's contract -- same constructor, three Python floats back,
+``optimizer.param_groups[i]['lr']`` honoured at every call, sampler indices drawn from the CPU default
+generator in the reference's order -- but the whole ``ppo_epoch x num_mini_batch`` loop (gather ->
+actor/critic forward -> Gaussian log-prob -> clipped surrogate + clipped value loss -> backward ->
+global-norm clip -> Adam) runs inside the sm_100a kernel behind ``sg_ppo_update``; the three
+``.item()`` syncs per minibatch of the reference (ppo.py:147-149) become one device->host read of a
+per-step trace at the end.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .adam import FusedAdam
+
+
+class PPO(object):
+    def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
+                 symmetry_coef=0, lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True,
+                 mirror_obs=None, mirror_act=None):
+        if mirror_obs and symmetry_coef > 0:
+            raise NotImplementedError("the symmetry-loss branch (ppo.py:111-136) is outside the hot path "
+                                      "(--loss-sym defaults to 0)")
+        self.actor_critic = actor_critic
+        self.clip_param = clip_param
+        self.ppo_epoch = ppo_epoch
+        self.num_mini_batch = num_mini_batch
+        self.value_loss_coef = value_loss_coef
+        self.entropy_coef = entropy_coef
+        self.max_grad_norm = max_grad_norm
+        self.use_clipped_value_loss = use_clipped_value_loss
+        self.optimizer = FusedAdam(actor_critic.parameters(), lr=lr, eps=eps)
+        self.symmetry_coef = symmetry_coef
+        self.mirror_obs = mirror_obs
+        self.mirror_act = mirror_act
+        self.is_cuda = next(actor_critic.parameters()).is_cuda
+        self.kernel_mode = 0            # 0: persistent cooperative kernel, 1: one launch per phase
+        self.dp = None                  # simgan_b200.dist.DataParallel or None
+        self.last_trace = None          # (n_steps, 4) {value_loss, action_loss, entropy, grad_norm}
+        self._ws = None
+        self._stage = None
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _workspace(self, cfg, dev):
+        need = _lib.lib().sg_ppo_workspace_bytes(C.byref(cfg))
+        if need < 0:
+            _lib.check(1, "sg_ppo_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def draw_permutations(self, S):
+        """ppo_epoch x torch.randperm(S) on the CPU default generator -- the sampler stream of
+        feed_forward_generator (storage.py:158-162), one draw per epoch (ppo.py:79-80)."""
+        n = self.ppo_epoch
+        if self._stage is None or self._stage.shape != (n, S):
+            self._stage = torch.empty(n, S, dtype=torch.int32).pin_memory() if torch.cuda.is_available() \
+                else torch.empty(n, S, dtype=torch.int32)
+        for e in range(n):
+            self._stage[e].copy_(torch.randperm(S))
+        return self._stage
+
+    def update(self, rollouts, permutations=None):
+        """PPO.update (ppo.py:65-157).  ``permutations`` (ppo_epoch, S) overrides the sampler draw (used by
+        parity tests to replay a recorded index stream)."""
+        ac = self.actor_critic
+        flat = ac.flat_params()
+        dev = flat.device
+        if not rollouts.rewards.is_cuda:
+            raise _lib.SgError("PPO.update needs the rollout buffer on the policy's CUDA device")
+        T, N = rollouts.rewards.shape[:2]
+        S = T * N
+        assert S >= self.num_mini_batch, (
+            "PPO requires the number of processes ({}) * number of steps ({}) = {} to be greater than or equal to "
+            "the number of PPO mini batches ({}).".format(N, T, S, self.num_mini_batch))
+        mbs = S // self.num_mini_batch
+        n_steps = self.ppo_epoch * self.num_mini_batch
+        opt = self.optimizer
+        m, v = opt.ensure_state(flat)
+        g = opt.param_groups[0]
+
+        cfg = _lib.PpoConfig()
+        cfg.obs_dim, cfg.hidden, cfg.act_dim = ac.obs_dim, ac.hidden_size, ac.act_dim
+        cfg.T, cfg.N = T, N
+        cfg.ppo_epoch, cfg.num_mini_batch, cfg.mini_batch_size = self.ppo_epoch, self.num_mini_batch, mbs
+        cfg.clip_param, cfg.value_loss_coef, cfg.entropy_coef = self.clip_param, self.value_loss_coef, self.entropy_coef
+        cfg.max_grad_norm = self.max_grad_norm
+        cfg.beta1, cfg.beta2, cfg.adam_eps = g["betas"][0], g["betas"][1], g["eps"]
+        cfg.use_clipped_value_loss = int(bool(self.use_clipped_value_loss))
+        cfg.first_adam_step = opt.step_count + 1
+        cfg.row_begin, cfg.row_end = (0, mbs) if self.dp is None else self.dp.shard(mbs)
+        cfg.mode = self.kernel_mode if self.dp is None else 1
+
+        lib = _lib.lib()
+        stream = _lib.current_stream()
+        ws = self._workspace(cfg, dev)
+        # advantage statistics (ppo.py:66-68); the normalisation itself is fused into the tile phase
+        stats = torch.empty(2, device=dev)
+        stat_ws = torch.empty(int(lib.sg_adv_stats_workspace_bytes(S)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.sg_adv_stats(_lib.ptr(rollouts.returns), _lib.ptr(rollouts.value_preds), S, _lib.ptr(stats),
+                                    _lib.ptr(stat_ws), stream), "sg_adv_stats")
+        # sampler index stream + Adam scalars -> device
+        if permutations is None:
+            perm_host = self.draw_permutations(S)
+        else:
+            perm_host = torch.as_tensor(permutations).to(torch.int32).reshape(self.ppo_epoch, S)
+        perm = perm_host.to(dev, non_blocking=True)
+        sched = torch.from_numpy(opt.schedule(n_steps)).to(dev)
+        trace = torch.empty(n_steps, 4, device=dev)
+
+        cb, user = _lib.NULL_ALLREDUCE, None
+        if self.dp is not None:
+            cb = self.dp.make_callback(ws)
+        rc = lib.sg_ppo_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
+                               _lib.ptr(rollouts.actions), _lib.ptr(rollouts.value_preds), _lib.ptr(rollouts.returns),
+                               _lib.ptr(rollouts.action_log_probs), _lib.ptr(stats), _lib.ptr(perm),
+                               _lib.ptr(sched[0]), _lib.ptr(sched[1]), _lib.ptr(trace), _lib.ptr(ws), cb, user, stream)
+        _lib.check(rc, "sg_ppo_update")
+        opt.step_count += n_steps
+
+        tr = trace.cpu()            # the one host sync of the update
+        if not bool(torch.isfinite(tr).all()):
+            raise _lib.SgError("sg_ppo_update produced non-finite losses (grid barrier timeout or diverged update)")
+        self.last_trace = tr
+        vl = al = ent = 0.0
+        for row in tr.tolist():     # Python-double running sums, like the reference's += .item()
+            vl += row[0]
+            al += row[1]
+            ent += row[2]
+        return vl / n_steps, al / n_steps, ent / n_steps

@@ -1,0 +1,365 @@
+// Shared device primitives for the simgan_b200 kernels (sm_100a).
+//
+// The per-minibatch math of the reference is a chain of small dense contractions over a tile of R
+// minibatch rows owned by one CTA (R = 8): X(R,K)·W(N,K)^T, dY(R,N)·W(N,K) and dY^T·X.  At the
+// reference's sizes (hidden 64..256, 1024 rows per minibatch spread over 128 CTAs) these are
+// latency-bound register-tile FMA problems, not tensor-core tiles; see DESIGN.md "Kernels".
+//
+// Layout conventions inside a CTA tile:
+//   forward activations   row-major   A[r*ld + k]      (ld multiple of 4, zero padded)
+//   backward deltas       transposed  D[n*R + r]       (all R rows of one unit contiguous)
+// Weights are nn.Linear (out,in) row-major in global memory and are read with ld.global.cg: they are
+// rewritten by the Adam phase between optimizer steps of the same persistent kernel, so the
+// non-coherent (.nc / L1) path must not be used.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/simgan_b200.h"
+
+namespace sg {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+#define SG_CUDA(call)                                      \
+    do {                                                   \
+        int _rc = ::sg::check_cuda((call), #call);         \
+        if (_rc) return _rc;                               \
+    } while (0)
+
+#define SG_REQUIRE(cond, ...)                              \
+    do {                                                   \
+        if (!(cond)) {                                     \
+            ::sg::set_error(__VA_ARGS__);                  \
+            return SG_ERR_INVALID;                         \
+        }                                                  \
+    } while (0)
+
+constexpr int kStepThreads = 256;   // threads per CTA of the step kernels
+constexpr int kHalf = 128;          // actor / critic halves
+constexpr int kRows = 8;            // minibatch rows per CTA tile
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OUT(r,n) = sum_k X[r*ldx+k] * W[n*K+k]          (epilogue adds bias / activation and stores)
+//   `nth` threads (local id t, nth % 32 == 0) cooperate; EVERY thread of the participating warps
+//   must call (warp shuffles).  8 lanes split K (stride 8*V), each lane carries 4 outputs x R rows;
+//   a butterfly reduce-scatter leaves every lane with one output and R/2 rows.
+//   V = 4 needs K % 4 == 0 and 16-byte aligned W rows; V = 1 handles any K.
+// ------------------------------------------------------------------------------------------------
+template <int R, int V, class Epi>
+__device__ __forceinline__ void gemm_xwT(const float* __restrict__ W, const float* __restrict__ X, int ldx,
+                                         int N, int K, int t, int nth, Epi epi) {
+    static_assert(R % 2 == 0, "R must be even");
+    constexpr int KS = 8, NT = 4;
+    const int kq = t & (KS - 1);
+    const int grp = t >> 3;
+    const int ngrp = nth >> 3;
+    for (int base = 0; base < N; base += ngrp * NT) {
+        const int n0 = base + grp * NT;
+        float acc[NT][R];
+#pragma unroll
+        for (int i = 0; i < NT; ++i)
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[i][r] = 0.f;
+        if (n0 < N) {
+            for (int k = kq * V; k < K; k += KS * V) {
+                float w[NT][V];
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    if (n0 + i < N) {
+                        if (V == 4) {
+                            float4 q = ld_cg4(W + (size_t)(n0 + i) * K + k);
+                            w[i][0] = q.x; w[i][1 % V] = q.y; w[i][2 % V] = q.z; w[i][3 % V] = q.w;
+                        } else {
+                            w[i][0] = ld_cg(W + (size_t)(n0 + i) * K + k);
+                        }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) w[i][v] = 0.f;
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float x[V];
+                    if (V == 4) {
+                        float4 q = *reinterpret_cast<const float4*>(X + r * ldx + k);
+                        x[0] = q.x; x[1 % V] = q.y; x[2 % V] = q.z; x[3 % V] = q.w;
+                    } else {
+                        x[0] = X[r * ldx + k];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NT; ++i)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) acc[i][r] = fmaf(w[i][v], x[v], acc[i][r]);
+                }
+            }
+        }
+        // reduce-scatter over the 8 K-split lanes
+        const bool up4 = (kq & 4) != 0, up2 = (kq & 2) != 0, up1 = (kq & 1) != 0;
+        float a2[2][R];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float send = up4 ? acc[j][r] : acc[j + 2][r];
+                float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+                a2[j][r] = (up4 ? acc[j + 2][r] : acc[j][r]) + recv;
+            }
+        float a1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float send = up2 ? a2[0][r] : a2[1][r];
+            float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            a1[r] = (up2 ? a2[1][r] : a2[0][r]) + recv;
+        }
+        float a0[R / 2];
+#pragma unroll
+        for (int r = 0; r < R / 2; ++r) {
+            float send = up1 ? a1[r] : a1[r + R / 2];
+            float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            a0[r] = (up1 ? a1[r + R / 2] : a1[r]) + recv;
+        }
+        const int n = n0 + (up4 ? 2 : 0) + (up2 ? 1 : 0);
+        if (n < N) {
+#pragma unroll
+            for (int r = 0; r < R / 2; ++r) epi(r + (up1 ? R / 2 : 0), n, a0[r]);
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void load_rows_t(const float* __restrict__ Yt, int n, float (&y)[R]) {
+    if (R % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < R / 4; ++q) {
+            float4 v = *reinterpret_cast<const float4*>(Yt + (size_t)n * R + 4 * q);
+            y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) y[r] = Yt[(size_t)n * R + r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// OUT(r,k) = sum_n Yt[n*R+r] * W[n*K+k]           (back-propagation through a Linear layer)
+//   Threads are laid out (k-chunk, n-slice); partial sums go through `scratch`
+//   (>= nth*R*V floats of shared memory) and are reduced after a CTA-wide barrier.
+//   ALL threads of the CTA must call (contains __syncthreads); `sync_after` adds the trailing one.
+// ------------------------------------------------------------------------------------------------
+template <int R, int V, class Epi>
+__device__ __forceinline__ void gemm_yW(const float* __restrict__ W, const float* __restrict__ Yt, int N, int K,
+                                        float* __restrict__ scratch, int t, int nth, Epi epi) {
+    const int KC = (K + V - 1) / V;              // V==4 requires K%4==0
+    const int KCp = KC < nth ? KC : nth;         // chunks handled per sweep
+    const int NS = KC < nth ? nth / KC : 1;      // n-slices
+    const int Nper = (N + NS - 1) / NS;
+    for (int kc0 = 0; kc0 < KC; kc0 += KCp) {
+        const int kc = kc0 + (t % KCp);
+        const int ns = t / KCp;
+        float acc[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[r][v] = 0.f;
+        const bool live = (ns < NS) && (kc < KC);
+        if (live) {
+            const int n_end = min(N, (ns + 1) * Nper);
+            for (int n = ns * Nper; n < n_end; ++n) {
+                float w[V];
+                if (V == 4) {
+                    float4 q = ld_cg4(W + (size_t)n * K + kc * 4);
+                    w[0] = q.x; w[1 % V] = q.y; w[2 % V] = q.z; w[3 % V] = q.w;
+                } else {
+                    w[0] = ld_cg(W + (size_t)n * K + kc);
+                }
+                float y[R];
+                load_rows_t<R>(Yt, n, y);
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+#pragma unroll
+                    for (int v = 0; v < V; ++v) acc[r][v] = fmaf(y[r], w[v], acc[r][v]);
+            }
+            // scratch[(ns*R + r) * (KCp*V) + (kc-kc0)*V + v]
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int v = 0; v < V; ++v) scratch[(size_t)(ns * R + r) * (KCp * V) + (kc - kc0) * V + v] = acc[r][v];
+        }
+        __syncthreads();
+        const int kw = min(KCp * V, K - kc0 * V);  // valid columns of this sweep
+        for (int e = t; e < R * kw; e += nth) {
+            const int r = e / kw, kk = e - r * kw;
+            float s = 0.f;
+            for (int q = 0; q < NS; ++q) s += scratch[(size_t)(q * R + r) * (KCp * V) + kk];
+            epi(r, kc0 * V + kk, s);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G[n*K+k] (+)= sum_r Yt[n*R+r] * X[r*ldx+k]       (per-CTA partial weight gradient -> global)
+// ------------------------------------------------------------------------------------------------
+template <int R, int V>
+__device__ __forceinline__ void outer_store(float* __restrict__ G, const float* __restrict__ Yt,
+                                            const float* __restrict__ X, int ldx, int N, int K, int t, int nth,
+                                            bool acc) {
+    const int KC = (K + V - 1) / V;
+    const int KCp = KC < nth ? KC : nth;
+    const int NS = KC < nth ? nth / KC : 1;
+    const int Nper = (N + NS - 1) / NS;
+    for (int kc0 = 0; kc0 < KC; kc0 += KCp) {
+        const int kc = kc0 + (t % KCp);
+        const int ns = t / KCp;
+        if (ns >= NS || kc >= KC) continue;
+        float xr[R][V];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (V == 4) {
+                float4 q = *reinterpret_cast<const float4*>(X + r * ldx + kc * 4);
+                xr[r][0] = q.x; xr[r][1 % V] = q.y; xr[r][2 % V] = q.z; xr[r][3 % V] = q.w;
+            } else {
+                xr[r][0] = X[r * ldx + kc];
+            }
+        }
+        const int n_end = min(N, (ns + 1) * Nper);
+        for (int n = ns * Nper; n < n_end; ++n) {
+            float y[R];
+            load_rows_t<R>(Yt, n, y);
+            float o[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) o[v] = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int v = 0; v < V; ++v) o[v] = fmaf(y[r], xr[r][v], o[v]);
+            if (V == 4) {
+                float4* gp = reinterpret_cast<float4*>(G + (size_t)n * K + kc * 4);
+                float4 q = make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]);
+                if (acc) { const float4 old = __ldcg(gp); q.x += old.x; q.y += old.y; q.z += old.z; q.w += old.w; }
+                __stcg(gp, q);
+            } else {
+                float* gp = G + (size_t)n * K + kc;
+                __stcg(gp, acc ? o[0] + __ldcg(gp) : o[0]);
+            }
+        }
+    }
+}
+
+// g[n] (+)= sum_{r<rows} Yt[n*R+r]   (bias gradient)
+template <int R>
+__device__ __forceinline__ void rowsum_store(float* __restrict__ g, const float* __restrict__ Yt, int N, int t, int nth,
+                                             bool acc, int rows = R) {
+    for (int n = t; n < N; n += nth) {
+        float y[R];
+        load_rows_t<R>(Yt, n, y);
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += (r < rows) ? y[r] : 0.f;
+        __stcg(g + n, acc ? s + __ldcg(g + n) : s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grid-wide barrier for cooperative (co-resident) launches: monotonically increasing arrival counter.
+// `*counter` must be zero at kernel start.  `gen` is the per-thread-0 generation count.
+// A spin cap turns a lost barrier into an error flag instead of a hung GPU.
+// ------------------------------------------------------------------------------------------------
+struct GridBarrier {
+    unsigned int* counter;
+    unsigned int* error_flag;
+    unsigned int nblocks;
+    unsigned int gen;
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            gen += 1;
+            const unsigned int target = gen * nblocks;
+            __threadfence();
+            atomicAdd(counter, 1u);
+            unsigned int seen;
+            long long spins = 0;
+            // once any barrier has timed out every later one falls through: the kernel drains quickly and
+            // the host sees the poisoned trace
+            bool dead = *(volatile unsigned int*)error_flag != 0u;
+            while (!dead) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+                if (seen >= target) break;
+                if (++spins > (1ll << 22)) { atomicExch(error_flag, 1u); dead = true; }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+};
+
+// flat policy layout (segment starts in floats), mirrored by sg_policy_layout()
+struct PolicyLayout {
+    int aw1, ab1, aw2, ab2, cw1, cb1, cw2, cb2, vw, vb, mw, mb, ls, total;
+};
+__host__ __device__ inline PolicyLayout make_policy_layout(int O, int H, int A) {
+    PolicyLayout L;
+    int o = 0;
+    L.aw1 = o; o += round_up(H * O, 4);
+    L.ab1 = o; o += round_up(H, 4);
+    L.aw2 = o; o += round_up(H * H, 4);
+    L.ab2 = o; o += round_up(H, 4);
+    L.cw1 = o; o += round_up(H * O, 4);
+    L.cb1 = o; o += round_up(H, 4);
+    L.cw2 = o; o += round_up(H * H, 4);
+    L.cb2 = o; o += round_up(H, 4);
+    L.vw = o; o += round_up(H, 4);
+    L.vb = o; o += 4;
+    L.mw = o; o += round_up(A * H, 4);
+    L.mb = o; o += round_up(A, 4);
+    L.ls = o; o += round_up(A, 4);
+    L.total = o;
+    return L;
+}
+struct DiscLayout {
+    int w1, b1, w2, b2, w3, b3, total;
+};
+__host__ __device__ inline DiscLayout make_disc_layout(int F, int H) {
+    DiscLayout L;
+    int o = 0;
+    L.w1 = o; o += round_up(H * F, 4);
+    L.b1 = o; o += round_up(H, 4);
+    L.w2 = o; o += round_up(H * H, 4);
+    L.b2 = o; o += round_up(H, 4);
+    L.w3 = o; o += round_up(H, 4);
+    L.b3 = o; o += 4;
+    L.total = o;
+    return L;
+}
+
+// Adam, in the op order of torch.optim.Adam's single-tensor path (torch/optim/adam.py,
+// called from A2C/algo/ppo.py:145 and A2C/algo/gail.py:188).
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float one_minus_b1, float b2,
+                                            float one_minus_b2, float step_size, float bc2_sqrt, float eps) {
+    m = m + one_minus_b1 * (g - m);                         // exp_avg.lerp_(grad, 1-beta1)
+    v = __fmul_rn(v, b2);                                   // exp_avg_sq.mul_(beta2)
+    v = v + __fmul_rn(__fmul_rn(one_minus_b2, g), g);       //   .addcmul_(grad, grad, value=1-beta2)
+    const float denom = __fdiv_rn(__fsqrt_rn(v), bc2_sqrt) + eps;
+    p = p + __fdiv_rn(__fmul_rn(-step_size, m), denom);     // param.addcdiv_(exp_avg, denom, value=-step_size)
+}
+
+}  // namespace sg

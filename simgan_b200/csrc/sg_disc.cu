@@ -1,0 +1,618 @@
+// GAIL discriminator on the device (A2C/algo/gail.py).
+//
+//   sg_disc_update          update_gail_dyn (gail.py:154-193): BCE-with-logits on expert (label 1) and
+//                           policy (label 0) rows + the WGAN-GP style gradient penalty on mixup rows
+//                           (gail.py:67-89) with a HAND-DERIVED double backward (no autograd in a kernel),
+//                           + Adam.  One persistent cooperative kernel runs all minibatches of an epoch.
+//   sg_disc_predict_reward  predict_reward_combined (gail.py:201-210) for one (N,F) block
+//   sg_disc_relabel         the whole T-step relabel loop of main_gail_dyn_ppo.py:275-297, including the
+//                           float64 RunningMeanStd merge (baselines/common/running_mean_std.py:33-56),
+//                           without a host round trip per step.
+//
+// Gradient-penalty backward.  Forward on x^: z1=W1x^+b1, h1=tanh z1, z2=W2h1+b2,
+// h2=tanh z2, d=w3.h2+b3.  Input gradient: u2=w3*(1-h2^2), v1=W2^T u2, u1=v1*(1-h1^2), g=W1^T u1,
+// n=|g|, penalty=lambda*mean((n-1)^2).  With gbar=(2 lambda/B)(n-1) g/n:
+//   dW1 += u1 gbar^T ;  ub1 = W1 gbar ;  vb1 = ub1*(1-h1^2) ;  hb1 = -2 ub1*v1*h1
+//   dW2 += u2 vb1^T  ;  ub2 = W2 vb1  ;  dw3 += ub2*(1-h2^2) ;  hb2 = -2 ub2*w3*h2 ;  zb2 = hb2*(1-h2^2)
+//   dW2 += zb2 h1^T  ;  db2 += zb2    ;  hb1 += W2^T zb2     ;  zb1 = hb1*(1-h1^2)
+//   dW1 += zb1 x^^T  ;  db1 += zb1
+#include "sg_common.cuh"
+
+namespace sg {
+
+constexpr int kTB = 2;            // (expert, policy, mixup) triples per CTA tile
+constexpr int kDR = 4 * kTB;      // row slots of a tile: [expert | policy | mixup | penalty-pair]
+
+struct DiscArgs {
+    int F, H, P, B, nsteps, row_begin, row_end, ntiles, nslots;
+    float gp_lambda, one_minus_b1, b2, one_minus_b2, eps;
+    DiscLayout L;
+    float *params, *m, *v;
+    const float *expert, *policy, *alpha;
+    const int32_t *eidx, *pidx;
+    const float *step_size, *bc2_sqrt;
+    float* trace;
+    float *gpart, *grad, *losspart;
+    unsigned int* bar;
+};
+
+struct DiscSmem {
+    float *X, *H1, *H2, *D, *DD, *LOSS, *Y2t, *L2t, *L1t, *U1x, *Z2x, *V1, *HB1, *C3, *SCR;
+    int ldf, ldh;
+    __host__ __device__ static int floats(int F, int H) {
+        const int ldf = round_up(F, 4), ldh = round_up(H, 4);
+        return kDR * ldf + 2 * kDR * ldh + 4 * kDR + 3 * kDR * ldh + 2 * kTB * ldh + 3 * kTB * ldh + kStepThreads * kDR * 4;
+    }
+    __device__ void carve(float* sm, int F, int H) {
+        ldf = round_up(F, 4); ldh = round_up(H, 4);
+        X = sm; sm += kDR * ldf;
+        H1 = sm; sm += kDR * ldh;
+        H2 = sm; sm += kDR * ldh;
+        D = sm; sm += kDR;
+        DD = sm; sm += kDR;
+        LOSS = sm; sm += 2 * kDR;
+        Y2t = sm; sm += kDR * ldh;    // [H][kDR]
+        L2t = sm; sm += kDR * ldh;
+        L1t = sm; sm += kDR * ldh;
+        U1x = sm; sm += kTB * ldh;    // [H][kTB]
+        Z2x = sm; sm += kTB * ldh;
+        V1 = sm; sm += kTB * ldh;     // [kTB][ldh]
+        HB1 = sm; sm += kTB * ldh;
+        C3 = sm; sm += kTB * ldh;
+        SCR = sm;
+    }
+};
+
+__device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
+__device__ __forceinline__ float sigmoidf(float z) { return __fdiv_rn(1.f, 1.f + expf(-z)); }
+
+// forward trunk for the rows of X (row-major [R][ldf]) -> H1, H2 (row-major) and logits D
+template <int R>
+__device__ __forceinline__ void disc_tile_forward(const float* __restrict__ params, const DiscLayout& L, int F, int H,
+                                                  const float* X, int ldf, float* H1, float* H2, int ldh, float* D, int tid) {
+    const float* W1 = params + L.w1; const float* B1 = params + L.b1;
+    const float* W2 = params + L.w2; const float* B2 = params + L.b2;
+    const float* W3 = params + L.w3; const float* B3 = params + L.b3;
+    auto e1 = [&](int r, int n, float s) { H1[r * ldh + n] = tanhf(s + ld_cg(B1 + n)); };
+    if ((F & 3) == 0) gemm_xwT<R, 4>(W1, X, ldf, H, F, tid, kStepThreads, e1);
+    else gemm_xwT<R, 1>(W1, X, ldf, H, F, tid, kStepThreads, e1);
+    __syncthreads();
+    auto e2 = [&](int r, int n, float s) { H2[r * ldh + n] = tanhf(s + ld_cg(B2 + n)); };
+    if ((H & 3) == 0) gemm_xwT<R, 4>(W2, H1, ldh, H, H, tid, kStepThreads, e2);
+    else gemm_xwT<R, 1>(W2, H1, ldh, H, H, tid, kStepThreads, e2);
+    __syncthreads();
+    auto e3 = [&](int r, int n, float s) { D[r] = s + ld_cg(B3); };
+    if ((H & 3) == 0) gemm_xwT<R, 4>(W3, H2, ldh, 1, H, tid, kStepThreads, e3);
+    else gemm_xwT<R, 1>(W3, H2, ldh, 1, H, tid, kStepThreads, e3);
+    __syncthreads();
+}
+
+__device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
+                          DiscSmem& sm, bool acc) {
+    constexpr int R = kDR, TB = kTB;
+    const int tid = threadIdx.x, nth = kStepThreads;
+    const int F = a.F, H = a.H, ldf = sm.ldf, ldh = sm.ldh;
+    const bool vecH = (H & 3) == 0, vecF = (F & 3) == 0;
+    const int row0 = a.row_begin + tile * TB;
+    const int32_t* eidx = a.eidx + (size_t)step * a.B;
+    const int32_t* pidx = a.pidx + (size_t)step * a.B;
+    const float* alpha = a.alpha + (size_t)step * a.B;
+    const float invB = 1.f / (float)a.B;
+    const float* W1 = a.params + a.L.w1; const float* W2 = a.params + a.L.w2; const float* W3 = a.params + a.L.w3;
+
+    // rows: [0,TB) expert, [TB,2TB) policy, [2TB,3TB) mixup = alpha*e + (1-alpha)*p (gail.py:72-75), rest zero
+    for (int e = tid; e < R * ldf; e += nth) {
+        const int r = e / ldf, k = e - r * ldf;
+        const int kind = r / TB, j = r - kind * TB;
+        const int row = row0 + j;
+        float x = 0.f;
+        if (kind < 3 && row < a.row_end && k < F) {
+            const float xe = a.expert[(size_t)eidx[row] * F + k];
+            const float xp = a.policy[(size_t)pidx[row] * F + k];
+            const float al = alpha[row];
+            x = kind == 0 ? xe : (kind == 1 ? xp : __fadd_rn(__fmul_rn(al, xe), __fmul_rn(__fsub_rn(1.f, al), xp)));
+        }
+        sm.X[e] = x;
+    }
+    __syncthreads();
+    disc_tile_forward<R>(a.params, a.L, F, H, sm.X, ldf, sm.H1, sm.H2, ldh, sm.D, tid);
+
+    // BCE-with-logits seeds (gail.py:171-176): expert target 1, policy target 0, both batch means
+    if (tid < R) {
+        const int kind = tid / TB, j = tid - kind * TB;
+        const bool ok = (row0 + j) < a.row_end;
+        float dd = 0.f, le = 0.f, lp = 0.f;
+        if (ok && kind == 0) { const float d = sm.D[tid]; dd = (sigmoidf(d) - 1.f) * invB; le = softplusf(-d); }
+        if (ok && kind == 1) { const float d = sm.D[tid]; dd = sigmoidf(d) * invB; lp = softplusf(d); }
+        sm.DD[tid] = dd; sm.LOSS[tid] = le; sm.LOSS[R + tid] = lp;
+    }
+    __syncthreads();
+    // Y2t = [dz2_e | dz2_p | u2 | 0] ;  L2t slots e,p and the u2 slot are final here
+    for (int e = tid; e < H * R; e += nth) {
+        const int n = e / R, r = e - n * R;
+        const int kind = r / TB;
+        const float h2 = sm.H2[r * ldh + n];
+        const float w3 = ld_cg(W3 + n);
+        const float base = w3 * (1.f - h2 * h2);
+        float y = 0.f;
+        if (kind < 2) y = sm.DD[r] * base;
+        else if (kind == 2) y = base;                // u2
+        sm.Y2t[e] = y;
+        if (kind < 2) sm.L2t[e] = y;
+        else if (kind == 2) sm.L2t[n * R + r + TB] = base;   // u2 pairs with vb1 in slot 3TB+j
+    }
+    __syncthreads();
+    // pass A: (Y2t . W2): e/p rows -> dz1 ; mixup rows -> v1, u1
+    auto epiA = [&](int r, int k, float s) {
+        const int kind = r / TB, j = r - kind * TB;
+        const float h1 = sm.H1[r * ldh + k];
+        const float t1 = s * (1.f - h1 * h1);
+        if (kind < 2) sm.L1t[k * R + r] = t1;                      // dz1
+        else if (kind == 2) { sm.V1[j * ldh + k] = s; sm.U1x[k * TB + j] = t1; sm.L1t[k * R + r + TB] = t1; }  // u1 -> slot 3TB+j
+    };
+    if (vecH) gemm_yW<R, 4>(W2, sm.Y2t, H, H, sm.SCR, tid, nth, epiA);
+    else gemm_yW<R, 1>(W2, sm.Y2t, H, H, sm.SCR, tid, nth, epiA);
+    // pass B: g = u1 . W1  (input gradient of the mixup rows) -> X rows 3TB+j (raw g for now)
+    float* G = sm.X + 3 * TB * ldf;
+    auto epiB = [&](int r, int k, float s) { G[r * ldf + k] = s; };
+    if (vecF) gemm_yW<TB, 4>(W1, sm.U1x, H, F, sm.SCR, tid, nth, epiB);
+    else gemm_yW<TB, 1>(W1, sm.U1x, H, F, sm.SCR, tid, nth, epiB);
+    // ||g||, penalty and gbar = (2 lambda / B)(n-1) g / n
+    if (tid < 32 * TB) {
+        const int j = tid >> 5, lane = tid & 31;
+        float ssq = 0.f;
+        for (int k = lane; k < F; k += 32) { const float g = G[j * ldf + k]; ssq += g * g; }
+        ssq = warp_sum(ssq);
+        const float nrm = sqrtf(ssq);
+        const bool ok = (row0 + j) < a.row_end;
+        const float coef = (ok && nrm > 0.f) ? (2.f * a.gp_lambda * invB) * (nrm - 1.f) / nrm : 0.f;
+        for (int k = lane; k < ldf; k += 32) G[j * ldf + k] = (k < F) ? coef * G[j * ldf + k] : 0.f;
+        if (lane == 0) sm.LOSS[2 * TB + j] = ok ? (nrm - 1.f) * (nrm - 1.f) : 0.f;   // LOSS[2TB..3TB) : penalty terms
+    }
+    __syncthreads();
+    // pass C: ub1 = gbar . W1^T -> vb1 (H1 rows 3TB+j), hb1
+    auto epiC = [&](int r, int n, float s) {
+        const float h1 = sm.H1[(2 * TB + r) * ldh + n];
+        sm.H1[(3 * TB + r) * ldh + n] = s * (1.f - h1 * h1);                 // vb1
+        sm.HB1[r * ldh + n] = -2.f * s * sm.V1[r * ldh + n] * h1;            // hb1
+    };
+    if (vecF) gemm_xwT<TB, 4>(W1, G, ldf, H, F, tid, nth, epiC);
+    else gemm_xwT<TB, 1>(W1, G, ldf, H, F, tid, nth, epiC);
+    __syncthreads();
+    // pass D: ub2 = vb1 . W2^T -> dw3 term, zb2
+    const float* VB1 = sm.H1 + 3 * TB * ldh;
+    auto epiD = [&](int r, int n, float s) {
+        const float h2 = sm.H2[(2 * TB + r) * ldh + n];
+        const float om = 1.f - h2 * h2;
+        sm.C3[r * ldh + n] = s * om;
+        const float zb2 = -2.f * s * ld_cg(W3 + n) * h2 * om;
+        sm.Z2x[n * TB + r] = zb2;
+        sm.L2t[n * R + 2 * TB + r] = zb2;
+    };
+    if (vecH) gemm_xwT<TB, 4>(W2, VB1, ldh, H, H, tid, nth, epiD);
+    else gemm_xwT<TB, 1>(W2, VB1, ldh, H, H, tid, nth, epiD);
+    __syncthreads();
+    // pass E: hb1 += zb2 . W2 ; zb1 = hb1*(1-h1^2)
+    auto epiE = [&](int r, int k, float s) {
+        const float h1 = sm.H1[(2 * TB + r) * ldh + k];
+        sm.L1t[k * R + 2 * TB + r] = (sm.HB1[r * ldh + k] + s) * (1.f - h1 * h1);
+    };
+    if (vecH) gemm_yW<TB, 4>(W2, sm.Z2x, H, H, sm.SCR, tid, nth, epiE);
+    else gemm_yW<TB, 1>(W2, sm.Z2x, H, H, sm.SCR, tid, nth, epiE);
+
+    // parameter gradients of this tile
+    if (vecH) outer_store<R, 4>(gout + a.L.w2, sm.L2t, sm.H1, ldh, H, H, tid, nth, acc);
+    else outer_store<R, 1>(gout + a.L.w2, sm.L2t, sm.H1, ldh, H, H, tid, nth, acc);
+    rowsum_store<R>(gout + a.L.b2, sm.L2t, H, tid, nth, acc, 3 * TB);
+    if (vecF) outer_store<R, 4>(gout + a.L.w1, sm.L1t, sm.X, ldf, H, F, tid, nth, acc);
+    else outer_store<R, 1>(gout + a.L.w1, sm.L1t, sm.X, ldf, H, F, tid, nth, acc);
+    rowsum_store<R>(gout + a.L.b1, sm.L1t, H, tid, nth, acc, 3 * TB);
+    for (int n = tid; n < H; n += nth) {
+        float s = 0.f;
+        for (int r = 0; r < 2 * TB; ++r) s += sm.DD[r] * sm.H2[r * ldh + n];
+        for (int j = 0; j < TB; ++j) s += sm.C3[j * ldh + n];
+        __stcg(gout + a.L.w3 + n, acc ? s + __ldcg(gout + a.L.w3 + n) : s);
+    }
+    if (tid == 0) {
+        float db3 = 0.f, le = 0.f, lp = 0.f, gp = 0.f;
+        for (int r = 0; r < 2 * TB; ++r) db3 += sm.DD[r];
+        for (int r = 0; r < TB; ++r) { le += sm.LOSS[r]; lp += sm.LOSS[R + TB + r]; gp += sm.LOSS[2 * TB + r]; }
+        if (acc) { db3 += __ldcg(gout + a.L.b3); le += lossout[0]; lp += lossout[1]; gp += lossout[2]; }
+        __stcg(gout + a.L.b3, db3);
+        lossout[0] = le; lossout[1] = lp; lossout[2] = gp;
+    }
+    __syncthreads();
+}
+
+__device__ void disc_reduce(const DiscArgs& a, int cta, int ncta) {
+    const int tid = threadIdx.x;
+    for (int p = cta * kStepThreads + tid; p < a.P; p += ncta * kStepThreads) {
+        float g = 0.f;
+        for (int c = 0; c < a.nslots; ++c) g += ld_cg(a.gpart + (size_t)c * a.P + p);
+        __stcg(a.grad + p, g);
+    }
+    if (cta == 0 && tid < 3) {
+        float s = 0.f;
+        for (int c = 0; c < a.nslots; ++c) s += ld_cg(a.losspart + c * 4 + tid);
+        __stcg(a.grad + a.P + tid, s);
+    }
+}
+
+__device__ void disc_adam(const DiscArgs& a, int step, int cta, int ncta) {
+    const int tid = threadIdx.x;
+    const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
+    for (int p = cta * kStepThreads + tid; p < a.P; p += ncta * kStepThreads) {
+        const float g = ld_cg(a.grad + p);
+        float pv = a.params[p], mv = a.m[p], vv = a.v[p];
+        adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+        a.params[p] = pv; a.m[p] = mv; a.v[p] = vv;
+    }
+    if (cta == 0 && tid == 0) {
+        const float invB = 1.f / (float)a.B;
+        const float le = ld_cg(a.grad + a.P) * invB, lp = ld_cg(a.grad + a.P + 1) * invB;
+        const float gp = a.gp_lambda * ld_cg(a.grad + a.P + 2) * invB;
+        float* tr = a.trace + (size_t)step * 3;
+        tr[0] = (le + lp) + gp; tr[1] = le; tr[2] = lp;
+    }
+}
+
+__device__ __forceinline__ void disc_phase1_all(const DiscArgs& a, int step, int cta, int ncta, float* smem) {
+    DiscSmem sm;
+    sm.carve(smem, a.F, a.H);
+    bool acc = false;
+    for (int tile = cta; tile < a.ntiles; tile += ncta) {
+        disc_tile(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
+        acc = true;
+    }
+}
+
+__global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    for (int step = 0; step < a.nsteps; ++step) {
+        disc_phase1_all(a, step, blockIdx.x, gridDim.x, smem);
+        gb.sync();
+        disc_reduce(a, blockIdx.x, gridDim.x);
+        gb.sync();
+        disc_adam(a, step, blockIdx.x, gridDim.x);
+        gb.sync();
+    }
+    // a timed-out grid barrier poisons the trace so the host raises instead of trusting the result
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
+}
+__global__ void __launch_bounds__(kStepThreads, 1) disc_phase1_kernel(DiscArgs a, int step) {
+    extern __shared__ __align__(16) float smem[];
+    disc_phase1_all(a, step, blockIdx.x, gridDim.x, smem);
+}
+__global__ void __launch_bounds__(kStepThreads) disc_phase2_kernel(DiscArgs a) { disc_reduce(a, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(kStepThreads) disc_phase3_kernel(DiscArgs a, int step) { disc_adam(a, step, blockIdx.x, gridDim.x); }
+
+// ---- reward prediction ---------------------------------------------------------------------------
+// raw reward of predict_reward_combined (gail.py:203-205) for n_rows rows of (.,F); optionally the
+// one-step return update (gail.py:206-209) when `returns` is given (single-block use).
+__global__ void __launch_bounds__(kStepThreads) disc_reward_kernel(const float* __restrict__ params, DiscLayout L, int F,
+                                                                   int H, const float* __restrict__ d_in, int n_rows,
+                                                                   float offset, float* __restrict__ reward,
+                                                                   float* __restrict__ returns, const float* __restrict__ masks,
+                                                                   float gamma, int has_returns) {
+    constexpr int R = kRows;
+    extern __shared__ __align__(16) float smem[];
+    const int ldf = round_up(F, 4), ldh = round_up(H, 4);
+    float* X = smem; float* H1 = X + R * ldf; float* H2 = H1 + R * ldh; float* D = H2 + R * ldh;
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile * R < n_rows; tile += gridDim.x) {
+        const int row0 = tile * R;
+        for (int e = tid; e < R * ldf; e += kStepThreads) {
+            const int r = e / ldf, k = e - r * ldf;
+            X[e] = (row0 + r < n_rows && k < F) ? d_in[(size_t)(row0 + r) * F + k] : 0.f;
+        }
+        __syncthreads();
+        disc_tile_forward<R>(params, L, F, H, X, ldf, H1, H2, ldh, D, tid);
+        if (tid < R && row0 + tid < n_rows) {
+            const int row = row0 + tid;
+            const float s = sigmoidf(D[tid]);
+            // (s + 1e-7).log() - (1 - s + 1e-7).log() + offset
+            const float rew = __fadd_rn(__fsub_rn(logf(__fadd_rn(s, 1e-7f)), logf(__fadd_rn(__fsub_rn(1.f, s), 1e-7f))), offset);
+            reward[row] = rew;
+            if (returns) returns[row] = has_returns ? __fadd_rn(__fmul_rn(__fmul_rn(returns[row], gamma), masks[row]), rew) : rew;
+        }
+        __syncthreads();
+    }
+}
+
+// returns_t = returns_{t-1}*gamma*masks[t] + raw_t per env column; keeps every step's returns for the
+// running statistics (gail.py:206-209 called with masks[step], main_gail_dyn_ppo.py:276-280).
+__global__ void __launch_bounds__(128) relabel_scan_kernel(const float* __restrict__ raw, const float* __restrict__ masks,
+                                                           float* __restrict__ ret_all, float* __restrict__ disc_returns,
+                                                           int T, int N, float gamma, int has_returns) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float ret = has_returns ? disc_returns[n] : 0.f;
+    constexpr int U = 8;
+    for (int t0 = 0; t0 < T; t0 += U) {
+        float r[U], m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u;
+            r[u] = t < T ? raw[(size_t)t * N + n] : 0.f;
+            m[u] = t < T ? masks[(size_t)t * N + n] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = t0 + u;
+            if (t >= T) break;
+            ret = (has_returns || t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), m[u]), r[u]) : r[u];
+            ret_all[(size_t)t * N + n] = ret;
+        }
+    }
+    disc_returns[n] = ret;
+}
+
+// numpy's float32 pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum), so that
+// np.mean / np.var of the N per-step returns are reproduced bit for bit.  SQ: sum (a[i]-c)^2 instead.
+template <bool SQ>
+__device__ float np_pairwise_sum(const float* a, int n, float c) {
+    auto f = [&](int i) { if (SQ) { const float d = __fsub_rn(a[i], c); return __fmul_rn(d, d); } return a[i]; };
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, f(i));
+        return res;
+    } else if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = f(j);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], f(i + j));
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, f(i));
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return __fadd_rn(np_pairwise_sum<SQ>(a, n2, c), np_pairwise_sum<SQ>(a + n2, n - n2, c));
+    }
+}
+
+// per-step batch moments in numpy's float32 arithmetic: np.mean(x), np.var(x) (running_mean_std.py:34-35)
+__global__ void __launch_bounds__(128) relabel_moments_kernel(const float* __restrict__ ret_all, int T, int N,
+                                                              float* __restrict__ bmean, float* __restrict__ bvar,
+                                                              float* __restrict__ mean_returns) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* x = ret_all + (size_t)t * N;
+    const float mean = __fdiv_rn(np_pairwise_sum<false>(x, N, 0.f), (float)N);
+    const float var = __fdiv_rn(np_pairwise_sum<true>(x, N, mean), (float)N);
+    bmean[t] = mean; bvar[t] = var;
+    mean_returns[t] = mean;
+}
+
+// the sequential float64 Chan merge (running_mean_std.py:45-56); scale[t] = sqrt(var_t + 1e-7)
+__global__ void relabel_rms_kernel(const float* __restrict__ bmean, const float* __restrict__ bvar, int T, int N,
+                                   double* __restrict__ rms, double* __restrict__ scale) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mean = rms[0], var = rms[1], count = rms[2];
+    const double bc = (double)N;
+    for (int t = 0; t < T; ++t) {
+        // explicit round-to-nearest ops: no FMA contraction, numpy evaluates these one by one
+        const double delta = __dsub_rn((double)bmean[t], mean);
+        const double tot = __dadd_rn(count, bc);
+        const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, bc), tot));
+        const double m_a = __dmul_rn(var, count);
+        const double m_b = (double)__fmul_rn(bvar[t], (float)N);     // float32 * int stays float32 in numpy
+        const double corr = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), bc), tot);
+        const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), corr);
+        mean = new_mean; var = __ddiv_rn(m2, tot); count = tot;
+        scale[t] = sqrt(__dadd_rn(var, 1e-7));
+    }
+    rms[0] = mean; rms[1] = var; rms[2] = count;
+}
+
+// rewards[t] = float32(clip(float64(raw)/sqrt(var_t+1e-7), -10, 10))   (main_gail_dyn_ppo.py:288-292)
+__global__ void __launch_bounds__(256) relabel_apply_kernel(const float* __restrict__ raw, const double* __restrict__ scale,
+                                                            float* __restrict__ rewards, int T, int N) {
+    const long long total = (long long)T * N;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(e / N);
+        double v = (double)raw[e] / scale[t];
+        v = fmin(fmax(v, -10.0), 10.0);
+        rewards[e] = (float)v;
+    }
+}
+
+static int disc_tiles(const sg_disc_config* c) { return (c->row_end - c->row_begin + kTB - 1) / kTB; }
+static int disc_grid(const sg_disc_config* c, int* sms_out) {
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    if (sms_out) *sms_out = sms;
+    int tiles = disc_tiles(c);
+    int g = tiles < sms ? tiles : sms;
+    return g < 1 ? 1 : g;
+}
+static int disc_validate(const sg_disc_config* c) {
+    SG_REQUIRE(c, "sg_disc: null config");
+    SG_REQUIRE(c->feat_dim > 0 && c->hidden > 0 && c->batch_size > 0 && c->n_steps > 0, "sg_disc: non-positive sizes");
+    SG_REQUIRE(c->row_begin >= 0 && c->row_begin < c->row_end && c->row_end <= c->batch_size,
+               "sg_disc: shard [%d,%d) outside minibatch of %d rows", c->row_begin, c->row_end, c->batch_size);
+    SG_REQUIRE(c->first_adam_step >= 1, "sg_disc: first_adam_step is 1-based");
+    const size_t smem = (size_t)DiscSmem::floats(c->feat_dim, c->hidden) * sizeof(float);
+    SG_REQUIRE(smem <= 220 * 1024, "sg_disc: tile needs %zu bytes of shared memory", smem);
+    return SG_OK;
+}
+struct DiscWs { size_t gpart, grad, losspart, bar, total; };
+static DiscWs disc_ws(const sg_disc_config* c, int grid) {
+    DiscLayout L = make_disc_layout(c->feat_dim, c->hidden);
+    DiscWs w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
+    w.gpart = take((size_t)grid * L.total * sizeof(float));
+    w.grad = take((size_t)(L.total + 4) * sizeof(float));
+    w.losspart = take((size_t)grid * 4 * sizeof(float));
+    w.bar = take(2 * sizeof(unsigned int));
+    w.total = o;
+    return w;
+}
+
+struct RelabelWs { size_t raw, ret_all, bmean, bvar, scale, total; };
+static RelabelWs relabel_ws(int T, int N) {
+    RelabelWs w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 255) / 256 * 256; return at; };
+    w.raw = take((size_t)T * N * sizeof(float));
+    w.ret_all = take((size_t)T * N * sizeof(float));
+    w.bmean = take((size_t)T * sizeof(float));
+    w.bvar = take((size_t)T * sizeof(float));
+    w.scale = take((size_t)T * sizeof(double));
+    w.total = o;
+    return w;
+}
+
+static int launch_reward(const float* params, int F, int H, const float* d_in, int n_rows, float offset, float* reward,
+                         float* returns, const float* masks, float gamma, int has_returns, cudaStream_t s) {
+    DiscLayout L = make_disc_layout(F, H);
+    const size_t smem = (size_t)(kRows * round_up(F, 4) + 2 * kRows * round_up(H, 4) + kRows) * sizeof(float);
+    SG_REQUIRE(smem <= 200 * 1024, "disc reward: tile needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SG_CUDA(cudaFuncSetAttribute(disc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int tiles = (n_rows + kRows - 1) / kRows;
+    int grid = tiles < 1184 ? tiles : 1184;
+    disc_reward_kernel<<<grid, kStepThreads, smem, s>>>(params, L, F, H, d_in, n_rows, offset, reward, returns, masks, gamma, has_returns);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int64_t sg_disc_workspace_bytes(const sg_disc_config* cfg) {
+    if (disc_validate(cfg)) return -1;
+    return (int64_t)disc_ws(cfg, disc_grid(cfg, nullptr)).total;
+}
+
+int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, float* adam_v, const float* expert,
+                   const float* policy_feat, const int32_t* expert_idx, const int32_t* policy_idx, const float* alpha,
+                   const float* step_size, const float* bc2_sqrt, float* trace, void* workspace,
+                   sg_allreduce_fn allreduce_cb, void* allreduce_user, void* stream) {
+    int rc = disc_validate(cfg);
+    if (rc) return rc;
+    SG_REQUIRE(params && adam_m && adam_v && expert && policy_feat && expert_idx && policy_idx && alpha && step_size &&
+                   bc2_sqrt && trace && workspace, "sg_disc_update: null pointer");
+    SG_REQUIRE(!(allreduce_cb && cfg->mode == 0), "sg_disc_update: the allreduce callback needs mode 1");
+    cudaStream_t s = (cudaStream_t)stream;
+    int sms = 0;
+    const int grid = disc_grid(cfg, &sms);
+    const DiscWs w = disc_ws(cfg, grid);
+    char* ws = (char*)workspace;
+    DiscArgs a;
+    a.F = cfg->feat_dim; a.H = cfg->hidden;
+    a.L = make_disc_layout(a.F, a.H);
+    a.P = a.L.total; a.B = cfg->batch_size; a.nsteps = cfg->n_steps;
+    a.row_begin = cfg->row_begin; a.row_end = cfg->row_end;
+    a.ntiles = disc_tiles(cfg);
+    a.nslots = grid < a.ntiles ? grid : a.ntiles;
+    a.gp_lambda = (float)cfg->gp_lambda;
+    a.one_minus_b1 = (float)(1.0 - cfg->beta1); a.b2 = (float)cfg->beta2; a.one_minus_b2 = (float)(1.0 - cfg->beta2);
+    a.eps = (float)cfg->adam_eps;
+    a.params = params; a.m = adam_m; a.v = adam_v;
+    a.expert = expert; a.policy = policy_feat; a.alpha = alpha; a.eidx = expert_idx; a.pidx = policy_idx;
+    a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
+    a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
+    a.bar = (unsigned int*)(ws + w.bar);
+    const size_t smem = (size_t)DiscSmem::floats(a.F, a.H) * sizeof(float);
+    SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
+    if (cfg->mode == 0) {
+        SG_CUDA(cudaFuncSetAttribute(disc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, disc_persistent_kernel, kStepThreads, smem));
+        SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_disc_update: cooperative grid of %d CTAs does not fit", grid);
+        void* kargs[] = {(void*)&a};
+        SG_CUDA(cudaLaunchCooperativeKernel((const void*)disc_persistent_kernel, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+    } else {
+        SG_CUDA(cudaFuncSetAttribute(disc_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int g2 = (a.P + kStepThreads - 1) / kStepThreads;
+        for (int step = 0; step < a.nsteps; ++step) {
+            disc_phase1_kernel<<<grid, kStepThreads, smem, s>>>(a, step);
+            disc_phase2_kernel<<<g2, kStepThreads, 0, s>>>(a);
+            if (allreduce_cb) {
+                int cb = allreduce_cb(a.grad, a.P + 3, allreduce_user);
+                SG_REQUIRE(cb == 0, "sg_disc_update: allreduce callback failed with %d at step %d", cb, step);
+            }
+            disc_phase3_kernel<<<g2, kStepThreads, 0, s>>>(a, step);
+        }
+        SG_CUDA(cudaGetLastError());
+    }
+    return SG_OK;
+}
+
+int sg_disc_predict_reward(const float* params, int feat_dim, int hidden, const float* d_in, int n_rows, double gamma,
+                           const float* masks, double offset, int has_returns, float* reward, float* returns,
+                           void* stream) {
+    SG_REQUIRE(params && d_in && reward && n_rows > 0 && feat_dim > 0 && hidden > 0, "sg_disc_predict_reward: bad arguments");
+    SG_REQUIRE(!returns || !has_returns || masks, "sg_disc_predict_reward: masks required to update returns");
+    return launch_reward(params, feat_dim, hidden, d_in, n_rows, (float)offset, reward, returns, masks, (float)gamma,
+                         has_returns, (cudaStream_t)stream);
+}
+
+int64_t sg_relabel_workspace_bytes(int T, int N) {
+    if (T <= 0 || N <= 0) return -1;
+    return (int64_t)relabel_ws(T, N).total;
+}
+
+static int relabel_from_raw(const float* raw, const float* masks, float* rewards, int T, int N, double gamma,
+                            float* disc_returns, int has_returns, double* rms_state, float* mean_returns, char* ws,
+                            const RelabelWs& w, cudaStream_t s) {
+    float* ret_all = (float*)(ws + w.ret_all);
+    float* bmean = (float*)(ws + w.bmean);
+    float* bvar = (float*)(ws + w.bvar);
+    double* scale = (double*)(ws + w.scale);
+    relabel_scan_kernel<<<(N + 127) / 128, 128, 0, s>>>(raw, masks, ret_all, disc_returns, T, N, (float)gamma, has_returns);
+    relabel_moments_kernel<<<(T + 127) / 128, 128, 0, s>>>(ret_all, T, N, bmean, bvar, mean_returns);
+    relabel_rms_kernel<<<1, 32, 0, s>>>(bmean, bvar, T, N, rms_state, scale);
+    long long total = (long long)T * N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 1184) blocks = 1184;
+    relabel_apply_kernel<<<blocks, 256, 0, s>>>(raw, scale, rewards, T, N);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_relabel_normalize(const float* raw_reward, const float* masks, float* rewards, int T, int N, double gamma,
+                         float* disc_returns, int has_returns, double* rms_state, float* mean_returns, void* workspace,
+                         void* stream) {
+    SG_REQUIRE(raw_reward && masks && rewards && disc_returns && rms_state && mean_returns && workspace,
+               "sg_relabel_normalize: null pointer");
+    SG_REQUIRE(T > 0 && N > 0, "sg_relabel_normalize: non-positive sizes");
+    const RelabelWs w = relabel_ws(T, N);
+    return relabel_from_raw(raw_reward, masks, rewards, T, N, gamma, disc_returns, has_returns, rms_state, mean_returns,
+                            (char*)workspace, w, (cudaStream_t)stream);
+}
+
+int sg_disc_relabel(const float* params, int feat_dim, int hidden, const float* obs_feat, const float* masks,
+                    float* rewards, int T, int N, double gamma, double offset, float* disc_returns, int has_returns,
+                    double* rms_state, float* mean_returns, void* workspace, void* stream) {
+    SG_REQUIRE(params && obs_feat && masks && rewards && disc_returns && rms_state && mean_returns && workspace,
+               "sg_disc_relabel: null pointer");
+    SG_REQUIRE(T > 0 && N > 0 && feat_dim > 0 && hidden > 0, "sg_disc_relabel: non-positive sizes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const RelabelWs w = relabel_ws(T, N);
+    char* ws = (char*)workspace;
+    float* raw = (float*)(ws + w.raw);
+    // reward for step t reads obs_feat[t+1] (main_gail_dyn_ppo.py:278): rows N.. of the (T+1,N,F) buffer
+    int rc = launch_reward(params, feat_dim, hidden, obs_feat + (size_t)N * feat_dim, T * N, (float)offset, raw, nullptr,
+                           nullptr, 0.f, 0, s);
+    if (rc) return rc;
+    return relabel_from_raw(raw, masks, rewards, T, N, gamma, disc_returns, has_returns, rms_state, mean_returns, ws, w, s);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

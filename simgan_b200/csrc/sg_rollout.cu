@@ -1,0 +1,276 @@
+// Rollout-buffer kernels: return/GAE scan, advantage statistics, sampler row gathers, fused insert,
+// and the batched actor-critic forward used by Policy.act / get_value / evaluate_actions.
+#include "sg_common.cuh"
+#include "sg_policy.cuh"
+
+namespace sg {
+
+// ------------------------------------------------------------------------------------------------
+// compute_returns (A2C/storage.py:103-142).  One thread per env column walks t = T-1..0; loads are
+// issued a block of UNR steps ahead of the dependent chain.  Every arithmetic step uses explicit
+// round-to-nearest mul/add in the reference's order so the result is bit-identical to the eager
+// fp32 tensor ops (no FMA contraction).
+//   mode 0: GAE + proper time limits   mode 1: GAE   mode 2: plain + proper limits   mode 3: plain
+// ------------------------------------------------------------------------------------------------
+constexpr int kUnr = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(128) returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ vpred,
+                                                           const float* __restrict__ masks,
+                                                           const float* __restrict__ bad, float* __restrict__ ret,
+                                                           const float* __restrict__ next_value, int T, int N,
+                                                           float g, float gl) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float nv = next_value[n];
+    constexpr bool GAE = (MODE <= 1), PROPER = (MODE == 0 || MODE == 2);
+    float carry;       // gae (GAE modes) or returns[t+1] (plain modes)
+    float v_next = nv;
+    if (GAE) { vpred[(size_t)T * N + n] = nv; carry = 0.f; }
+    else { ret[(size_t)T * N + n] = nv; carry = nv; }
+    for (int t0 = T; t0 > 0; t0 -= kUnr) {
+        float r[kUnr], v[kUnr], m[kUnr], b[kUnr];
+#pragma unroll
+        for (int u = 0; u < kUnr; ++u) {
+            const int t = t0 - 1 - u;
+            if (t >= 0) {
+                r[u] = rewards[(size_t)t * N + n];
+                v[u] = vpred[(size_t)t * N + n];
+                m[u] = masks[(size_t)(t + 1) * N + n];
+                b[u] = PROPER ? bad[(size_t)(t + 1) * N + n] : 1.f;
+            } else { r[u] = v[u] = m[u] = 0.f; b[u] = 1.f; }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnr; ++u) {
+            const int t = t0 - 1 - u;
+            if (t < 0) break;
+            float out;
+            if (GAE) {
+                // delta = r + gamma*V[t+1]*m - V[t];  gae = delta + (gamma*lambda)*m*gae;  gae *= bad
+                const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(g, v_next), m[u])), v[u]);
+                carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m[u]), carry));
+                if (PROPER) carry = __fmul_rn(carry, b[u]);
+                out = __fadd_rn(carry, v[u]);
+                v_next = v[u];
+            } else if (PROPER) {
+                // (ret[t+1]*gamma*m + r)*bad + (1-bad)*V[t]
+                const float a = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(carry, g), m[u]), r[u]), b[u]);
+                out = __fadd_rn(a, __fmul_rn(__fsub_rn(1.f, b[u]), v[u]));
+                carry = out;
+            } else {
+                out = __fadd_rn(__fmul_rn(__fmul_rn(carry, g), m[u]), r[u]);
+                carry = out;
+            }
+            ret[(size_t)t * N + n] = out;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// advantage statistics: mean and unbiased std of (returns - value_preds)[:S]  (A2C/algo/ppo.py:66-68)
+// fp64 accumulation; stage 1 = per-CTA partial (sum, sumsq), stage 2 = one CTA finalises.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatBlocks = 296;
+
+__global__ void __launch_bounds__(256) adv_partial_kernel(const float* __restrict__ ret, const float* __restrict__ vp,
+                                                          int S, double* __restrict__ part) {
+    double s = 0.0, q = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < S; i += gridDim.x * blockDim.x) {
+        const double a = (double)__fsub_rn(ret[i], vp[i]);
+        s += a; q += a * a;
+    }
+    __shared__ double sh[2][8];
+    s = warp_sum(s); q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0, tq = 0;
+        for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+        part[2 * blockIdx.x] = ts; part[2 * blockIdx.x + 1] = tq;
+    }
+}
+
+__global__ void adv_final_kernel(const double* __restrict__ part, int nblocks, int S, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0, q = 0;
+        for (int b = 0; b < nblocks; ++b) { s += part[2 * b]; q += part[2 * b + 1]; }
+        const double mean = s / S;
+        double var = (q - s * mean) / (S > 1 ? (S - 1) : 1);
+        if (var < 0) var = 0;
+        out[0] = (float)mean;
+        out[1] = (S > 1) ? (float)sqrt(var) : __int_as_float(0x7fc00000);  // torch.std of 1 element = nan
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler row gathers / block copies
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPtrs = 12;
+struct GatherArgs {
+    const float* src[kMaxPtrs];
+    float* dst[kMaxPtrs];
+    int dim[kMaxPtrs];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(GatherArgs a, const int64_t* __restrict__ idx, int n_rows) {
+    const int i = blockIdx.y;
+    const int d = a.dim[i];
+    const long long total = (long long)n_rows * d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(e / d), c = (int)(e - (long long)j * d);
+        a.dst[i][e] = a.src[i][(size_t)idx[j] * d + c];
+    }
+}
+
+__global__ void __launch_bounds__(256) copy_blocks_kernel(GatherArgs a) {
+    const int i = blockIdx.y;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.dim[i]; e += gridDim.x * blockDim.x) a.dst[i][e] = a.src[i][e];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Policy forward (A2C/model.py:89-114)
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(kStepThreads) policy_forward_kernel(const float* __restrict__ params, PolicyLayout L,
+                                                                      int O, int H, int A, const float* __restrict__ obs,
+                                                                      int B, const float* __restrict__ noise,
+                                                                      const float* __restrict__ actions_in,
+                                                                      float* __restrict__ value, float* __restrict__ action,
+                                                                      float* __restrict__ logp, float* __restrict__ entropy) {
+    extern __shared__ __align__(16) float smem[];
+    PolicyTile<R> T;
+    T.carve(smem, O, H, A);
+    const int tid = threadIdx.x;
+    for (int tile = blockIdx.x; tile * R < B; tile += gridDim.x) {
+        const int row0 = tile * R;
+        for (int e = tid; e < R * T.ldo; e += kStepThreads) {
+            const int r = e / T.ldo, k = e - r * T.ldo;
+            T.X[e] = (row0 + r < B && k < O) ? obs[(size_t)(row0 + r) * O + k] : 0.f;
+        }
+        __syncthreads();
+        policy_tile_forward<R>(params, L, O, H, A, T, tid);
+        // per (row, action): sample / copy the action
+        for (int e = tid; e < R * A; e += kStepThreads) {
+            const int r = e / A, a = e - r * A;
+            const int row = row0 + r;
+            float act = 0.f;
+            if (row < B) {
+                const float mu = T.MU[r * T.lda + a];
+                if (actions_in) act = actions_in[(size_t)row * A + a];
+                else if (noise) act = __fadd_rn(__fmul_rn(noise[(size_t)row * A + a], expf(ld_cg(params + L.ls + a))), mu);
+                else act = mu;
+                if (action) action[(size_t)row * A + a] = act;
+            }
+            T.ACT[r * T.lda + a] = act;
+        }
+        __syncthreads();
+        if (tid < R && row0 + tid < B) {
+            const int row = row0 + tid;
+            if (value) value[row] = T.VAL[tid];
+            if (logp) logp[row] = gaussian_logp_row(T.MU + tid * T.lda, T.ACT + tid * T.lda, params + L.ls, A);
+        }
+        if (entropy && blockIdx.x == 0 && tile == 0 && tid == 0) entropy[0] = gaussian_entropy(params + L.ls, A);
+        __syncthreads();
+    }
+}
+
+}  // namespace sg
+
+using namespace sg;
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int sg_compute_returns(const float* rewards, float* value_preds, const float* masks, const float* bad_masks,
+                       float* returns, const float* next_value, int T, int N, double gamma, double gae_lambda,
+                       int use_gae, int use_proper_time_limits, void* stream) {
+    SG_REQUIRE(T > 0 && N > 0, "sg_compute_returns: T and N must be positive (T=%d N=%d)", T, N);
+    SG_REQUIRE(rewards && value_preds && masks && bad_masks && returns && next_value, "sg_compute_returns: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
+    const int threads = 128, blocks = (N + threads - 1) / threads;
+    const int mode = use_gae ? (use_proper_time_limits ? 0 : 1) : (use_proper_time_limits ? 2 : 3);
+    switch (mode) {
+        case 0: returns_scan_kernel<0><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 1: returns_scan_kernel<1><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 2: returns_scan_kernel<2><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        default: returns_scan_kernel<3><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+    }
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int64_t sg_adv_stats_workspace_bytes(int S) { (void)S; return (int64_t)kStatBlocks * 2 * sizeof(double); }
+
+int sg_adv_stats(const float* returns, const float* value_preds, int S, float* out_stats, void* workspace, void* stream) {
+    SG_REQUIRE(S > 0 && returns && value_preds && out_stats && workspace, "sg_adv_stats: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    int blocks = (S + 255) / 256;
+    if (blocks > kStatBlocks) blocks = kStatBlocks;
+    adv_partial_kernel<<<blocks, 256, 0, s>>>(returns, value_preds, S, (double*)workspace);
+    adv_final_kernel<<<1, 32, 0, s>>>((const double*)workspace, blocks, S, out_stats);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_gather_rows(const float* const* h_src, float* const* h_dst, const int* h_dims, int n_tensors,
+                   const int64_t* idx, int n_rows, void* stream) {
+    SG_REQUIRE(n_tensors > 0 && n_tensors <= kMaxPtrs, "sg_gather_rows: n_tensors must be in 1..%d", kMaxPtrs);
+    if (n_rows == 0) return SG_OK;
+    SG_REQUIRE(n_rows > 0 && idx, "sg_gather_rows: bad index array");
+    GatherArgs a;
+    a.n = n_tensors;
+    int maxd = 1;
+    for (int i = 0; i < n_tensors; ++i) {
+        SG_REQUIRE(h_src[i] && h_dst[i] && h_dims[i] > 0, "sg_gather_rows: tensor %d invalid", i);
+        a.src[i] = h_src[i]; a.dst[i] = h_dst[i]; a.dim[i] = h_dims[i];
+        if (h_dims[i] > maxd) maxd = h_dims[i];
+    }
+    long long total = (long long)n_rows * maxd;
+    int bx = (int)((total + 255) / 256);
+    if (bx > 1184) bx = 1184;
+    gather_rows_kernel<<<dim3(bx, n_tensors), 256, 0, (cudaStream_t)stream>>>(a, idx, n_rows);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_copy_blocks(const float* const* h_src, float* const* h_dst, const int* h_count, int n_copies, void* stream) {
+    SG_REQUIRE(n_copies > 0 && n_copies <= kMaxPtrs, "sg_copy_blocks: n_copies must be in 1..%d", kMaxPtrs);
+    GatherArgs a;
+    a.n = n_copies;
+    int maxc = 1;
+    for (int i = 0; i < n_copies; ++i) {
+        SG_REQUIRE(h_src[i] && h_dst[i] && h_count[i] >= 0, "sg_copy_blocks: block %d invalid", i);
+        a.src[i] = h_src[i]; a.dst[i] = h_dst[i]; a.dim[i] = h_count[i];
+        if (h_count[i] > maxc) maxc = h_count[i];
+    }
+    int bx = (maxc + 255) / 256;
+    if (bx > 592) bx = 592;
+    copy_blocks_kernel<<<dim3(bx, n_copies), 256, 0, (cudaStream_t)stream>>>(a);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int sg_policy_forward(const float* params, int obs_dim, int hidden, int act_dim, const float* obs, int B,
+                      const float* noise, const float* actions_in, float* value, float* action, float* logp,
+                      float* entropy, void* stream) {
+    SG_REQUIRE(params && obs && B > 0 && obs_dim > 0 && hidden > 0 && act_dim > 0, "sg_policy_forward: bad arguments");
+    PolicyLayout L = make_policy_layout(obs_dim, hidden, act_dim);
+    const size_t smem = (size_t)PolicyTile<kRows>::floats(obs_dim, hidden, act_dim) * sizeof(float);
+    SG_REQUIRE(smem <= 200 * 1024, "sg_policy_forward: tile needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SG_CUDA(cudaFuncSetAttribute(policy_forward_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int tiles = (B + kRows - 1) / kRows;
+    int grid = tiles < 1184 ? tiles : 1184;
+    policy_forward_kernel<kRows><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(params, L, obs_dim, hidden, act_dim, obs, B,
+                                                                                     noise, actions_in, value, action, logp, entropy);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

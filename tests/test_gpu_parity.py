@@ -1,0 +1,403 @@
+"""CUDA hot path vs the CPU oracle and the golden vectors of the real reference.  All calls go through
+the C ABI (ctypes) underneath the reference-shaped Python classes."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import CASES, Golden
+from oracle import ppo_gail_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+gu = None
+sg = None
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _gpu():
+    global gu, sg
+    assert torch.cuda.is_available(), "the -m gpu suite needs a CUDA device"
+    import gpu_util
+    import simgan_b200
+    gu, sg = gpu_util, simgan_b200
+    yield
+
+
+# fp32 tolerances (north_star: bit-exact indexing/sampling, <=1e-4 rel on losses/returns)
+LOSS_RTOL = 1e-4
+
+
+# ------------------------------------------------------------------------------------------- returns / GAE
+@pytest.mark.parametrize("T,N", [(37, 5), (128, 4), (2048, 16), (64, 300)])
+@pytest.mark.parametrize("use_gae,proper", [(True, True), (True, False), (False, True), (False, False)])
+def test_compute_returns_bitexact(T, N, use_gae, proper):
+    torch.manual_seed(0)
+    p = orc.init_policy(14, 64, 7)
+    buf = orc.synth_rollout(T, N, 14, 7, 25, p, seed=T + N, ep_len=9.0)
+    buf["bad_masks"][min(3, T), 0] = 0.0
+    buf["rewards"].copy_(torch.randn(T, N, 1))
+    nv = torch.randn(N, 1)
+    rs = gu.make_storage(buf, 14, 7, 25)
+    rs.compute_returns(nv.to(gu.DEV), use_gae, 0.99, 0.95, proper)
+    orc.compute_returns(buf, nv, use_gae, 0.99, 0.95, proper)
+    assert torch.equal(rs.returns.cpu(), buf["returns"])
+    assert torch.equal(rs.value_preds.cpu(), buf["value_preds"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_gae_golden_bitexact(case):
+    g = Golden(case)
+    buf = g.buffer()
+    buf["rewards"].copy_(g.t("relabel_rewards"))
+    rs = gu.make_storage(buf, g.O, g.A, g.F)
+    rs.compute_returns(g.t("next_value").to(gu.DEV), True, 0.99, 0.95, True)
+    assert torch.equal(rs.returns.cpu(), g.t("gae_returns"))
+
+
+def test_adv_stats():
+    from simgan_b200 import _lib
+    g = Golden(CASES[0])
+    ret = g.t("gae_returns").to(gu.DEV)
+    vp = g.buffer()["value_preds"]
+    vp[-1] = g.t("next_value")
+    vp = vp.to(gu.DEV)
+    lib = _lib.lib()
+    out = torch.empty(2, device=gu.DEV)
+    ws = torch.empty(int(lib.sg_adv_stats_workspace_bytes(g.S)), dtype=torch.uint8, device=gu.DEV)
+    _lib.check(lib.sg_adv_stats(_lib.ptr(ret), _lib.ptr(vp), g.S, _lib.ptr(out), _lib.ptr(ws), _lib.current_stream()))
+    mean, std = out.cpu().tolist()
+    assert abs(mean - g.z["adv_mean_std"][0]) <= 1e-6 * max(1.0, abs(g.z["adv_mean_std"][0])) + 1e-7
+    assert abs(std - g.z["adv_mean_std"][1]) <= 1e-6 * g.z["adv_mean_std"][1]
+
+
+# ------------------------------------------------------------------------------------------------- sampler
+def test_feed_forward_generator_bitexact():
+    g = Golden("ragged_seed1.npz")
+    buf = g.buffer()
+    rs = gu.make_storage(buf, g.O, g.A, g.F)
+    adv = torch.randn(g.T, g.N, 1)
+    torch.manual_seed(11)
+    mine = list(rs.feed_forward_generator(adv.to(gu.DEV), num_mini_batch=5))
+    torch.manual_seed(11)
+    ref = list(orc.feed_forward_batches(buf, adv, num_mini_batch=5))
+    assert len(mine) == len(ref) == 5
+    for mb, rb in zip(mine, ref):
+        assert len(mb) == len(rb) == 10
+        for x, y in zip(mb, rb):
+            assert torch.equal(x.cpu(), y)
+    torch.manual_seed(12)
+    mine = list(rs.feed_forward_generator(None, mini_batch_size=24))
+    torch.manual_seed(12)
+    ref = list(orc.feed_forward_batches(buf, None, mini_batch_size=24))
+    assert len(mine) == len(ref) and mine[0][7] is None
+    assert torch.equal(mine[-1][-1].cpu(), ref[-1][-1])
+    # RNG stream left where the reference leaves it
+    after = torch.rand(3)
+    torch.manual_seed(12)
+    torch.randperm(g.S)
+    assert torch.equal(torch.rand(3), after)
+
+
+def test_insert_and_after_update():
+    T, N, O, A, F = 3, 2, 14, 7, 25
+    from oracle.ref_shim import BoxSpace
+    rs = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, F)
+    rs.to(gu.DEV)
+    buf = orc.new_buffer(T, N, O, A, F)
+    step = 0
+    gen = torch.Generator().manual_seed(0)
+    for _ in range(4):
+        args = [torch.randn(N, O, generator=gen), torch.zeros(N, 1), torch.randn(N, A, generator=gen),
+                torch.randn(N, 1, generator=gen), torch.randn(N, 1, generator=gen), torch.randn(N, 1, generator=gen),
+                (torch.rand(N, 1, generator=gen) > 0.3).float(), torch.ones(N, 1), torch.randn(N, F, generator=gen)]
+        rs.insert(*[a.to(gu.DEV) for a in args])
+        step = orc.buffer_insert(buf, step, *args)
+        assert rs.step == step
+    rs.after_update()
+    orc.buffer_after_update(buf)
+    for k, v in buf.items():
+        assert torch.equal(getattr(rs, k).cpu(), v), k
+
+
+# --------------------------------------------------------------------------------------------- actor-critic
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("B", [1, 16, 77])
+def test_policy_forward(case, B):
+    g = Golden(case)
+    p = g.policy()
+    pol = gu.make_policy(p, g.O, g.H, g.A)
+    gen = torch.Generator().manual_seed(B)
+    x = torch.randn(B, g.O, generator=gen)
+    act = torch.randn(B, g.A, generator=gen)
+    v_o, lp_o, ent_o = orc.policy_evaluate(p, x, act)
+    with torch.no_grad():
+        v, lp, ent, _ = pol.evaluate_actions(x.to(gu.DEV), None, None, act.to(gu.DEV))
+    assert gu.rel_err(v.cpu(), v_o) < 2e-6
+    assert gu.rel_err(lp.cpu(), lp_o) < 2e-6
+    assert abs(float(ent) - float(ent_o)) < 2e-6 * abs(float(ent_o))
+    assert gu.rel_err(pol.get_value(x.to(gu.DEV), None, None).cpu(), v_o) < 2e-6
+    # deterministic act = mean
+    v_d, a_d, lp_d = orc.policy_act(p, x, deterministic=True)
+    v2, a2, lp2, _ = pol.act(x.to(gu.DEV), None, None, deterministic=True)
+    assert gu.rel_err(a2.cpu(), a_d) < 2e-6 and gu.rel_err(lp2.cpu(), lp_d) < 2e-6
+    # sampled act: same CUDA-generator stream as torch.normal(mean, std) in the reference's Normal.sample()
+    torch.cuda.manual_seed(5)
+    v3, a3, lp3, _ = pol.act(x.to(gu.DEV), None, None)
+    torch.cuda.manual_seed(5)
+    mean = a2
+    std = pol.dist.logstd._bias.detach().t().exp().expand_as(mean)
+    a_ref = torch.normal(mean, std)
+    assert gu.rel_err(a3, a_ref) < 2e-6
+    _, mean_o, logstd_o = orc.policy_forward(p, x)
+    lp_chk = orc.gaussian_logp_entropy(mean_o, logstd_o, a3.cpu())[0]
+    assert gu.rel_err(lp3.cpu(), lp_chk) < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------------ PPO
+def _ppo_objects(g, mode):
+    pol = gu.make_policy(g.policy(), g.O, g.H, g.A)
+    agent = sg.PPO(pol, 0.2, g.ppo_epoch, g.nmb, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    agent.kernel_mode = mode
+    buf = g.buffer()
+    buf["rewards"].copy_(g.t("relabel_rewards"))
+    buf["returns"].copy_(g.t("gae_returns"))
+    buf["value_preds"][-1] = g.t("next_value")
+    rs = gu.make_storage(buf, g.O, g.A, g.F)
+    return pol, agent, rs, buf
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("mode", [1, 0])
+def test_ppo_per_step_trace_vs_oracle(case, mode):
+    """Every optimizer step's (value_loss, action_loss, entropy, grad_norm) against the oracle replaying the
+    same recorded index stream; parameters after the whole update."""
+    g = Golden(case)
+    pol, agent, rs, buf = _ppo_objects(g, mode)
+    ora = orc.PPOOracle(g.policy(), g.hyper())
+    trace = []
+    out_o = ora.update(buf, index_chunks=g.ppo_chunks(), trace=trace)
+    out = agent.update(rs, permutations=g.t("ppo_perm"))
+    tr = agent.last_trace.double().numpy()
+    tr_o = np.array(trace)
+    scale = np.abs(tr_o).max(axis=0)
+    # first step: identical state on both sides -> tight
+    assert np.all(np.abs(tr[0] - tr_o[0]) <= 5e-6 * scale + 1e-7), (tr[0], tr_o[0])
+    # all steps (fp32 reassociation compounds through Adam)
+    assert np.all(np.abs(tr - tr_o) <= LOSS_RTOL * scale + 1e-6), np.abs(tr - tr_o).max(axis=0) / scale
+    for i in range(3):
+        assert abs(out[i] - out_o[i]) <= LOSS_RTOL * max(abs(out_o[i]), scale[i])
+    po = ora.params()
+    pm = gu.policy_params(pol)
+    for k in orc.POLICY_KEYS:
+        assert torch.allclose(pm[k], po[k].reshape(-1), rtol=1e-3, atol=2e-5), k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_ppo_update_golden_rng(case):
+    """Drop-in call: PPO.update draws its own permutations from the CPU generator; compare with the losses
+    the REAL reference produced from the same generator state."""
+    g = Golden(case)
+    pol, agent, rs, _ = _ppo_objects(g, 0)
+    torch.set_rng_state(g.t("rng_before_ppo"))
+    out = agent.update(rs)
+    ref = g.z["ppo_losses"]
+    assert abs(out[0] - ref[0]) <= LOSS_RTOL * abs(ref[0])
+    assert abs(out[2] - ref[2]) <= LOSS_RTOL * abs(ref[2])
+    assert abs(out[1] - ref[1]) <= LOSS_RTOL * max(abs(ref[1]), 0.05)   # action loss hovers around zero
+    pm = gu.policy_params(pol)
+    for k, v in g.policy("pol1").items():
+        assert torch.allclose(pm[k], v.reshape(-1), rtol=1e-3, atol=2e-5), k
+    # the generator was consumed exactly as the reference consumes it
+    torch.set_rng_state(g.t("rng_before_ppo"))
+    for _ in range(g.ppo_epoch):
+        torch.randperm(g.S)
+    expect = torch.rand(4)
+    torch.set_rng_state(g.t("rng_before_ppo"))
+    pol2, agent2, rs2, _ = _ppo_objects(g, 0)
+    agent2.update(rs2)
+    assert torch.equal(torch.rand(4), expect)
+
+
+def test_ppo_modes_bit_identical():
+    g = Golden(CASES[0])
+    outs = []
+    for mode in (0, 1):
+        pol, agent, rs, _ = _ppo_objects(g, mode)
+        agent.update(rs, permutations=g.t("ppo_perm"))
+        outs.append((agent.last_trace.clone(), pol.flat_params().cpu().clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
+def test_ppo_lr_schedule_and_step_count():
+    from simgan_b200.utils import update_linear_schedule
+    g = Golden(CASES[0])
+    pol, agent, rs, buf = _ppo_objects(g, 0)
+    ora = orc.PPOOracle(g.policy(), g.hyper())
+    for j in range(2):
+        update_linear_schedule(agent.optimizer, j, 4, 3e-4)
+        update_linear_schedule(ora.optimizer, j, 4, 3e-4)
+        out = agent.update(rs, permutations=g.t("ppo_perm"))
+        out_o = ora.update(buf, index_chunks=g.ppo_chunks())
+        assert abs(out[0] - out_o[0]) <= 2e-4 * abs(out_o[0])
+    assert agent.optimizer.step_count == 2 * g.ppo_epoch * g.nmb
+
+
+# ------------------------------------------------------------------------------------------- discriminator
+def _disc_objects(g, mode):
+    from torch.utils.data import DataLoader, TensorDataset
+    d = gu.make_disc(g.disc(), g.F, g.HD)
+    d.kernel_mode = mode
+    buf = g.buffer()
+    rs = gu.make_storage(buf, g.O, g.A, g.F)
+    expert = g.t("expert")
+    loader = DataLoader(TensorDataset(expert.to(gu.DEV)), batch_size=g.gail_batch, shuffle=True,
+                        drop_last=len(expert) > g.gail_batch)
+    return d, rs, buf, expert, loader
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("mode", [1, 0])
+def test_disc_update_vs_oracle(case, mode):
+    g = Golden(case)
+    d, rs, buf, expert, loader = _disc_objects(g, mode)
+    ora = orc.DiscOracle(g.disc())
+    for e in range(g.gail_epoch):
+        trace = []
+        out_o = ora.update_epoch(expert, buf, batch_size=g.gail_batch, replay=g.disc_replay(e), trace=trace)
+        out = d.update_gail_dyn(loader, rs, replay=g.disc_replay(e))
+        tr, tr_o = d.last_trace.double().numpy(), np.array(trace)
+        if e == 0:
+            assert np.all(np.abs(tr[0] - tr_o[0]) <= 1e-5 * np.abs(tr_o[0])), (tr[0], tr_o[0])
+        assert np.all(np.abs(tr - tr_o) <= 2e-4 * np.abs(tr_o) + 1e-6), (np.abs(tr - tr_o) / np.abs(tr_o)).max(axis=0)
+        for i in range(3):
+            assert abs(out[i] - out_o[i]) <= LOSS_RTOL * abs(out_o[i])
+    pm, po = gu.disc_params(d), ora.params()
+    for k in orc.DISC_KEYS:
+        assert torch.allclose(pm[k], po[k].reshape(-1), rtol=2e-3, atol=5e-5), k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_disc_update_golden_rng(case):
+    """Drop-in call with the caller's DataLoader: index streams and alphas come from the CPU generator."""
+    g = Golden(case)
+    d, rs, buf, expert, loader = _disc_objects(g, 0)
+    torch.set_rng_state(g.t("rng_before_disc"))
+    outs = [d.update_gail_dyn(loader, rs) for _ in range(g.gail_epoch)]
+    ref = g.z["disc_losses"]
+    assert np.all(np.abs(np.array(outs) - ref) <= LOSS_RTOL * np.abs(ref)), (outs, ref)
+    after = torch.rand(4)
+    # reference consumption of the generator: replay with the real DataLoader + oracle sampler
+    torch.set_rng_state(g.t("rng_before_disc"))
+    for _ in range(g.gail_epoch):
+        n = 0
+        pol_chunks = None
+        for eb in loader:
+            if pol_chunks is None:
+                pol_chunks = orc.sampler_chunks(g.S, g.gail_batch)
+            if n >= len(pol_chunks):
+                break
+            torch.rand(g.gail_batch, 1)
+            n += 1
+    assert torch.equal(torch.rand(4), after)
+    pm = gu.disc_params(d)
+    for k, v in g.disc("disc1").items():
+        assert torch.allclose(pm[k], v.reshape(-1), rtol=2e-3, atol=5e-5), k
+
+
+def test_disc_modes_bit_identical():
+    g = Golden(CASES[0])
+    outs = []
+    for mode in (0, 1):
+        d, rs, buf, expert, loader = _disc_objects(g, mode)
+        d.update_gail_dyn(loader, rs, replay=g.disc_replay(0))
+        outs.append((d.last_trace.clone(), d.flat_params().cpu().clone()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
+# ------------------------------------------------------------------------------------------ reward relabel
+@pytest.mark.parametrize("case", CASES)
+def test_relabel_normalize_bitexact(case):
+    """Everything after the discriminator forward is integer-like bookkeeping in fixed arithmetic: feed the
+    reference's own raw rewards and require bit-identical rewards, returns and float64 RMS state."""
+    from simgan_b200 import _lib
+    g = Golden(case)
+    T, N = g.T, g.N
+    lib = _lib.lib()
+    raw = g.t("relabel_raw_reward").reshape(T, N).contiguous().to(gu.DEV)
+    masks = g.buffer()["masks"].to(gu.DEV)
+    rewards = torch.empty(T, N, 1, device=gu.DEV)
+    dret = torch.zeros(N, 1, device=gu.DEV)
+    rms = torch.tensor([0.0, 1.0, 1e-4], dtype=torch.float64, device=gu.DEV)
+    mret = torch.empty(T, device=gu.DEV)
+    ws = torch.empty(int(lib.sg_relabel_workspace_bytes(T, N)), dtype=torch.uint8, device=gu.DEV)
+    _lib.check(lib.sg_relabel_normalize(_lib.ptr(raw), _lib.ptr(masks), _lib.ptr(rewards), T, N, 0.99, _lib.ptr(dret), 0,
+                                        _lib.ptr(rms), _lib.ptr(mret), _lib.ptr(ws), _lib.current_stream()))
+    assert torch.equal(rewards.cpu(), g.t("relabel_rewards"))
+    assert torch.equal(dret.cpu(), g.t("relabel_disc_returns"))
+    assert np.array_equal(rms.cpu().numpy(), g.z["relabel_rms"])
+    assert np.allclose(mret.cpu().double().numpy(), g.z["relabel_mean_returns"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_relabel_rollout_vs_golden(case):
+    """Full relabel incl. the discriminator forward (fp32 transcendental differences allowed)."""
+    g = Golden(case)
+    d = gu.make_disc(g.disc("disc1"), g.F, g.HD)
+    rs = gu.make_storage(g.buffer(), g.O, g.A, g.F)
+    rms = sg.RunningMeanStd(shape=())
+    r_sa = float(g.z["r_sa"])
+    from simgan_b200.algo.gail import alive_bonus_offset
+    assert alive_bonus_offset(rs.masks, g.T, g.N, float(g.z["gail_tar_length"])) == r_sa
+    mret = d.relabel_rollout(rs, 0.99, -r_sa, rms)
+    ref = g.t("relabel_rewards")
+    assert float((rs.rewards.cpu() - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+    assert gu.rel_err(d.returns.cpu(), g.t("relabel_disc_returns")) <= 1e-4
+    assert abs(float(rms.var) - g.z["relabel_rms"][1]) <= 1e-4 * g.z["relabel_rms"][1]
+    assert float(rms.count) == g.z["relabel_rms"][2]
+    # per-step API gives the same stream (slow path used by an unmodified main loop)
+    d2 = gu.make_disc(g.disc("disc1"), g.F, g.HD)
+    rs2 = gu.make_storage(g.buffer(), g.O, g.A, g.F)
+    for t in range(min(g.T, 6)):
+        rew, ret = d2.predict_reward_combined(rs2.obs_feat[t + 1], 0.99, rs2.masks[t], offset=-r_sa)
+        assert gu.rel_err(rew.cpu(), g.t("relabel_raw_reward")[t]) <= 1e-4
+    # second pass keeps state (returns / rms persist across iterations)
+    d.relabel_rollout(rs, 0.99, -r_sa, rms)
+    assert float(rms.count) == g.z["relabel_rms"][2] + g.S
+
+
+# ---------------------------------------------------------------------------------------- whole update phase
+@pytest.mark.parametrize("case", CASES)
+def test_full_update_phase_dropin(case):
+    """D-update x E -> relabel -> GAE -> PPO.update through the reference-shaped classes, consuming the CPU
+    generator from the recorded state, against the REAL reference's outputs (golden)."""
+    from torch.utils.data import DataLoader, TensorDataset
+    g = Golden(case)
+    pol = gu.make_policy(g.policy(), g.O, g.H, g.A)
+    agent = sg.PPO(pol, 0.2, g.ppo_epoch, g.nmb, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    d = gu.make_disc(g.disc(), g.F, g.HD)
+    rs = gu.make_storage(g.buffer(), g.O, g.A, g.F)
+    expert = g.t("expert").to(gu.DEV)
+    loader = DataLoader(TensorDataset(expert), batch_size=g.gail_batch, shuffle=True, drop_last=len(expert) > g.gail_batch)
+    with torch.no_grad():
+        next_value = pol.get_value(rs.obs[-1], rs.recurrent_hidden_states[-1], rs.masks[-1]).detach()
+    assert gu.rel_err(next_value.cpu(), g.t("next_value")) < 2e-6
+    torch.set_rng_state(g.t("rng_before_disc"))
+    for _ in range(g.gail_epoch):
+        dl = d.update_gail_dyn(loader, rs)
+    assert np.all(np.abs(np.array(dl) - g.z["disc_losses"][-1]) <= LOSS_RTOL * np.abs(g.z["disc_losses"][-1]))
+    rms = sg.RunningMeanStd(shape=())
+    d.relabel_rollout(rs, 0.99, -float(g.z["r_sa"]), rms)
+    rs.compute_returns(next_value, True, 0.99, 0.95, True)
+    ref_ret = g.t("gae_returns")
+    assert float((rs.returns.cpu() - ref_ret)[:-1].abs().max()) <= 2e-4 * float(ref_ret.abs().max())
+    out = agent.update(rs)
+    ref = g.z["ppo_losses"]
+    assert abs(out[0] - ref[0]) <= 5e-4 * abs(ref[0])
+    assert abs(out[2] - ref[2]) <= 1e-4 * abs(ref[2])
+    rs.after_update()
+    assert torch.equal(rs.obs[0], rs.obs[-1])
