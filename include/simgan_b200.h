@@ -31,6 +31,9 @@ extern "C" {
 
 const char* sg_last_error(void);
 int sg_version(void);
+/* Number of CUDA kernel launches this library has issued in this process (monotonic; bench.py reads
+ * it before/after the timed region to report gpu_launches). */
+long long sg_launch_count(void);
 /* SM count / cooperative-launch capability of the current device (0 if no device). */
 int sg_device_sm_count(void);
 

@@ -41,6 +41,7 @@ ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
 SIGNATURES = {
     "sg_last_error": (C.c_char_p, []),
     "sg_version": (C.c_int, []),
+    "sg_launch_count": (C.c_longlong, []),
     "sg_device_sm_count": (C.c_int, []),
     "sg_policy_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "sg_disc_layout": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int)]),
@@ -112,6 +113,41 @@ def disc_layout(feat_dim, hidden):
     if total < 0:
         check(1, "sg_disc_layout")
     return list(offs), total
+
+
+class KernelTimer(object):
+    """Optional CUDA-event timing of the hot-path launches, on the stream they are launched on.
+    bench.py enables it to attribute the timed region to kernels (roofline.achieved); disabled (the
+    default) it costs nothing."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []        # (name, start_event, end_event)
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        self.records.append((name, s, e))
+        return e
+
+    @staticmethod
+    def stop(token):
+        if token is not None:
+            token.record()
+
+    def drain(self):
+        """{name: [ms, ...]} for every finished record; clears the list (caller synchronises first)."""
+        out = {}
+        for name, s, e in self.records:
+            out.setdefault(name, []).append(s.elapsed_time(e))
+        self.records = []
+        return out
+
+
+timer = KernelTimer()
 
 
 def current_stream():

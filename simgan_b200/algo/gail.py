@@ -139,10 +139,12 @@ class Discriminator(nn.Module):
         cb, user = _lib.NULL_ALLREDUCE, None
         if self.dp is not None:
             cb = self.dp.make_callback(ws)
+        tok = _lib.timer.start("disc_update")
         rc = lib.sg_disc_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(expert),
                                 _lib.ptr(policy_feat), _lib.ptr(idx_dev[0]), _lib.ptr(idx_dev[1]), _lib.ptr(alpha_dev),
                                 _lib.ptr(sched[0]), _lib.ptr(sched[1]), _lib.ptr(trace), _lib.ptr(ws), cb, user,
                                 _lib.current_stream())
+        _lib.timer.stop(tok)
         _lib.check(rc, "sg_disc_update")
         opt.step_count += n
         tr = trace.cpu()
@@ -261,10 +263,12 @@ class Discriminator(nn.Module):
         rms_dev = torch.tensor([float(ret_rms.mean), float(ret_rms.var), float(ret_rms.count)], dtype=torch.float64,
                                device=dev)
         mean_returns = torch.empty(T, device=dev)
+        tok = _lib.timer.start("disc_relabel")
         rc = lib.sg_disc_relabel(_lib.ptr(flat), self.feat_dim, self.hidden_dim, _lib.ptr(rollouts.obs_feat),
                                  _lib.ptr(rollouts.masks), _lib.ptr(rollouts.rewards), T, N, float(gamma), float(offset),
                                  _lib.ptr(self.returns), int(has), _lib.ptr(rms_dev), _lib.ptr(mean_returns),
                                  _lib.ptr(ws), _lib.current_stream())
+        _lib.timer.stop(tok)
         _lib.check(rc, "sg_disc_relabel")
         self.__dict__["_rms_dev"] = rms_dev
         if sync:

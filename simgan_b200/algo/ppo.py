@@ -114,10 +114,12 @@ class PPO(object):
         cb, user = _lib.NULL_ALLREDUCE, None
         if self.dp is not None:
             cb = self.dp.make_callback(ws)
+        tok = _lib.timer.start("ppo_update")
         rc = lib.sg_ppo_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
                                _lib.ptr(rollouts.actions), _lib.ptr(rollouts.value_preds), _lib.ptr(rollouts.returns),
                                _lib.ptr(rollouts.action_log_probs), _lib.ptr(stats), _lib.ptr(perm),
                                _lib.ptr(sched[0]), _lib.ptr(sched[1]), _lib.ptr(trace), _lib.ptr(ws), cb, user, stream)
+        _lib.timer.stop(tok)
         _lib.check(rc, "sg_ppo_update")
         opt.step_count += n_steps
 

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "sg_common.cuh"
 
 namespace sg {
@@ -13,6 +15,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return SG_OK;
@@ -27,6 +33,8 @@ extern "C" {
 const char* sg_last_error(void) { return sg::g_err; }
 
 int sg_version(void) { return 100; }
+
+long long sg_launch_count(void) { return sg::launches(); }
 
 int sg_device_sm_count(void) {
     int dev = 0, n = 0;

@@ -22,6 +22,7 @@ namespace sg {
 
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void count_launches(int n);   // kernel launches issued by this library (sg_launch_count)
 
 #define SG_CUDA(call)                                      \
     do {                                                   \

@@ -483,6 +483,7 @@ static int launch_reward(const float* params, int F, int H, const float* d_in, i
     int tiles = (n_rows + kRows - 1) / kRows;
     int grid = tiles < 1184 ? tiles : 1184;
     disc_reward_kernel<<<grid, kStepThreads, smem, s>>>(params, L, F, H, d_in, n_rows, offset, reward, returns, masks, gamma, has_returns);
+    count_launches(1);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
@@ -537,6 +538,7 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
         SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_disc_update: cooperative grid of %d CTAs does not fit", grid);
         void* kargs[] = {(void*)&a};
         SG_CUDA(cudaLaunchCooperativeKernel((const void*)disc_persistent_kernel, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+        count_launches(1);
     } else {
         SG_CUDA(cudaFuncSetAttribute(disc_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int g2 = (a.P + kStepThreads - 1) / kStepThreads;
@@ -548,6 +550,7 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
                 SG_REQUIRE(cb == 0, "sg_disc_update: allreduce callback failed with %d at step %d", cb, step);
             }
             disc_phase3_kernel<<<g2, kStepThreads, 0, s>>>(a, step);
+            count_launches(3);
         }
         SG_CUDA(cudaGetLastError());
     }
@@ -582,6 +585,7 @@ static int relabel_from_raw(const float* raw, const float* masks, float* rewards
     int blocks = (int)((total + 255) / 256);
     if (blocks > 1184) blocks = 1184;
     relabel_apply_kernel<<<blocks, 256, 0, s>>>(raw, scale, rewards, T, N);
+    count_launches(4);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }

@@ -386,6 +386,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
         SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_ppo_update: cooperative grid of %d CTAs does not fit", grid);
         void* kargs[] = {(void*)&a};
         SG_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_persistent_kernel<kRows>, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+        count_launches(1);
     } else {
         SG_CUDA(cudaFuncSetAttribute(ppo_phase1_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int g2 = (a.P + kStepThreads - 1) / kStepThreads;
@@ -397,6 +398,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
                 SG_REQUIRE(cb == 0, "sg_ppo_update: allreduce callback failed with %d at step %d", cb, step);
             }
             ppo_phase3_kernel<<<g2, kStepThreads, 0, s>>>(a, step);
+            count_launches(3);
         }
         SG_CUDA(cudaGetLastError());
     }

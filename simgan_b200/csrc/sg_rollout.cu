@@ -197,6 +197,7 @@ int sg_compute_returns(const float* rewards, float* value_preds, const float* ma
         case 2: returns_scan_kernel<2><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
         default: returns_scan_kernel<3><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
     }
+    count_launches(1);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
@@ -210,6 +211,7 @@ int sg_adv_stats(const float* returns, const float* value_preds, int S, float* o
     if (blocks > kStatBlocks) blocks = kStatBlocks;
     adv_partial_kernel<<<blocks, 256, 0, s>>>(returns, value_preds, S, (double*)workspace);
     adv_final_kernel<<<1, 32, 0, s>>>((const double*)workspace, blocks, S, out_stats);
+    count_launches(2);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
@@ -231,6 +233,7 @@ int sg_gather_rows(const float* const* h_src, float* const* h_dst, const int* h_
     int bx = (int)((total + 255) / 256);
     if (bx > 1184) bx = 1184;
     gather_rows_kernel<<<dim3(bx, n_tensors), 256, 0, (cudaStream_t)stream>>>(a, idx, n_rows);
+    count_launches(1);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
@@ -248,6 +251,7 @@ int sg_copy_blocks(const float* const* h_src, float* const* h_dst, const int* h_
     int bx = (maxc + 255) / 256;
     if (bx > 592) bx = 592;
     copy_blocks_kernel<<<dim3(bx, n_copies), 256, 0, (cudaStream_t)stream>>>(a);
+    count_launches(1);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }
@@ -268,6 +272,7 @@ int sg_policy_forward(const float* params, int obs_dim, int hidden, int act_dim,
     int grid = tiles < 1184 ? tiles : 1184;
     policy_forward_kernel<kRows><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(params, L, obs_dim, hidden, act_dim, obs, B,
                                                                                      noise, actions_in, value, action, logp, entropy);
+    count_launches(1);
     SG_CUDA(cudaGetLastError());
     return SG_OK;
 }

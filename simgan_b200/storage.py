@@ -102,10 +102,12 @@ class RolloutStorage(object):
         _require_cuda(self.rewards, "compute_returns")
         T, N = self.rewards.shape[:2]
         nv = next_value.detach().to(device=self.rewards.device, dtype=torch.float32).contiguous()
+        tok = _lib.timer.start("compute_returns")
         rc = _lib.lib().sg_compute_returns(_lib.ptr(self.rewards), _lib.ptr(self.value_preds), _lib.ptr(self.masks),
                                            _lib.ptr(self.bad_masks), _lib.ptr(self.returns), _lib.ptr(nv), T, N,
                                            float(gamma), float(gae_lambda), int(bool(use_gae)),
                                            int(bool(use_proper_time_limits)), _lib.current_stream())
+        _lib.timer.stop(tok)
         _lib.check(rc, "sg_compute_returns")
 
     # ---- minibatch sampler -----------------------------------------------------------------------------

@@ -43,6 +43,8 @@ def make_storage(buf, O, A, F):
     return rs
 
 
-def rel_err(a, b):
+def rel_err(a, b, floor=1e-30):
+    """max |a-b| relative to max |b|; ``floor`` is the natural scale of the quantity (keeps a batch whose
+    values happen to cancel to ~0 from turning fp32 rounding into a huge relative error)."""
     a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
-    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    return float((a - b).abs().max() / b.abs().max().clamp_min(floor))

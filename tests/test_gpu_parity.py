@@ -135,14 +135,14 @@ def test_policy_forward(case, B):
     v_o, lp_o, ent_o = orc.policy_evaluate(p, x, act)
     with torch.no_grad():
         v, lp, ent, _ = pol.evaluate_actions(x.to(gu.DEV), None, None, act.to(gu.DEV))
-    assert gu.rel_err(v.cpu(), v_o) < 2e-6
+    assert gu.rel_err(v.cpu(), v_o, floor=0.5) < 2e-6      # value = 64-term dot product of O(1) terms
     assert gu.rel_err(lp.cpu(), lp_o) < 2e-6
     assert abs(float(ent) - float(ent_o)) < 2e-6 * abs(float(ent_o))
-    assert gu.rel_err(pol.get_value(x.to(gu.DEV), None, None).cpu(), v_o) < 2e-6
+    assert gu.rel_err(pol.get_value(x.to(gu.DEV), None, None).cpu(), v_o, floor=0.5) < 2e-6
     # deterministic act = mean
     v_d, a_d, lp_d = orc.policy_act(p, x, deterministic=True)
     v2, a2, lp2, _ = pol.act(x.to(gu.DEV), None, None, deterministic=True)
-    assert gu.rel_err(a2.cpu(), a_d) < 2e-6 and gu.rel_err(lp2.cpu(), lp_d) < 2e-6
+    assert gu.rel_err(a2.cpu(), a_d, floor=0.05) < 2e-6 and gu.rel_err(lp2.cpu(), lp_d) < 2e-6
     # sampled act: same CUDA-generator stream as torch.normal(mean, std) in the reference's Normal.sample()
     torch.cuda.manual_seed(5)
     v3, a3, lp3, _ = pol.act(x.to(gu.DEV), None, None)
