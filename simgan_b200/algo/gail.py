@@ -177,7 +177,8 @@ class Discriminator(nn.Module):
             e_idx, p_idx, alpha = self.draw_epoch_indices(expert.shape[0], expert_loader.batch_size,
                                                           bool(expert_loader.drop_last), S)
         else:
-            e_idx, p_idx, alpha = [torch.as_tensor(x) for x in replay]
+            e_idx, p_idx, alpha = [x if torch.is_tensor(x) else torch.stack([torch.as_tensor(r).reshape(-1) for r in x])
+                                   for x in replay]
         return self._run_update(expert, policy_feat, e_idx, p_idx, alpha)
 
     def update(self, expert_loader, rollouts, obsfilt=None, is_gail_dyn=False, a_dim=None):

@@ -183,6 +183,7 @@ def test_ppo_per_step_trace_vs_oracle(case, mode):
     tr = agent.last_trace.double().numpy()
     tr_o = np.array(trace)
     scale = np.abs(tr_o).max(axis=0)
+    scale[1] = max(scale[1], 0.5)      # action loss = mean of cancelling ratio*adv terms of magnitude E|adv| ~ 0.8
     # first step: identical state on both sides -> tight
     assert np.all(np.abs(tr[0] - tr_o[0]) <= 5e-6 * scale + 1e-7), (tr[0], tr_o[0])
     # all steps (fp32 reassociation compounds through Adam)
@@ -215,8 +216,8 @@ def test_ppo_update_golden_rng(case):
     for _ in range(g.ppo_epoch):
         torch.randperm(g.S)
     expect = torch.rand(4)
+    pol2, agent2, rs2, _ = _ppo_objects(g, 0)      # construction itself draws from the CPU generator
     torch.set_rng_state(g.t("rng_before_ppo"))
-    pol2, agent2, rs2, _ = _ppo_objects(g, 0)
     agent2.update(rs2)
     assert torch.equal(torch.rand(4), expect)
 
