@@ -47,6 +47,18 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float4 ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
+// Where a kernel reads the network weights from.  LdGlobal: flat parameter vector in global memory, read
+// through L2 (ld.global.cg) because the Adam phase of the same persistent kernel rewrites it between
+// steps.  LdShared: a CTA-private image of the flat vector in shared memory ("resident" kernels).
+struct LdGlobal {
+    static __device__ __forceinline__ float ld(const float* p) { return __ldcg(p); }
+    static __device__ __forceinline__ float4 ld4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+};
+struct LdShared {
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -65,7 +77,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 //   a butterfly reduce-scatter leaves every lane with one output and R/2 rows.
 //   V = 4 needs K % 4 == 0 and 16-byte aligned W rows; V = 1 handles any K.
 // ------------------------------------------------------------------------------------------------
-template <int R, int V, class Epi>
+template <int R, int V, class WL = LdGlobal, class Epi>
 __device__ __forceinline__ void gemm_xwT(const float* __restrict__ W, const float* __restrict__ X, int ldx,
                                          int N, int K, int t, int nth, Epi epi) {
     static_assert(R % 2 == 0, "R must be even");
@@ -87,10 +99,10 @@ __device__ __forceinline__ void gemm_xwT(const float* __restrict__ W, const floa
                 for (int i = 0; i < NT; ++i) {
                     if (n0 + i < N) {
                         if (V == 4) {
-                            float4 q = ld_cg4(W + (size_t)(n0 + i) * K + k);
+                            float4 q = WL::ld4(W + (size_t)(n0 + i) * K + k);
                             w[i][0] = q.x; w[i][1 % V] = q.y; w[i][2 % V] = q.z; w[i][3 % V] = q.w;
                         } else {
-                            w[i][0] = ld_cg(W + (size_t)(n0 + i) * K + k);
+                            w[i][0] = WL::ld(W + (size_t)(n0 + i) * K + k);
                         }
                     } else {
 #pragma unroll
@@ -166,7 +178,7 @@ __device__ __forceinline__ void load_rows_t(const float* __restrict__ Yt, int n,
 //   (>= nth*R*V floats of shared memory) and are reduced after a CTA-wide barrier.
 //   ALL threads of the CTA must call (contains __syncthreads); `sync_after` adds the trailing one.
 // ------------------------------------------------------------------------------------------------
-template <int R, int V, class Epi>
+template <int R, int V, class WL = LdGlobal, class Epi>
 __device__ __forceinline__ void gemm_yW(const float* __restrict__ W, const float* __restrict__ Yt, int N, int K,
                                         float* __restrict__ scratch, int t, int nth, Epi epi) {
     const int KC = (K + V - 1) / V;              // V==4 requires K%4==0
@@ -187,10 +199,10 @@ __device__ __forceinline__ void gemm_yW(const float* __restrict__ W, const float
             for (int n = ns * Nper; n < n_end; ++n) {
                 float w[V];
                 if (V == 4) {
-                    float4 q = ld_cg4(W + (size_t)n * K + kc * 4);
+                    float4 q = WL::ld4(W + (size_t)n * K + kc * 4);
                     w[0] = q.x; w[1 % V] = q.y; w[2 % V] = q.z; w[3 % V] = q.w;
                 } else {
-                    w[0] = ld_cg(W + (size_t)n * K + kc);
+                    w[0] = WL::ld(W + (size_t)n * K + kc);
                 }
                 float y[R];
                 load_rows_t<R>(Yt, n, y);
@@ -283,6 +295,9 @@ __device__ __forceinline__ void rowsum_store(float* __restrict__ g, const float*
 // ------------------------------------------------------------------------------------------------
 // Grid-wide barrier for cooperative (co-resident) launches: monotonically increasing arrival counter.
 // `*counter` must be zero at kernel start.  `gen` is the per-thread-0 generation count.
+// Arrive = red.release.gpu after the CTA barrier (cumulative: publishes every thread's prior writes),
+// wait = ld.acquire.gpu spin by thread 0 followed by the CTA barrier.  Data exchanged across the
+// barrier is written with st.cg and read with ld.cg (L2), so no L1 invalidation is needed.
 // A spin cap turns a lost barrier into an error flag instead of a hung GPU.
 // ------------------------------------------------------------------------------------------------
 struct GridBarrier {
@@ -295,23 +310,92 @@ struct GridBarrier {
         if (threadIdx.x == 0) {
             gen += 1;
             const unsigned int target = gen * nblocks;
-            __threadfence();
-            atomicAdd(counter, 1u);
+            asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
             unsigned int seen;
             long long spins = 0;
             // once any barrier has timed out every later one falls through: the kernel drains quickly and
             // the host sees the poisoned trace
-            bool dead = *(volatile unsigned int*)error_flag != 0u;
-            while (!dead) {
+            bool dead = false;
+            while (true) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
                 if (seen >= target) break;
-                if (++spins > (1ll << 22)) { atomicExch(error_flag, 1u); dead = true; }
+                if ((++spins & 1023) == 0) {
+                    if (*(volatile unsigned int*)error_flag != 0u) dead = true;
+                    if (spins > (1ll << 22)) { atomicExch(error_flag, 1u); dead = true; }
+                    if (dead) break;
+                }
             }
-            __threadfence();
         }
         __syncthreads();
     }
 };
+
+// Deterministic CTA-wide sum of one double per thread (256 threads): xor-butterfly inside each warp,
+// then the 8 warp sums added in warp order by every thread.  `red` = 8 doubles of shared memory.
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();                       // protects `red` against the previous use
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    return tot;
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// Sum of `nslots` partial vectors over the float range [p0,p1) (both multiples of 4):
+// out[p] = sum_c part[c*stride + p] in a fixed order.  All 256 threads of the CTA must call.
+// `scr4` = 256 float4 of shared memory.  Ends with a CTA barrier (the slice of `out` is visible to the
+// whole CTA through L2 afterwards).
+__device__ __forceinline__ void reduce_partials_slice(const float* __restrict__ part, size_t stride, int nslots, int p0,
+                                                      int p1, float* __restrict__ out, float4* scr4, int tid) {
+    const int n4 = (p1 - p0) >> 2;
+    if (n4 <= 0) { __syncthreads(); return; }
+    if (n4 <= 128) {
+        const int NQ = 256 / n4;
+        const int j = tid % n4, q = tid / n4;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < NQ) {
+            const float* src = part + p0 + 4 * j;
+            int c = q;
+            for (; c + 3 * NQ < nslots; c += 4 * NQ) {      // four independent L2 loads in flight
+                const float4 v0 = ld_cg4(src + (size_t)c * stride);
+                const float4 v1 = ld_cg4(src + (size_t)(c + NQ) * stride);
+                const float4 v2 = ld_cg4(src + (size_t)(c + 2 * NQ) * stride);
+                const float4 v3 = ld_cg4(src + (size_t)(c + 3 * NQ) * stride);
+                s = f4_add(f4_add(f4_add(f4_add(s, v0), v1), v2), v3);
+            }
+            for (; c < nslots; c += NQ) s = f4_add(s, ld_cg4(src + (size_t)c * stride));
+            scr4[q * n4 + j] = s;
+        }
+        __syncthreads();
+        if (tid < n4) {
+            float4 t = scr4[tid];
+            for (int qq = 1; qq < NQ; ++qq) t = f4_add(t, scr4[qq * n4 + tid]);
+            __stcg(reinterpret_cast<float4*>(out + p0 + 4 * tid), t);
+        }
+        __syncthreads();
+    } else {
+        // wide slices (large networks): every thread owns whole columns
+        for (int j = tid; j < n4; j += 256) {
+            const float* src = part + p0 + 4 * j;
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+            int c = 0;
+            for (; c + 3 < nslots; c += 4) {
+                const float4 v0 = ld_cg4(src + (size_t)c * stride);
+                const float4 v1 = ld_cg4(src + (size_t)(c + 1) * stride);
+                const float4 v2 = ld_cg4(src + (size_t)(c + 2) * stride);
+                const float4 v3 = ld_cg4(src + (size_t)(c + 3) * stride);
+                s = f4_add(f4_add(f4_add(f4_add(s, v0), v1), v2), v3);
+            }
+            for (; c < nslots; ++c) s = f4_add(s, ld_cg4(src + (size_t)c * stride));
+            __stcg(reinterpret_cast<float4*>(out + p0 + 4 * j), s);
+        }
+        __syncthreads();
+    }
+}
 
 // flat policy layout (segment starts in floats), mirrored by sg_policy_layout()
 struct PolicyLayout {

@@ -3,7 +3,13 @@
 //   sg_disc_update          update_gail_dyn (gail.py:154-193): BCE-with-logits on expert (label 1) and
 //                           policy (label 0) rows + the WGAN-GP style gradient penalty on mixup rows
 //                           (gail.py:67-89) with a HAND-DERIVED double backward (no autograd in a kernel),
-//                           + Adam.  One persistent cooperative kernel runs all minibatches of an epoch.
+//                           + Adam.  One persistent cooperative kernel runs all minibatches of an epoch:
+//                           phase A (tile: forward / double backward -> per-CTA partial gradient), grid
+//                           barrier, phase B (CTA c sums slice c of the partials in a fixed order and
+//                           applies Adam to that slice -- the discriminator has no gradient clipping, so
+//                           no global norm is needed), grid barrier.  In the "resident" variant (mode 0
+//                           when it fits in shared memory) every CTA then refreshes a private shared-memory
+//                           image of the parameters and reads its weights from there in the tile phase.
 //   sg_disc_predict_reward  predict_reward_combined (gail.py:201-210) for one (N,F) block
 //   sg_disc_relabel         the whole T-step relabel loop of main_gail_dyn_ppo.py:275-297, including the
 //                           float64 RunningMeanStd merge (baselines/common/running_mean_std.py:33-56),
@@ -24,7 +30,7 @@ constexpr int kTB = 2;            // (expert, policy, mixup) triples per CTA til
 constexpr int kDR = 4 * kTB;      // row slots of a tile: [expert | policy | mixup | penalty-pair]
 
 struct DiscArgs {
-    int F, H, P, B, nsteps, row_begin, row_end, ntiles, nslots;
+    int F, H, P, B, nsteps, row_begin, row_end, ntiles, nslots, SL;
     float gp_lambda, one_minus_b1, b2, one_minus_b2, eps;
     DiscLayout L;
     float *params, *m, *v;
@@ -67,28 +73,29 @@ __device__ __forceinline__ float softplusf(float z) { return fmaxf(z, 0.f) + log
 __device__ __forceinline__ float sigmoidf(float z) { return __fdiv_rn(1.f, 1.f + expf(-z)); }
 
 // forward trunk for the rows of X (row-major [R][ldf]) -> H1, H2 (row-major) and logits D
-template <int R>
+template <int R, class WL>
 __device__ __forceinline__ void disc_tile_forward(const float* __restrict__ params, const DiscLayout& L, int F, int H,
                                                   const float* X, int ldf, float* H1, float* H2, int ldh, float* D, int tid) {
     const float* W1 = params + L.w1; const float* B1 = params + L.b1;
     const float* W2 = params + L.w2; const float* B2 = params + L.b2;
     const float* W3 = params + L.w3; const float* B3 = params + L.b3;
-    auto e1 = [&](int r, int n, float s) { H1[r * ldh + n] = tanhf(s + ld_cg(B1 + n)); };
-    if ((F & 3) == 0) gemm_xwT<R, 4>(W1, X, ldf, H, F, tid, kStepThreads, e1);
-    else gemm_xwT<R, 1>(W1, X, ldf, H, F, tid, kStepThreads, e1);
+    auto e1 = [&](int r, int n, float s) { H1[r * ldh + n] = tanhf(s + WL::ld(B1 + n)); };
+    if ((F & 3) == 0) gemm_xwT<R, 4, WL>(W1, X, ldf, H, F, tid, kStepThreads, e1);
+    else gemm_xwT<R, 1, WL>(W1, X, ldf, H, F, tid, kStepThreads, e1);
     __syncthreads();
-    auto e2 = [&](int r, int n, float s) { H2[r * ldh + n] = tanhf(s + ld_cg(B2 + n)); };
-    if ((H & 3) == 0) gemm_xwT<R, 4>(W2, H1, ldh, H, H, tid, kStepThreads, e2);
-    else gemm_xwT<R, 1>(W2, H1, ldh, H, H, tid, kStepThreads, e2);
+    auto e2 = [&](int r, int n, float s) { H2[r * ldh + n] = tanhf(s + WL::ld(B2 + n)); };
+    if ((H & 3) == 0) gemm_xwT<R, 4, WL>(W2, H1, ldh, H, H, tid, kStepThreads, e2);
+    else gemm_xwT<R, 1, WL>(W2, H1, ldh, H, H, tid, kStepThreads, e2);
     __syncthreads();
-    auto e3 = [&](int r, int n, float s) { D[r] = s + ld_cg(B3); };
-    if ((H & 3) == 0) gemm_xwT<R, 4>(W3, H2, ldh, 1, H, tid, kStepThreads, e3);
-    else gemm_xwT<R, 1>(W3, H2, ldh, 1, H, tid, kStepThreads, e3);
+    auto e3 = [&](int r, int n, float s) { D[r] = s + WL::ld(B3); };
+    if ((H & 3) == 0) gemm_xwT<R, 4, WL>(W3, H2, ldh, 1, H, tid, kStepThreads, e3);
+    else gemm_xwT<R, 1, WL>(W3, H2, ldh, 1, H, tid, kStepThreads, e3);
     __syncthreads();
 }
 
-__device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                          DiscSmem& sm, bool acc) {
+template <class WL>
+__device__ void disc_tile(const DiscArgs& a, const float* __restrict__ W, int step, int tile, float* __restrict__ gout,
+                          float* __restrict__ lossout, DiscSmem& sm, bool acc) {
     constexpr int R = kDR, TB = kTB;
     const int tid = threadIdx.x, nth = kStepThreads;
     const int F = a.F, H = a.H, ldf = sm.ldf, ldh = sm.ldh;
@@ -98,7 +105,7 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
     const int32_t* pidx = a.pidx + (size_t)step * a.B;
     const float* alpha = a.alpha + (size_t)step * a.B;
     const float invB = 1.f / (float)a.B;
-    const float* W1 = a.params + a.L.w1; const float* W2 = a.params + a.L.w2; const float* W3 = a.params + a.L.w3;
+    const float* W1 = W + a.L.w1; const float* W2 = W + a.L.w2; const float* W3 = W + a.L.w3;
 
     // rows: [0,TB) expert, [TB,2TB) policy, [2TB,3TB) mixup = alpha*e + (1-alpha)*p (gail.py:72-75), rest zero
     for (int e = tid; e < R * ldf; e += nth) {
@@ -115,7 +122,7 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
         sm.X[e] = x;
     }
     __syncthreads();
-    disc_tile_forward<R>(a.params, a.L, F, H, sm.X, ldf, sm.H1, sm.H2, ldh, sm.D, tid);
+    disc_tile_forward<R, WL>(W, a.L, F, H, sm.X, ldf, sm.H1, sm.H2, ldh, sm.D, tid);
 
     // BCE-with-logits seeds (gail.py:171-176): expert target 1, policy target 0, both batch means
     if (tid < R) {
@@ -132,7 +139,7 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
         const int n = e / R, r = e - n * R;
         const int kind = r / TB;
         const float h2 = sm.H2[r * ldh + n];
-        const float w3 = ld_cg(W3 + n);
+        const float w3 = WL::ld(W3 + n);
         const float base = w3 * (1.f - h2 * h2);
         float y = 0.f;
         if (kind < 2) y = sm.DD[r] * base;
@@ -150,13 +157,13 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
         if (kind < 2) sm.L1t[k * R + r] = t1;                      // dz1
         else if (kind == 2) { sm.V1[j * ldh + k] = s; sm.U1x[k * TB + j] = t1; sm.L1t[k * R + r + TB] = t1; }  // u1 -> slot 3TB+j
     };
-    if (vecH) gemm_yW<R, 4>(W2, sm.Y2t, H, H, sm.SCR, tid, nth, epiA);
-    else gemm_yW<R, 1>(W2, sm.Y2t, H, H, sm.SCR, tid, nth, epiA);
+    if (vecH) gemm_yW<R, 4, WL>(W2, sm.Y2t, H, H, sm.SCR, tid, nth, epiA);
+    else gemm_yW<R, 1, WL>(W2, sm.Y2t, H, H, sm.SCR, tid, nth, epiA);
     // pass B: g = u1 . W1  (input gradient of the mixup rows) -> X rows 3TB+j (raw g for now)
     float* G = sm.X + 3 * TB * ldf;
     auto epiB = [&](int r, int k, float s) { G[r * ldf + k] = s; };
-    if (vecF) gemm_yW<TB, 4>(W1, sm.U1x, H, F, sm.SCR, tid, nth, epiB);
-    else gemm_yW<TB, 1>(W1, sm.U1x, H, F, sm.SCR, tid, nth, epiB);
+    if (vecF) gemm_yW<TB, 4, WL>(W1, sm.U1x, H, F, sm.SCR, tid, nth, epiB);
+    else gemm_yW<TB, 1, WL>(W1, sm.U1x, H, F, sm.SCR, tid, nth, epiB);
     // ||g||, penalty and gbar = (2 lambda / B)(n-1) g / n
     if (tid < 32 * TB) {
         const int j = tid >> 5, lane = tid & 31;
@@ -176,8 +183,8 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
         sm.H1[(3 * TB + r) * ldh + n] = s * (1.f - h1 * h1);                 // vb1
         sm.HB1[r * ldh + n] = -2.f * s * sm.V1[r * ldh + n] * h1;            // hb1
     };
-    if (vecF) gemm_xwT<TB, 4>(W1, G, ldf, H, F, tid, nth, epiC);
-    else gemm_xwT<TB, 1>(W1, G, ldf, H, F, tid, nth, epiC);
+    if (vecF) gemm_xwT<TB, 4, WL>(W1, G, ldf, H, F, tid, nth, epiC);
+    else gemm_xwT<TB, 1, WL>(W1, G, ldf, H, F, tid, nth, epiC);
     __syncthreads();
     // pass D: ub2 = vb1 . W2^T -> dw3 term, zb2
     const float* VB1 = sm.H1 + 3 * TB * ldh;
@@ -185,20 +192,20 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
         const float h2 = sm.H2[(2 * TB + r) * ldh + n];
         const float om = 1.f - h2 * h2;
         sm.C3[r * ldh + n] = s * om;
-        const float zb2 = -2.f * s * ld_cg(W3 + n) * h2 * om;
+        const float zb2 = -2.f * s * WL::ld(W3 + n) * h2 * om;
         sm.Z2x[n * TB + r] = zb2;
         sm.L2t[n * R + 2 * TB + r] = zb2;
     };
-    if (vecH) gemm_xwT<TB, 4>(W2, VB1, ldh, H, H, tid, nth, epiD);
-    else gemm_xwT<TB, 1>(W2, VB1, ldh, H, H, tid, nth, epiD);
+    if (vecH) gemm_xwT<TB, 4, WL>(W2, VB1, ldh, H, H, tid, nth, epiD);
+    else gemm_xwT<TB, 1, WL>(W2, VB1, ldh, H, H, tid, nth, epiD);
     __syncthreads();
     // pass E: hb1 += zb2 . W2 ; zb1 = hb1*(1-h1^2)
     auto epiE = [&](int r, int k, float s) {
         const float h1 = sm.H1[(2 * TB + r) * ldh + k];
         sm.L1t[k * R + 2 * TB + r] = (sm.HB1[r * ldh + k] + s) * (1.f - h1 * h1);
     };
-    if (vecH) gemm_yW<TB, 4>(W2, sm.Z2x, H, H, sm.SCR, tid, nth, epiE);
-    else gemm_yW<TB, 1>(W2, sm.Z2x, H, H, sm.SCR, tid, nth, epiE);
+    if (vecH) gemm_yW<TB, 4, WL>(W2, sm.Z2x, H, H, sm.SCR, tid, nth, epiE);
+    else gemm_yW<TB, 1, WL>(W2, sm.Z2x, H, H, sm.SCR, tid, nth, epiE);
 
     // parameter gradients of this tile
     if (vecH) outer_store<R, 4>(gout + a.L.w2, sm.L2t, sm.H1, ldh, H, H, tid, nth, acc);
@@ -224,28 +231,32 @@ __device__ void disc_tile(const DiscArgs& a, int step, int tile, float* __restri
     __syncthreads();
 }
 
-__device__ void disc_reduce(const DiscArgs& a, int cta, int ncta) {
+// ---- phase B: slice `cta` of the flat gradient (+ loss sums by CTA 0) --------------------------------
+__device__ void disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4) {
     const int tid = threadIdx.x;
-    for (int p = cta * kStepThreads + tid; p < a.P; p += ncta * kStepThreads) {
-        float g = 0.f;
-        for (int c = 0; c < a.nslots; ++c) g += ld_cg(a.gpart + (size_t)c * a.P + p);
-        __stcg(a.grad + p, g);
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid);
+    if (cta == 0 && tid < 32) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int c = tid; c < a.nslots; c += 32) {
+            s0 += ld_cg(a.losspart + c * 4); s1 += ld_cg(a.losspart + c * 4 + 1); s2 += ld_cg(a.losspart + c * 4 + 2);
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2); }
     }
-    if (cta == 0 && tid < 3) {
-        float s = 0.f;
-        for (int c = 0; c < a.nslots; ++c) s += ld_cg(a.losspart + c * 4 + tid);
-        __stcg(a.grad + a.P + tid, s);
-    }
+    __syncthreads();
 }
 
-__device__ void disc_adam(const DiscArgs& a, int step, int cta, int ncta) {
+// ---- Adam on slice `cta` (the discriminator has no gradient clipping: A2C/algo/gail.py:186-188) --------
+__device__ void disc_adam_slice(const DiscArgs& a, int step, int cta) {
     const int tid = threadIdx.x;
     const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
-    for (int p = cta * kStepThreads + tid; p < a.P; p += ncta * kStepThreads) {
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    for (int p = p0 + tid; p < p1; p += kStepThreads) {
         const float g = ld_cg(a.grad + p);
-        float pv = a.params[p], mv = a.m[p], vv = a.v[p];
+        float pv = __ldcg(a.params + p), mv = __ldcg(a.m + p), vv = __ldcg(a.v + p);
         adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
-        a.params[p] = pv; a.m[p] = mv; a.v[p] = vv;
+        __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
     }
     if (cta == 0 && tid == 0) {
         const float invB = 1.f / (float)a.B;
@@ -256,36 +267,77 @@ __device__ void disc_adam(const DiscArgs& a, int step, int cta, int ncta) {
     }
 }
 
-__device__ __forceinline__ void disc_phase1_all(const DiscArgs& a, int step, int cta, int ncta, float* smem) {
+template <class WL>
+__device__ __forceinline__ void disc_phaseA(const DiscArgs& a, const float* W, int step, int cta, int ncta, float* smem) {
     DiscSmem sm;
     sm.carve(smem, a.F, a.H);
     bool acc = false;
     for (int tile = cta; tile < a.ntiles; tile += ncta) {
-        disc_tile(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
+        disc_tile<WL>(a, W, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
         acc = true;
     }
+}
+
+__device__ __forceinline__ void disc_poison_on_timeout(const DiscArgs& a) {
+    // a timed-out grid barrier poisons the trace so the host raises instead of trusting the result
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
+}
+
+// CTA-private shared-memory image of the flat parameter vector <- global (through L2)
+__device__ __forceinline__ void load_param_image(float* Ws, const float* __restrict__ params, int P, int tid) {
+    constexpr int U = 4;
+    for (int p = 4 * tid; p < P; p += 4 * kStepThreads * U) {
+        float4 q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = p + 4 * kStepThreads * u;
+            q[u] = i < P ? ld_cg4(params + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = p + 4 * kStepThreads * u;
+            if (i < P) *reinterpret_cast<float4*>(Ws + i) = q[u];
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kStepThreads, 1) disc_resident_kernel(DiscArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* Ws = smem; float* tile = Ws + a.P;
+    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    for (int step = 0; step < a.nsteps; ++step) {
+        load_param_image(Ws, a.params, a.P, threadIdx.x);
+        disc_phaseA<LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+        gb.sync();
+        disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile));
+        disc_adam_slice(a, step, blockIdx.x);
+        gb.sync();
+    }
+    disc_poison_on_timeout(a);
 }
 
 __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscArgs a) {
     extern __shared__ __align__(16) float smem[];
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     for (int step = 0; step < a.nsteps; ++step) {
-        disc_phase1_all(a, step, blockIdx.x, gridDim.x, smem);
+        disc_phaseA<LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
         gb.sync();
-        disc_reduce(a, blockIdx.x, gridDim.x);
-        gb.sync();
-        disc_adam(a, step, blockIdx.x, gridDim.x);
+        disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(smem));
+        disc_adam_slice(a, step, blockIdx.x);
         gb.sync();
     }
-    // a timed-out grid barrier poisons the trace so the host raises instead of trusting the result
-    if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
+    disc_poison_on_timeout(a);
 }
-__global__ void __launch_bounds__(kStepThreads, 1) disc_phase1_kernel(DiscArgs a, int step) {
+__global__ void __launch_bounds__(kStepThreads, 1) disc_phaseA_kernel(DiscArgs a, int step) {
     extern __shared__ __align__(16) float smem[];
-    disc_phase1_all(a, step, blockIdx.x, gridDim.x, smem);
+    disc_phaseA<LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
 }
-__global__ void __launch_bounds__(kStepThreads) disc_phase2_kernel(DiscArgs a) { disc_reduce(a, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(kStepThreads) disc_phase3_kernel(DiscArgs a, int step) { disc_adam(a, step, blockIdx.x, gridDim.x); }
+__global__ void __launch_bounds__(kStepThreads) disc_phaseB_kernel(DiscArgs a) {
+    __shared__ float4 scr4[kStepThreads];
+    disc_reduce_slice(a, blockIdx.x, scr4);
+}
+__global__ void __launch_bounds__(kStepThreads) disc_phaseC_kernel(DiscArgs a, int step) { disc_adam_slice(a, step, blockIdx.x); }
 
 // ---- reward prediction ---------------------------------------------------------------------------
 // raw reward of predict_reward_combined (gail.py:203-205) for n_rows rows of (.,F); optionally the
@@ -307,7 +359,7 @@ __global__ void __launch_bounds__(kStepThreads) disc_reward_kernel(const float* 
             X[e] = (row0 + r < n_rows && k < F) ? d_in[(size_t)(row0 + r) * F + k] : 0.f;
         }
         __syncthreads();
-        disc_tile_forward<R>(params, L, F, H, X, ldf, H1, H2, ldh, D, tid);
+        disc_tile_forward<R, LdGlobal>(params, L, F, H, X, ldf, H1, H2, ldh, D, tid);
         if (tid < R && row0 + tid < n_rows) {
             const int row = row0 + tid;
             const float s = sigmoidf(D[tid]);
@@ -432,14 +484,26 @@ static int disc_grid(const sg_disc_config* c, int* sms_out) {
     int g = tiles < sms ? tiles : sms;
     return g < 1 ? 1 : g;
 }
+constexpr size_t kDiscMaxDynSmem = 227 * 1024 - 1024;
+static size_t disc_tile_smem_floats(const sg_disc_config* c) {
+    size_t f = (size_t)DiscSmem::floats(c->feat_dim, c->hidden);
+    return f < 4 * kStepThreads ? 4 * kStepThreads : f;      // phase B needs 256 float4 of scratch
+}
+static size_t disc_resident_smem_bytes(const sg_disc_config* c) {
+    DiscLayout L = make_disc_layout(c->feat_dim, c->hidden);
+    return ((size_t)L.total + disc_tile_smem_floats(c)) * sizeof(float);
+}
 static int disc_validate(const sg_disc_config* c) {
     SG_REQUIRE(c, "sg_disc: null config");
     SG_REQUIRE(c->feat_dim > 0 && c->hidden > 0 && c->batch_size > 0 && c->n_steps > 0, "sg_disc: non-positive sizes");
     SG_REQUIRE(c->row_begin >= 0 && c->row_begin < c->row_end && c->row_end <= c->batch_size,
                "sg_disc: shard [%d,%d) outside minibatch of %d rows", c->row_begin, c->row_end, c->batch_size);
     SG_REQUIRE(c->first_adam_step >= 1, "sg_disc: first_adam_step is 1-based");
-    const size_t smem = (size_t)DiscSmem::floats(c->feat_dim, c->hidden) * sizeof(float);
-    SG_REQUIRE(smem <= 220 * 1024, "sg_disc: tile needs %zu bytes of shared memory", smem);
+    SG_REQUIRE(c->mode >= 0 && c->mode <= 3, "sg_disc: mode must be 0 (auto), 1 (phased), 2 (persistent) or 3 (resident)");
+    const size_t smem = disc_tile_smem_floats(c) * sizeof(float);
+    SG_REQUIRE(smem <= kDiscMaxDynSmem, "sg_disc: tile needs %zu bytes of shared memory", smem);
+    SG_REQUIRE(c->mode != 3 || disc_resident_smem_bytes(c) <= kDiscMaxDynSmem,
+               "sg_disc: resident mode needs %zu bytes of shared memory", disc_resident_smem_bytes(c));
     return SG_OK;
 }
 struct DiscWs { size_t gpart, grad, losspart, bar, total; };
@@ -508,7 +572,7 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     if (rc) return rc;
     SG_REQUIRE(params && adam_m && adam_v && expert && policy_feat && expert_idx && policy_idx && alpha && step_size &&
                    bc2_sqrt && trace && workspace, "sg_disc_update: null pointer");
-    SG_REQUIRE(!(allreduce_cb && cfg->mode == 0), "sg_disc_update: the allreduce callback needs mode 1");
+    SG_REQUIRE(!(allreduce_cb && cfg->mode != 1), "sg_disc_update: the allreduce callback needs mode 1");
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 0;
     const int grid = disc_grid(cfg, &sms);
@@ -521,6 +585,7 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     a.row_begin = cfg->row_begin; a.row_end = cfg->row_end;
     a.ntiles = disc_tiles(cfg);
     a.nslots = grid < a.ntiles ? grid : a.ntiles;
+    a.SL = round_up((a.P + grid - 1) / grid, 4);
     a.gp_lambda = (float)cfg->gp_lambda;
     a.one_minus_b1 = (float)(1.0 - cfg->beta1); a.b2 = (float)cfg->beta2; a.one_minus_b2 = (float)(1.0 - cfg->beta2);
     a.eps = (float)cfg->adam_eps;
@@ -529,27 +594,31 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
     a.bar = (unsigned int*)(ws + w.bar);
-    const size_t smem = (size_t)DiscSmem::floats(a.F, a.H) * sizeof(float);
+    const size_t smem_tile = disc_tile_smem_floats(cfg) * sizeof(float);
+    const size_t smem_res = disc_resident_smem_bytes(cfg);
+    int mode = cfg->mode;
+    if (mode == 0) mode = smem_res <= kDiscMaxDynSmem ? 3 : 2;
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
-    if (cfg->mode == 0) {
-        SG_CUDA(cudaFuncSetAttribute(disc_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (mode == 3 || mode == 2) {
+        const void* fn = mode == 3 ? (const void*)disc_resident_kernel : (const void*)disc_persistent_kernel;
+        const size_t smem = mode == 3 ? smem_res : smem_tile;
+        SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, disc_persistent_kernel, kStepThreads, smem));
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepThreads, smem));
         SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_disc_update: cooperative grid of %d CTAs does not fit", grid);
         void* kargs[] = {(void*)&a};
-        SG_CUDA(cudaLaunchCooperativeKernel((const void*)disc_persistent_kernel, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+        SG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kStepThreads), kargs, smem, s));
         count_launches(1);
     } else {
-        SG_CUDA(cudaFuncSetAttribute(disc_phase1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int g2 = (a.P + kStepThreads - 1) / kStepThreads;
+        SG_CUDA(cudaFuncSetAttribute(disc_phaseA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
         for (int step = 0; step < a.nsteps; ++step) {
-            disc_phase1_kernel<<<grid, kStepThreads, smem, s>>>(a, step);
-            disc_phase2_kernel<<<g2, kStepThreads, 0, s>>>(a);
+            disc_phaseA_kernel<<<grid, kStepThreads, smem_tile, s>>>(a, step);
+            disc_phaseB_kernel<<<grid, kStepThreads, 0, s>>>(a);
             if (allreduce_cb) {
                 int cb = allreduce_cb(a.grad, a.P + 3, allreduce_user);
                 SG_REQUIRE(cb == 0, "sg_disc_update: allreduce callback failed with %d at step %d", cb, step);
             }
-            disc_phase3_kernel<<<g2, kStepThreads, 0, s>>>(a, step);
+            disc_phaseC_kernel<<<grid, kStepThreads, 0, s>>>(a, step);
             count_launches(3);
         }
         SG_CUDA(cudaGetLastError());

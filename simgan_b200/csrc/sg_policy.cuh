@@ -31,7 +31,7 @@ struct PolicyTile {
 };
 
 // X must be loaded (zero padded to ldo) and visible.  Ends with a CTA barrier; MU and VAL are valid after.
-template <int R>
+template <int R, class WL = LdGlobal>
 __device__ __forceinline__ void policy_tile_forward(const float* __restrict__ params, const PolicyLayout& L, int O,
                                                     int H, int A, const PolicyTile<R>& T, int tid) {
     const int half = tid >> 7, t = tid & (kHalf - 1);
@@ -42,31 +42,32 @@ __device__ __forceinline__ void policy_tile_forward(const float* __restrict__ pa
     float* h1 = T.H1 + half * R * T.ldh;
     float* h2 = T.H2 + half * R * T.ldh;
     const int ldh = T.ldh;
-    auto epi1 = [&](int r, int n, float s) { h1[r * ldh + n] = tanhf(s + ld_cg(B1 + n)); };
-    if ((O & 3) == 0) gemm_xwT<R, 4>(W1, T.X, T.ldo, H, O, t, kHalf, epi1);
-    else gemm_xwT<R, 1>(W1, T.X, T.ldo, H, O, t, kHalf, epi1);
+    auto epi1 = [&](int r, int n, float s) { h1[r * ldh + n] = tanhf(s + WL::ld(B1 + n)); };
+    if ((O & 3) == 0) gemm_xwT<R, 4, WL>(W1, T.X, T.ldo, H, O, t, kHalf, epi1);
+    else gemm_xwT<R, 1, WL>(W1, T.X, T.ldo, H, O, t, kHalf, epi1);
     __syncthreads();
-    auto epi2 = [&](int r, int n, float s) { h2[r * ldh + n] = tanhf(s + ld_cg(B2 + n)); };
-    if ((H & 3) == 0) gemm_xwT<R, 4>(W2, h1, ldh, H, H, t, kHalf, epi2);
-    else gemm_xwT<R, 1>(W2, h1, ldh, H, H, t, kHalf, epi2);
+    auto epi2 = [&](int r, int n, float s) { h2[r * ldh + n] = tanhf(s + WL::ld(B2 + n)); };
+    if ((H & 3) == 0) gemm_xwT<R, 4, WL>(W2, h1, ldh, H, H, t, kHalf, epi2);
+    else gemm_xwT<R, 1, WL>(W2, h1, ldh, H, H, t, kHalf, epi2);
     __syncthreads();
     const float* WH = params + (half ? L.vw : L.mw);
     const float* BH = params + (half ? L.vb : L.mb);
     const int NH = half ? 1 : A;
     float* out = half ? T.VAL : T.MU;
     const int ldout = half ? 1 : T.lda;
-    auto epih = [&](int r, int n, float s) { out[r * ldout + n] = s + ld_cg(BH + n); };
-    if ((H & 3) == 0) gemm_xwT<R, 4>(WH, h2, ldh, NH, H, t, kHalf, epih);
-    else gemm_xwT<R, 1>(WH, h2, ldh, NH, H, t, kHalf, epih);
+    auto epih = [&](int r, int n, float s) { out[r * ldout + n] = s + WL::ld(BH + n); };
+    if ((H & 3) == 0) gemm_xwT<R, 4, WL>(WH, h2, ldh, NH, H, t, kHalf, epih);
+    else gemm_xwT<R, 1, WL>(WH, h2, ldh, NH, H, t, kHalf, epih);
     __syncthreads();
 }
 
 // log-prob of `act` under N(mu, exp(logstd)) summed over the action dim, in the op order of
 // torch.distributions.Normal.log_prob (called from A2C/distributions.py:52-53).
+template <class WL = LdGlobal>
 __device__ __forceinline__ float gaussian_logp_row(const float* mu, const float* act, const float* logstd, int A) {
     float lp = 0.f;
     for (int a = 0; a < A; ++a) {
-        const float sigma = expf(ld_cg(logstd + a));
+        const float sigma = expf(WL::ld(logstd + a));
         const float var = sigma * sigma;
         const float d = act[a] - mu[a];
         lp += -(d * d) / (2.f * var) - logf(sigma) - SG_LOG_SQRT_2PI;
@@ -74,9 +75,10 @@ __device__ __forceinline__ float gaussian_logp_row(const float* mu, const float*
     return lp;
 }
 
+template <class WL = LdGlobal>
 __device__ __forceinline__ float gaussian_entropy(const float* logstd, int A) {
     float e = 0.f;
-    for (int a = 0; a < A; ++a) e += 0.5f + 0.5f * SG_LOG_2PI + logf(expf(ld_cg(logstd + a)));
+    for (int a = 0; a < A; ++a) e += 0.5f + 0.5f * SG_LOG_2PI + logf(expf(WL::ld(logstd + a)));
     return e;
 }
 

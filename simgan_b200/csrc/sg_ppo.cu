@@ -1,14 +1,25 @@
 // PPO.update on the device (A2C/algo/ppo.py:65-157).
 //
-// One optimizer step = three grid-wide phases:
-//   1. tile phase   every CTA owns tiles of R=8 minibatch rows: sampler gather (A2C/storage.py:169-185)
-//                   -> actor/critic forward -> Gaussian log-prob -> clipped surrogate + clipped value
-//                   loss -> hand-derived backward -> per-CTA partial gradient (P floats) in L2
-//   2. reduce phase partial gradients summed in a fixed order -> flat gradient (+ loss sums)
-//                   [data-parallel mode: the NCCL sum-allreduce of that vector happens here]
-//   3. adam phase   global-norm clip (A2C/algo/ppo.py:143-144) + Adam (ppo.py:145) on a param slice
-// mode 0 runs all steps of the call inside ONE persistent cooperative kernel with grid barriers between
-// phases; mode 1 launches one kernel per phase (debug / data-parallel path).
+// One optimizer step = grid-wide phases:
+//   A  tile phase     every CTA owns tiles of R=8 minibatch rows: sampler gather (A2C/storage.py:169-185)
+//                     -> actor/critic forward -> Gaussian log-prob -> clipped surrogate + clipped value
+//                     loss -> hand-derived backward -> per-CTA partial gradient (P floats) in L2
+//   B  reduce-scatter CTA c sums slice c of all partial gradients in a fixed order -> flat gradient,
+//                     plus the slice's sum of squares (fp64) for the global norm
+//                     [data-parallel mode: the sum-allreduce of the flat gradient happens after B]
+//   C  clip + Adam    global-norm clip (A2C/algo/ppo.py:143-144) + Adam (ppo.py:145)
+//
+// Kernel variants (sg_ppo_config.mode):
+//   resident   (mode 0 when it fits, mode 3 forced) ONE persistent cooperative kernel for all steps of
+//              the call; every CTA keeps a private image of the parameters AND the Adam moments in
+//              shared memory, applies the identical clip+Adam update redundantly after all-gathering
+//              the reduced gradient, and reads its weights from shared memory in the tile phase.
+//              Two grid barriers per optimizer step.
+//   persistent (mode 0 otherwise, mode 2 forced) same single launch, parameters stay in global memory
+//              (read through L2), Adam is partitioned by slice; three grid barriers per step.
+//   phased     (mode 1) one launch per phase; the data-parallel path (host allreduce callback).
+// persistent and phased are bit-identical; resident differs only by fp32 reassociation of nothing --
+// it runs the same arithmetic in the same order -- and is bit-identical too.
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
 
@@ -16,7 +27,7 @@ namespace sg {
 
 struct PpoArgs {
     int O, H, A, S, P;
-    int nmb, mbs, nsteps, row_begin, row_end, ntiles, nslots;
+    int nmb, mbs, nsteps, row_begin, row_end, ntiles, nslots, SL, nslices;
     int clipped_vloss, first_adam_step;
     float clip, ratio_lo, ratio_hi, c_v, c_e, max_norm;
     float one_minus_b1, b2, one_minus_b2, eps;
@@ -27,6 +38,7 @@ struct PpoArgs {
     const float *step_size, *bc2_sqrt;
     float* trace;
     float *gpart, *grad, *losspart, *scal;
+    double* ssq;
     unsigned int* bar;
 };
 
@@ -50,10 +62,12 @@ struct PpoSmem {
     }
 };
 
-// ---- phase 1: one tile of R minibatch rows ------------------------------------------------------
-template <int R>
-__device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                         PpoSmem<R>& sm, bool acc) {
+// ---- phase A: one tile of R minibatch rows --------------------------------------------------------
+// W = flat parameter image the weights are read from (global through L2, or the CTA's shared copy).
+template <int R, class WL>
+__device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step, int tile, float* __restrict__ gout,
+                         float* __restrict__ lossout, PpoSmem<R>& sm, bool acc) {
+    static_assert(R == 8, "the per-row loss warp below maps 8 rows x 4 lanes");
     const int tid = threadIdx.x;
     const int O = a.O, H = a.H, A = a.A;
     const PolicyTile<R>& T = sm.T;
@@ -62,7 +76,6 @@ __device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict
     const int row0 = a.row_begin + tile * R;
     float* rRet = sm.ROW;            float* rVp = sm.ROW + R;     float* rOlp = sm.ROW + 2 * R;
     float* rAdv = sm.ROW + 3 * R;    float* rValid = sm.ROW + 4 * R;
-    float* rVl = sm.ROW + 5 * R;     float* rAl = sm.ROW + 6 * R;
 
     // gather this tile's rows (flat sample id = t*N+n, A2C/storage.py:169-181)
     for (int e = tid; e < R * T.ldo; e += kStepThreads) {
@@ -75,30 +88,40 @@ __device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict
         const int row = row0 + r;
         T.ACT[e] = (row < a.row_end && k < A) ? a.actions[(size_t)idx[row] * A + k] : 0.f;
     }
-    if (tid < R) {
-        const int row = row0 + tid;
+    if (tid >= kStepThreads - R) {          // last warp: keeps the row scalars off the warps gathering X
+        const int r = tid - (kStepThreads - R);
+        const int row = row0 + r;
         const bool ok = row < a.row_end;
         const int i = ok ? idx[row] : 0;
         const float ret = ok ? a.ret[i] : 0.f, vp = ok ? a.vpred[i] : 0.f;
-        rRet[tid] = ret; rVp[tid] = vp; rOlp[tid] = ok ? a.oldlp[i] : 0.f;
+        rRet[r] = ret; rVp[r] = vp; rOlp[r] = ok ? a.oldlp[i] : 0.f;
         // (adv - mean) / (std + 1e-5)   (A2C/algo/ppo.py:66-68)
         const float mean = a.advstats[0], sd = a.advstats[1];
-        rAdv[tid] = ok ? __fdiv_rn(__fsub_rn(__fsub_rn(ret, vp), mean), __fadd_rn(sd, 1e-5f)) : 0.f;
-        rValid[tid] = ok ? 1.f : 0.f;
+        rAdv[r] = ok ? __fdiv_rn(__fsub_rn(__fsub_rn(ret, vp), mean), __fadd_rn(sd, 1e-5f)) : 0.f;
+        rValid[r] = ok ? 1.f : 0.f;
     }
     __syncthreads();
 
-    policy_tile_forward<R>(a.params, a.L, O, H, A, T, tid);
+    policy_tile_forward<R, WL>(W, a.L, O, H, A, T, tid);
 
-    // per-row losses and the gradient seeds d loss / d mu, d loss / d value
-    const float* ls = a.params + a.L.ls;
-    if (tid < R) {
-        const int r = tid;
-        float vl = 0.f, al = 0.f, dv = 0.f, coef = 0.f;
+    // per-row losses and the gradient seeds d loss / d mu, d loss / d value: one warp, 4 lanes per row
+    const float* ls = W + a.L.ls;
+    if (tid < 32) {
+        const int r = tid >> 2, sub = tid & 3;
         const bool ok = rValid[r] != 0.f;
         const float invB = 1.f / (float)a.mbs;
+        // log-prob of the stored action, summed over the action dim (A2C/distributions.py:52-53)
+        float lp = 0.f;
+        for (int k = sub; k < A; k += 4) {
+            const float sigma = expf(WL::ld(ls + k));
+            const float var = sigma * sigma;
+            const float d = T.ACT[r * T.lda + k] - T.MU[r * T.lda + k];
+            lp += -(d * d) / (2.f * var) - logf(sigma) - SG_LOG_SQRT_2PI;
+        }
+        lp += __shfl_xor_sync(0xffffffffu, lp, 1);
+        lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+        float vl = 0.f, al = 0.f, dv = 0.f, coef = 0.f;
         if (ok) {
-            const float lp = gaussian_logp_row(T.MU + r * T.lda, T.ACT + r * T.lda, ls, A);
             const float ratio = expf(lp - rOlp[r]);
             const float adv = rAdv[r];
             const float s1 = ratio * adv;
@@ -125,23 +148,27 @@ __device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict
                 dv = a.c_v * invB * (v - ret);
             }
         }
-        rVl[r] = vl; rAl[r] = al;
-        sm.DVt[r] = dv;
-        for (int k = 0; k < A; ++k) {
-            const float sigma = expf(ld_cg(ls + k));
+        for (int k = sub; k < A; k += 4) {
+            const float sigma = expf(WL::ld(ls + k));
             const float var = sigma * sigma;
             const float d = T.ACT[r * T.lda + k] - T.MU[r * T.lda + k];
-            sm.DMUt[k * R + r] = ok ? coef * d / var : 0.f;          // d logp / d mu   = (a-mu)/var
+            sm.DMUt[k * R + r] = ok ? coef * d / var : 0.f;              // d logp / d mu     = (a-mu)/var
             sm.DLSt[k * R + r] = ok ? coef * (d * d / var - 1.f) : 0.f;  // d logp / d logstd = (a-mu)^2/var - 1
+        }
+        if (sub == 0) sm.DVt[r] = dv;
+        // loss sums over the tile's rows (lanes sub==0 carry them), fixed butterfly order
+        float svl = sub == 0 ? vl : 0.f, sal = sub == 0 ? al : 0.f;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            svl += __shfl_xor_sync(0xffffffffu, svl, o);
+            sal += __shfl_xor_sync(0xffffffffu, sal, o);
+        }
+        if (tid == 0) {
+            if (acc) { svl += lossout[0]; sal += lossout[1]; }
+            lossout[0] = svl; lossout[1] = sal;
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        float svl = 0.f, sal = 0.f;
-        for (int r = 0; r < R; ++r) { svl += rVl[r]; sal += rAl[r]; }
-        if (acc) { svl += lossout[0]; sal += lossout[1]; }
-        lossout[0] = svl; lossout[1] = sal;
-    }
 
     // ---- backward -------------------------------------------------------------------------------
     const int half = tid >> 7, t = tid & (kHalf - 1);
@@ -152,13 +179,13 @@ __device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict
     float* dz2 = sm.DZ2t + half * R * ldh;     // [H][R]
     float* dz1 = sm.DZ1t + half * R * ldh;
     float* scr = sm.SCR + half * kHalf * R * 4;
-    const float* Wh = a.params + (half ? a.L.vw : a.L.mw);
+    const float* Wh = W + (half ? a.L.vw : a.L.mw);
     const float* Dh = half ? sm.DVt : sm.DMUt;
     const int NH = half ? 1 : A;
     // head back-prop: dZ2 = (dHead . Whead) * (1 - h2^2)
     auto epi_h = [&](int r, int k, float s) { const float h = h2[r * ldh + k]; dz2[k * R + r] = s * (1.f - h * h); };
-    if (vecH) gemm_yW<R, 4>(Wh, Dh, NH, H, scr, t, kHalf, epi_h);
-    else gemm_yW<R, 1>(Wh, Dh, NH, H, scr, t, kHalf, epi_h);
+    if (vecH) gemm_yW<R, 4, WL>(Wh, Dh, NH, H, scr, t, kHalf, epi_h);
+    else gemm_yW<R, 1, WL>(Wh, Dh, NH, H, scr, t, kHalf, epi_h);
     // head parameter gradients
     {
         float* gW = gout + (half ? a.L.vw : a.L.mw);
@@ -169,10 +196,10 @@ __device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict
         if (!half) rowsum_store<R>(gout + a.L.ls, sm.DLSt, A, t, kHalf, acc);
     }
     // layer 2 back-prop: dZ1 = (dZ2 . W2) * (1 - h1^2)
-    const float* W2 = a.params + (half ? a.L.cw2 : a.L.aw2);
+    const float* W2 = W + (half ? a.L.cw2 : a.L.aw2);
     auto epi_2 = [&](int r, int k, float s) { const float h = h1[r * ldh + k]; dz1[k * R + r] = s * (1.f - h * h); };
-    if (vecH) gemm_yW<R, 4>(W2, dz2, H, H, scr, t, kHalf, epi_2);
-    else gemm_yW<R, 1>(W2, dz2, H, H, scr, t, kHalf, epi_2);
+    if (vecH) gemm_yW<R, 4, WL>(W2, dz2, H, H, scr, t, kHalf, epi_2);
+    else gemm_yW<R, 1, WL>(W2, dz2, H, H, scr, t, kHalf, epi_2);
     {
         float* gW2 = gout + (half ? a.L.cw2 : a.L.aw2);
         float* gB2 = gout + (half ? a.L.cb2 : a.L.ab2);
@@ -188,69 +215,158 @@ __device__ void ppo_tile(const PpoArgs& a, int step, int tile, float* __restrict
     __syncthreads();   // smem is reused by the next tile
 }
 
-// ---- phase 2: deterministic reduction of the per-CTA partial gradients ----------------------------
-__device__ void ppo_reduce(const PpoArgs& a, int cta, int ncta) {
-    const int tid = threadIdx.x;
-    for (int p = cta * kStepThreads + tid; p < a.P; p += ncta * kStepThreads) {
-        float g = 0.f;
-        for (int c = 0; c < a.nslots; ++c) g += ld_cg(a.gpart + (size_t)c * a.P + p);
-        __stcg(a.grad + p, g);
-    }
-    if (cta == 0 && tid < 2) {
-        float s = 0.f;
-        for (int c = 0; c < a.nslots; ++c) s += ld_cg(a.losspart + c * 4 + tid);
-        __stcg(a.grad + a.P + tid, s);
-    }
-    if (cta == 0 && tid == 2) a.scal[0] = gaussian_entropy(a.params + a.L.ls, a.A);   // before Adam touches logstd
-}
-
-// ---- phase 3: clip_grad_norm_ + Adam ---------------------------------------------------------------
-__device__ void ppo_adam(const PpoArgs& a, int step, int cta, int ncta, double* red) {
-    const int tid = threadIdx.x;
-    // every CTA forms the same global norm in the same order (identical clip factor everywhere)
-    double s = 0.0;
-    for (int p = tid; p < a.P; p += kStepThreads) {
-        float g = ld_cg(a.grad + p);
-        if (p >= a.L.ls && p < a.L.ls + a.A) g -= a.c_e;      // d(-c_e * entropy)/d logstd = -c_e
-        s += (double)g * (double)g;
-    }
-    s = warp_sum(s);
-    if ((tid & 31) == 0) red[tid >> 5] = s;
-    __syncthreads();
-    double tot = 0.0;
-    for (int w = 0; w < kStepThreads / 32; ++w) tot += red[w];
-    const float norm = (float)sqrt(tot);
-    float clip = a.max_norm / (norm + 1e-6f);
-    if (clip > 1.f) clip = 1.f;
-    const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
-    for (int p = cta * kStepThreads + tid; p < a.P; p += ncta * kStepThreads) {
-        float g = ld_cg(a.grad + p);
-        if (p >= a.L.ls && p < a.L.ls + a.A) g -= a.c_e;
-        g *= clip;
-        float pv = a.params[p], mv = a.m[p], vv = a.v[p];
-        adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
-        a.params[p] = pv; a.m[p] = mv; a.v[p] = vv;
-    }
-    if (cta == 0 && tid == 0) {
-        const float invB = 1.f / (float)a.mbs;
-        float* tr = a.trace + (size_t)step * 4;
-        tr[0] = ld_cg(a.grad + a.P) * invB;
-        tr[1] = ld_cg(a.grad + a.P + 1) * invB;
-        tr[2] = a.scal[0];
-        tr[3] = norm;
-    }
-    __syncthreads();
-}
-
-template <int R>
-__device__ __forceinline__ void ppo_phase1_all(const PpoArgs& a, int step, int cta, int ncta, float* smem) {
+template <int R, class WL>
+__device__ __forceinline__ void ppo_phaseA(const PpoArgs& a, const float* W, int step, int cta, int ncta, float* smem) {
     PpoSmem<R> sm;
     sm.carve(smem, a.O, a.H, a.A);
     bool acc = false;
     for (int tile = cta; tile < a.ntiles; tile += ncta) {
-        ppo_tile<R>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
+        ppo_tile<R, WL>(a, W, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
         acc = true;
     }
+}
+
+// effective gradient = d loss/d theta of (c_v*L_V + L_pi - c_e*H): the entropy term only touches logstd
+__device__ __forceinline__ float eff_grad(const PpoArgs& a, int p, float g) {
+    return (p >= a.L.ls && p < a.L.ls + a.A) ? g - a.c_e : g;
+}
+
+// ---- phase B: slice `cta` of the flat gradient (+ loss sums and the entropy scalar by CTA 0) ---------
+// `ls` = logstd of the CURRENT parameters (before this step's Adam), read with WL.
+template <class WL>
+__device__ void ppo_reduce_slice(const PpoArgs& a, int cta, float4* scr4, const float* ls) {
+    const int tid = threadIdx.x;
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid);
+    if (cta == 0 && tid < 32) {
+        // loss sums over the partial slots: lane-strided, then a fixed butterfly
+        float s0 = 0.f, s1 = 0.f;
+        for (int c = tid; c < a.nslots; c += 32) { s0 += ld_cg(a.losspart + c * 4); s1 += ld_cg(a.losspart + c * 4 + 1); }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.scal, gaussian_entropy<WL>(ls, a.A)); }
+    }
+}
+
+// sum of squares (fp64) of slice `cta` of the effective gradient -> ssq[cta].  Reads the (possibly
+// allreduced) flat gradient back through L2 so the fused and the phased paths do identical arithmetic.
+__device__ void ppo_ssq_slice(const PpoArgs& a, int cta, double* red) {
+    const int tid = threadIdx.x;
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    double s = 0.0;
+    for (int p = p0 + 4 * tid; p < p1; p += 4 * kStepThreads) {
+        const float4 g = ld_cg4(a.grad + p);
+        const float gx = eff_grad(a, p, g.x), gy = eff_grad(a, p + 1, g.y), gz = eff_grad(a, p + 2, g.z), gw = eff_grad(a, p + 3, g.w);
+        s += (double)gx * (double)gx; s += (double)gy * (double)gy; s += (double)gz * (double)gz; s += (double)gw * (double)gw;
+    }
+    const double tot = block_sum_256(s, red);
+    if (tid == 0) __stcg(a.ssq + cta, tot);
+}
+
+// global gradient norm from the slice partials (identical in every CTA) -> clip factor of clip_grad_norm_
+__device__ __forceinline__ float ppo_clip_factor(const PpoArgs& a, double* red, float* norm_out) {
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (int c = tid; c < a.nslices; c += kStepThreads) s += __ldcg(a.ssq + c);
+    const double tot = block_sum_256(s, red);
+    const float norm = (float)sqrt(tot);
+    float clip = a.max_norm / (norm + 1e-6f);
+    if (clip > 1.f) clip = 1.f;
+    *norm_out = norm;
+    return clip;
+}
+
+__device__ __forceinline__ void ppo_write_trace(const PpoArgs& a, int step, float norm) {
+    const float invB = 1.f / (float)a.mbs;
+    float* tr = a.trace + (size_t)step * 4;
+    tr[0] = ld_cg(a.grad + a.P) * invB;
+    tr[1] = ld_cg(a.grad + a.P + 1) * invB;
+    tr[2] = ld_cg(a.scal);
+    tr[3] = norm;
+}
+
+// ---- phase C, partitioned: clip + Adam on slice `cta` of the global parameter vector -----------------
+__device__ void ppo_adam_slice(const PpoArgs& a, int step, int cta, double* red) {
+    const int tid = threadIdx.x;
+    float norm;
+    const float clip = ppo_clip_factor(a, red, &norm);
+    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
+    const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    for (int p = p0 + tid; p < p1; p += kStepThreads) {
+        const float g = eff_grad(a, p, ld_cg(a.grad + p)) * clip;
+        float pv = __ldcg(a.params + p), mv = __ldcg(a.m + p), vv = __ldcg(a.v + p);
+        adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+        __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
+    }
+}
+
+// ---- phase C, redundant: every CTA updates its private shared-memory image of params / moments -------
+__device__ void ppo_adam_resident(const PpoArgs& a, int step, int cta, float* Ws, float* Ms, float* Vs, double* red) {
+    const int tid = threadIdx.x;
+    float norm;
+    const float clip = ppo_clip_factor(a, red, &norm);
+    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
+    const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
+    constexpr int U = 4;
+    for (int p = 4 * tid; p < a.P; p += 4 * kStepThreads * U) {
+        float4 g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = p + 4 * kStepThreads * u;
+            g[u] = q < a.P ? ld_cg4(a.grad + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = p + 4 * kStepThreads * u;
+            if (q >= a.P) break;
+            const float gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+            float4 pw = *reinterpret_cast<float4*>(Ws + q), pm = *reinterpret_cast<float4*>(Ms + q), pv = *reinterpret_cast<float4*>(Vs + q);
+            float w[4] = {pw.x, pw.y, pw.z, pw.w}, m[4] = {pm.x, pm.y, pm.z, pm.w}, v[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                adam_update(w[i], m[i], v[i], eff_grad(a, q + i, gg[i]) * clip, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            *reinterpret_cast<float4*>(Ws + q) = make_float4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<float4*>(Ms + q) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4*>(Vs + q) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void poison_trace_on_timeout(const PpoArgs& a) {
+    // a timed-out grid barrier poisons the trace so the host raises instead of trusting the result
+    if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kStepThreads, 1) ppo_resident_kernel(PpoArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ double red[kStepThreads / 32];
+    const int tid = threadIdx.x;
+    float* Ws = smem; float* Ms = Ws + a.P; float* Vs = Ms + a.P; float* tile = Vs + a.P;
+    for (int p = 4 * tid; p < a.P; p += 4 * kStepThreads) {
+        *reinterpret_cast<float4*>(Ws + p) = ld_cg4(a.params + p);
+        *reinterpret_cast<float4*>(Ms + p) = ld_cg4(a.m + p);
+        *reinterpret_cast<float4*>(Vs + p) = ld_cg4(a.v + p);
+    }
+    __syncthreads();
+    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    for (int step = 0; step < a.nsteps; ++step) {
+        ppo_phaseA<R, LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+        gb.sync();
+        ppo_reduce_slice<LdShared>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.L.ls);
+        ppo_ssq_slice(a, blockIdx.x, red);
+        gb.sync();
+        ppo_adam_resident(a, step, blockIdx.x, Ws, Ms, Vs, red);
+    }
+    if (blockIdx.x == 0) {
+        for (int p = 4 * tid; p < a.P; p += 4 * kStepThreads) {
+            __stcg(reinterpret_cast<float4*>(a.params + p), *reinterpret_cast<float4*>(Ws + p));
+            __stcg(reinterpret_cast<float4*>(a.m + p), *reinterpret_cast<float4*>(Ms + p));
+            __stcg(reinterpret_cast<float4*>(a.v + p), *reinterpret_cast<float4*>(Vs + p));
+        }
+    }
+    poison_trace_on_timeout(a);
 }
 
 template <int R>
@@ -259,31 +375,38 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
     __shared__ double red[kStepThreads / 32];
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     for (int step = 0; step < a.nsteps; ++step) {
-        ppo_phase1_all<R>(a, step, blockIdx.x, gridDim.x, smem);
+        ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
         gb.sync();
-        ppo_reduce(a, blockIdx.x, gridDim.x);
+        ppo_reduce_slice<LdGlobal>(a, blockIdx.x, reinterpret_cast<float4*>(smem), a.params + a.L.ls);
+        ppo_ssq_slice(a, blockIdx.x, red);
         gb.sync();
-        ppo_adam(a, step, blockIdx.x, gridDim.x, red);
+        ppo_adam_slice(a, step, blockIdx.x, red);
         gb.sync();
     }
-    // a timed-out grid barrier poisons the trace so the host raises instead of trusting the result
-    if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
+    poison_trace_on_timeout(a);
 }
 
 template <int R>
-__global__ void __launch_bounds__(kStepThreads, 1) ppo_phase1_kernel(PpoArgs a, int step) {
+__global__ void __launch_bounds__(kStepThreads, 1) ppo_phaseA_kernel(PpoArgs a, int step) {
     extern __shared__ __align__(16) float smem[];
-    ppo_phase1_all<R>(a, step, blockIdx.x, gridDim.x, smem);
+    ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
 }
-__global__ void __launch_bounds__(kStepThreads) ppo_phase2_kernel(PpoArgs a) { ppo_reduce(a, blockIdx.x, gridDim.x); }
-__global__ void __launch_bounds__(kStepThreads) ppo_phase3_kernel(PpoArgs a, int step) {
+__global__ void __launch_bounds__(kStepThreads) ppo_phaseB_kernel(PpoArgs a) {
+    __shared__ float4 scr4[kStepThreads];
+    ppo_reduce_slice<LdGlobal>(a, blockIdx.x, scr4, a.params + a.L.ls);
+}
+__global__ void __launch_bounds__(kStepThreads) ppo_ssq_kernel(PpoArgs a) {
     __shared__ double red[kStepThreads / 32];
-    ppo_adam(a, step, blockIdx.x, gridDim.x, red);
+    ppo_ssq_slice(a, blockIdx.x, red);
+}
+__global__ void __launch_bounds__(kStepThreads) ppo_phaseC_kernel(PpoArgs a, int step) {
+    __shared__ double red[kStepThreads / 32];
+    ppo_adam_slice(a, step, blockIdx.x, red);
 }
 
 static int ppo_tiles(const sg_ppo_config* c) { return (c->row_end - c->row_begin + kRows - 1) / kRows; }
 
-// number of CTAs of the tile phase == number of partial-gradient slots
+// number of CTAs of the tile phase == number of partial-gradient slots == number of gradient slices
 static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
@@ -292,6 +415,16 @@ static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
     int g = tiles < sms ? tiles : sms;
     return g < 1 ? 1 : g;
 }
+
+static size_t ppo_tile_smem_floats(const sg_ppo_config* c) {
+    size_t f = (size_t)PpoSmem<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
+    return f < 4 * kStepThreads ? 4 * kStepThreads : f;      // phase B needs 256 float4 of scratch
+}
+static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
+    PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
+    return (3 * (size_t)L.total + ppo_tile_smem_floats(c)) * sizeof(float);
+}
+constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus static shared memory headroom
 
 static int ppo_validate(const sg_ppo_config* c) {
     SG_REQUIRE(c, "sg_ppo: null config");
@@ -302,13 +435,16 @@ static int ppo_validate(const sg_ppo_config* c) {
     SG_REQUIRE(c->row_begin >= 0 && c->row_begin < c->row_end && c->row_end <= c->mini_batch_size,
                "sg_ppo: shard [%d,%d) outside minibatch of %d rows", c->row_begin, c->row_end, c->mini_batch_size);
     SG_REQUIRE(c->first_adam_step >= 1, "sg_ppo: first_adam_step is 1-based");
-    const size_t smem = (size_t)PpoSmem<kRows>::floats(c->obs_dim, c->hidden, c->act_dim) * sizeof(float);
-    SG_REQUIRE(smem <= 220 * 1024, "sg_ppo: tile needs %zu bytes of shared memory (hidden too large)", smem);
+    SG_REQUIRE(c->mode >= 0 && c->mode <= 3, "sg_ppo: mode must be 0 (auto), 1 (phased), 2 (persistent) or 3 (resident)");
+    const size_t smem = ppo_tile_smem_floats(c) * sizeof(float);
+    SG_REQUIRE(smem <= kMaxDynSmem, "sg_ppo: tile needs %zu bytes of shared memory (hidden too large)", smem);
+    SG_REQUIRE(c->mode != 3 || ppo_resident_smem_bytes(c) <= kMaxDynSmem,
+               "sg_ppo: resident mode needs %zu bytes of shared memory", ppo_resident_smem_bytes(c));
     return SG_OK;
 }
 
 struct PpoWs {
-    size_t gpart, grad, losspart, scal, bar, total;
+    size_t gpart, grad, losspart, scal, ssq, bar, total;
 };
 static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
@@ -319,6 +455,7 @@ static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     w.grad = take((size_t)(L.total + 4) * sizeof(float));
     w.losspart = take((size_t)grid * 4 * sizeof(float));
     w.scal = take(4 * sizeof(float));
+    w.ssq = take((size_t)grid * sizeof(double));
     w.bar = take(2 * sizeof(unsigned int));
     w.total = o;
     return w;
@@ -344,7 +481,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     if (rc) return rc;
     SG_REQUIRE(params && adam_m && adam_v && obs && actions && value_preds && returns && old_logp && adv_stats && perm &&
                    step_size && bc2_sqrt && trace && workspace, "sg_ppo_update: null pointer");
-    SG_REQUIRE(!(allreduce_cb && cfg->mode == 0), "sg_ppo_update: the allreduce callback needs mode 1");
+    SG_REQUIRE(!(allreduce_cb && cfg->mode != 1), "sg_ppo_update: the allreduce callback needs mode 1");
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 0;
     const int grid = ppo_grid(cfg, &sms);
@@ -361,6 +498,8 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     a.row_begin = cfg->row_begin; a.row_end = cfg->row_end;
     a.ntiles = ppo_tiles(cfg);
     a.nslots = grid < a.ntiles ? grid : a.ntiles;
+    a.SL = round_up((a.P + grid - 1) / grid, 4);
+    a.nslices = (a.P + a.SL - 1) / a.SL;
     a.clipped_vloss = cfg->use_clipped_value_loss;
     a.first_adam_step = cfg->first_adam_step;
     a.clip = (float)cfg->clip_param;
@@ -373,32 +512,37 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     a.obs = obs; a.actions = actions; a.vpred = value_preds; a.ret = returns; a.oldlp = old_logp; a.advstats = adv_stats;
     a.perm = perm; a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
-    a.scal = (float*)(ws + w.scal); a.bar = (unsigned int*)(ws + w.bar);
+    a.scal = (float*)(ws + w.scal); a.ssq = (double*)(ws + w.ssq); a.bar = (unsigned int*)(ws + w.bar);
 
-    const size_t smem = (size_t)PpoSmem<kRows>::floats(a.O, a.H, a.A) * sizeof(float);
+    const size_t smem_tile = ppo_tile_smem_floats(cfg) * sizeof(float);
+    const size_t smem_res = ppo_resident_smem_bytes(cfg);
+    int mode = cfg->mode;
+    if (mode == 0) mode = smem_res <= kMaxDynSmem ? 3 : 2;
     // partial-gradient padding lanes must be zero; barrier words must be zero
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
 
-    if (cfg->mode == 0) {
-        SG_CUDA(cudaFuncSetAttribute(ppo_persistent_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (mode == 3 || mode == 2) {
+        const void* fn = mode == 3 ? (const void*)ppo_resident_kernel<kRows> : (const void*)ppo_persistent_kernel<kRows>;
+        const size_t smem = mode == 3 ? smem_res : smem_tile;
+        SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppo_persistent_kernel<kRows>, kStepThreads, smem));
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepThreads, smem));
         SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_ppo_update: cooperative grid of %d CTAs does not fit", grid);
         void* kargs[] = {(void*)&a};
-        SG_CUDA(cudaLaunchCooperativeKernel((const void*)ppo_persistent_kernel<kRows>, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+        SG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kStepThreads), kargs, smem, s));
         count_launches(1);
     } else {
-        SG_CUDA(cudaFuncSetAttribute(ppo_phase1_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int g2 = (a.P + kStepThreads - 1) / kStepThreads;
+        SG_CUDA(cudaFuncSetAttribute(ppo_phaseA_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));
         for (int step = 0; step < a.nsteps; ++step) {
-            ppo_phase1_kernel<kRows><<<grid, kStepThreads, smem, s>>>(a, step);
-            ppo_phase2_kernel<<<g2, kStepThreads, 0, s>>>(a);
+            ppo_phaseA_kernel<kRows><<<grid, kStepThreads, smem_tile, s>>>(a, step);
+            ppo_phaseB_kernel<<<grid, kStepThreads, 0, s>>>(a);
             if (allreduce_cb) {
                 int cb = allreduce_cb(a.grad, a.P + 2, allreduce_user);
                 SG_REQUIRE(cb == 0, "sg_ppo_update: allreduce callback failed with %d at step %d", cb, step);
             }
-            ppo_phase3_kernel<<<g2, kStepThreads, 0, s>>>(a, step);
-            count_launches(3);
+            ppo_ssq_kernel<<<grid, kStepThreads, 0, s>>>(a);
+            ppo_phaseC_kernel<<<grid, kStepThreads, 0, s>>>(a, step);
+            count_launches(4);
         }
         SG_CUDA(cudaGetLastError());
     }

@@ -170,7 +170,7 @@ def _ppo_objects(g, mode):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 2, 0])
 def test_ppo_per_step_trace_vs_oracle(case, mode):
     """Every optimizer step's (value_loss, action_loss, entropy, grad_norm) against the oracle replaying the
     same recorded index stream; parameters after the whole update."""
@@ -223,14 +223,16 @@ def test_ppo_update_golden_rng(case):
 
 
 def test_ppo_modes_bit_identical():
+    """resident (0 = auto at these sizes), phased (1) and persistent (2) kernels run the same arithmetic."""
     g = Golden(CASES[0])
     outs = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         pol, agent, rs, _ = _ppo_objects(g, mode)
         agent.update(rs, permutations=g.t("ppo_perm"))
         outs.append((agent.last_trace.clone(), pol.flat_params().cpu().clone()))
-    assert torch.equal(outs[0][0], outs[1][0])
-    assert torch.equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0])
+        assert torch.equal(outs[0][1], o[1])
 
 
 def test_ppo_lr_schedule_and_step_count():
@@ -261,7 +263,7 @@ def _disc_objects(g, mode):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 2, 0])
 def test_disc_update_vs_oracle(case, mode):
     g = Golden(case)
     d, rs, buf, expert, loader = _disc_objects(g, mode)
@@ -312,12 +314,13 @@ def test_disc_update_golden_rng(case):
 def test_disc_modes_bit_identical():
     g = Golden(CASES[0])
     outs = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         d, rs, buf, expert, loader = _disc_objects(g, mode)
         d.update_gail_dyn(loader, rs, replay=g.disc_replay(0))
         outs.append((d.last_trace.clone(), d.flat_params().cpu().clone()))
-    assert torch.equal(outs[0][0], outs[1][0])
-    assert torch.equal(outs[0][1], outs[1][1])
+    for o in outs[1:]:
+        assert torch.equal(outs[0][0], o[0])
+        assert torch.equal(outs[0][1], o[1])
 
 
 # ------------------------------------------------------------------------------------------ reward relabel
