@@ -352,6 +352,9 @@ def run_cuda(args):
         "gpu_launches": int(launches),
         "kernels": kernels, "roofline": roof, "clocks": clocks,
         "losses_last_step": [float(x) for x in losses],
+        "phase_cycles_last_launch": {"ppo": dict(zip(["image", "tile", "bar1", "reduce_ssq", "bar2", "clip_adam", "bar3"],
+                                                     w.agent.phase_cycles())),
+                                     "disc": dict(zip(["image", "tile", "bar1", "reduce_adam", "bar2"], w.disc.phase_cycles()))},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -102,10 +102,15 @@ typedef struct sg_ppo_config {
     int first_adam_step;      /* Adam step count of the first minibatch in this call (1-based) */
     int row_begin, row_end;   /* data-parallel shard: rows [row_begin,row_end) of every minibatch are
                                  processed locally (0, mini_batch_size on a single GPU) */
-    int mode;                 /* 0 = one persistent cooperative kernel, 1 = one launch per phase */
+    int mode;                 /* 0 = auto (resident if the parameter image fits in shared memory, else
+                                 persistent), 1 = one launch per phase, 2 = persistent (weights through L2),
+                                 3 = resident (weights in shared memory) */
 } sg_ppo_config;
 
 int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg);
+/* Diagnostics: byte offset inside the workspace of 8 int64 per-phase clock64 totals of CTA 0 of the last
+ * persistent launch {param image, tile phase, barrier 1, reduce+ssq, barrier 2, clip+Adam, barrier 3, -}. */
+int64_t sg_ppo_phase_cycles_offset(const sg_ppo_config* cfg);
 
 /* PPO.update (A2C/algo/ppo.py:65-157) for cfg->ppo_epoch epochs.
  *   params/adam_m/adam_v : flat policy vectors (updated in place)
@@ -133,10 +138,12 @@ typedef struct sg_disc_config {
     double beta1, beta2, adam_eps;
     int first_adam_step;
     int row_begin, row_end;   /* data-parallel shard of every minibatch */
-    int mode;                 /* 0 persistent, 1 launch per phase */
+    int mode;                 /* as sg_ppo_config.mode */
 } sg_disc_config;
 
 int64_t sg_disc_workspace_bytes(const sg_disc_config* cfg);
+/* Diagnostics, as sg_ppo_phase_cycles_offset: {param image, tile phase, barrier 1, reduce+Adam, barrier 2}. */
+int64_t sg_disc_phase_cycles_offset(const sg_disc_config* cfg);
 
 /* Discriminator.update_gail_dyn (A2C/algo/gail.py:154-193) for cfg->n_steps minibatches.
  *   expert (N_exp,F) expert rows; policy_feat = obs_feat[1:] viewed (S,F)

@@ -55,8 +55,10 @@ SIGNATURES = {
     "sg_policy_forward": (C.c_int, [c_void, C.c_int, C.c_int, C.c_int, c_void, C.c_int, c_void, c_void, c_void, c_void,
                                     c_void, c_void, c_void]),
     "sg_ppo_workspace_bytes": (C.c_int64, [C.POINTER(PpoConfig)]),
+    "sg_ppo_phase_cycles_offset": (C.c_int64, [C.POINTER(PpoConfig)]),
     "sg_ppo_update": (C.c_int, [C.POINTER(PpoConfig)] + [c_void] * 14 + [ALLREDUCE_FN, c_void, c_void]),
     "sg_disc_workspace_bytes": (C.c_int64, [C.POINTER(DiscConfig)]),
+    "sg_disc_phase_cycles_offset": (C.c_int64, [C.POINTER(DiscConfig)]),
     "sg_disc_update": (C.c_int, [C.POINTER(DiscConfig)] + [c_void] * 12 + [ALLREDUCE_FN, c_void, c_void]),
     "sg_disc_predict_reward": (C.c_int, [c_void, C.c_int, C.c_int, c_void, C.c_int, C.c_double, c_void, C.c_double,
                                          C.c_int, c_void, c_void, c_void]),

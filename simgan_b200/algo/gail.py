@@ -74,6 +74,8 @@ class Discriminator(nn.Module):
         state = dict(self.__dict__)
         state.pop("_flat", None)
         state["_ws"] = None
+        state.pop("_prof_view", None)
+        state.pop("_rms_dev", None)
         return state
 
     # ---- update --------------------------------------------------------------------------------------------
@@ -147,6 +149,7 @@ class Discriminator(nn.Module):
         _lib.timer.stop(tok)
         _lib.check(rc, "sg_disc_update")
         opt.step_count += n
+        self.__dict__["_prof_view"] = (ws, int(lib.sg_disc_phase_cycles_offset(C.byref(cfg))))
         tr = trace.cpu()
         if not bool(torch.isfinite(tr).all()):
             raise _lib.SgError("sg_disc_update produced non-finite losses (grid barrier timeout or diverged update)")
@@ -157,6 +160,12 @@ class Discriminator(nn.Module):
             le += row[1]
             lp += row[2]
         return lt / n, le / n, lp / n
+
+    def phase_cycles(self):
+        """Diagnostics: per-phase SM-clock totals of CTA 0 of the last persistent launch
+        {param image, tile phase, barrier 1, reduce+Adam, barrier 2}."""
+        ws, off = self.__dict__["_prof_view"]
+        return ws[off:off + 64].view(torch.int64)[:5].cpu().tolist()
 
     def update_gail_dyn(self, expert_loader, rollouts, replay=None):
         """gail.py:154-193.  ``expert_loader`` is the caller's DataLoader over TensorDataset(expert (N_exp,F))

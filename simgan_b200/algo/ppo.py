@@ -63,6 +63,12 @@ class PPO(object):
             self._stage[e].copy_(torch.randperm(S))
         return self._stage
 
+    def phase_cycles(self):
+        """Diagnostics: per-phase SM-clock totals of CTA 0 of the last persistent launch
+        {param image, tile phase, barrier 1, reduce+ssq, barrier 2, clip+Adam, barrier 3}."""
+        ws, off = self._prof_view
+        return ws[off:off + 64].view(torch.int64)[:7].cpu().tolist()
+
     def update(self, rollouts, permutations=None):
         """PPO.update (ppo.py:65-157).  ``permutations`` (ppo_epoch, S) overrides the sampler draw (used by
         parity tests to replay a recorded index stream)."""
@@ -123,6 +129,7 @@ class PPO(object):
         _lib.check(rc, "sg_ppo_update")
         opt.step_count += n_steps
 
+        self._prof_view = (ws, int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
         tr = trace.cpu()            # the one host sync of the update
         if not bool(torch.isfinite(tr).all()):
             raise _lib.SgError("sg_ppo_update produced non-finite losses (grid barrier timeout or diverged update)")

@@ -219,11 +219,22 @@ __device__ __forceinline__ void gemm_yW(const float* __restrict__ W, const float
         }
         __syncthreads();
         const int kw = min(KCp * V, K - kc0 * V);  // valid columns of this sweep
-        for (int e = t; e < R * kw; e += nth) {
-            const int r = e / kw, kk = e - r * kw;
-            float s = 0.f;
-            for (int q = 0; q < NS; ++q) s += scratch[(size_t)(q * R + r) * (KCp * V) + kk];
-            epi(r, kc0 * V + kk, s);
+        if (kw <= nth) {
+            // (row, column) mapping fixed per thread: one division per sweep instead of one per element
+            const int rstep = nth / kw;
+            const int kk = t % kw;
+            for (int r = t / kw; r < R; r += rstep) {
+                float s = 0.f;
+                for (int q = 0; q < NS; ++q) s += scratch[(size_t)(q * R + r) * (KCp * V) + kk];
+                epi(r, kc0 * V + kk, s);
+            }
+        } else {
+            for (int r = 0; r < R; ++r)
+                for (int kk = t; kk < kw; kk += nth) {
+                    float s = 0.f;
+                    for (int q = 0; q < NS; ++q) s += scratch[(size_t)(q * R + r) * (KCp * V) + kk];
+                    epi(r, kc0 * V + kk, s);
+                }
         }
         __syncthreads();
     }
@@ -330,6 +341,18 @@ struct GridBarrier {
     }
 };
 
+// Per-phase clock64 totals of one thread of one CTA of a persistent kernel (diagnostics: which part of an
+// optimizer step the time goes to).  slot[i] accumulates the cycles between lap(i) and the previous lap.
+struct PhaseClock {
+    long long* slots;
+    bool on;
+    long long t0;
+    __device__ __forceinline__ void start() { if (on) t0 = clock64(); }
+    __device__ __forceinline__ void lap(int i) {
+        if (on) { const long long t = clock64(); slots[i] += t - t0; t0 = t; }
+    }
+};
+
 // Deterministic CTA-wide sum of one double per thread (256 threads): xor-butterfly inside each warp,
 // then the 8 warp sums added in warp order by every thread.  `red` = 8 doubles of shared memory.
 __device__ __forceinline__ double block_sum_256(double v, double* red) {
@@ -348,11 +371,14 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float
 // Sum of `nslots` partial vectors over the float range [p0,p1) (both multiples of 4):
 // out[p] = sum_c part[c*stride + p] in a fixed order.  All 256 threads of the CTA must call.
 // `scr4` = 256 float4 of shared memory.  Ends with a CTA barrier (the slice of `out` is visible to the
-// whole CTA through L2 afterwards).
-__device__ __forceinline__ void reduce_partials_slice(const float* __restrict__ part, size_t stride, int nslots, int p0,
-                                                      int p1, float* __restrict__ out, float4* scr4, int tid) {
+// whole CTA through L2 afterwards).  Narrow slices (<= 128 float4): thread tid < n4 finalises float4 tid of
+// the slice and gets it back in `mine` (returns true), so callers can fuse work on the reduced values.
+__device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ part, size_t stride, int nslots, int p0,
+                                                      int p1, float* __restrict__ out, float4* scr4, int tid,
+                                                      float4& mine) {
     const int n4 = (p1 - p0) >> 2;
-    if (n4 <= 0) { __syncthreads(); return; }
+    mine = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n4 <= 0) { __syncthreads(); return true; }
     if (n4 <= 128) {
         const int NQ = 256 / n4;
         const int j = tid % n4, q = tid / n4;
@@ -360,7 +386,14 @@ __device__ __forceinline__ void reduce_partials_slice(const float* __restrict__ 
         if (q < NQ) {
             const float* src = part + p0 + 4 * j;
             int c = q;
-            for (; c + 3 * NQ < nslots; c += 4 * NQ) {      // four independent L2 loads in flight
+            for (; c + 7 * NQ < nslots; c += 8 * NQ) {      // eight independent L2 loads in flight
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = ld_cg4(src + (size_t)(c + u * NQ) * stride);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
+            }
+            for (; c + 3 * NQ < nslots; c += 4 * NQ) {
                 const float4 v0 = ld_cg4(src + (size_t)c * stride);
                 const float4 v1 = ld_cg4(src + (size_t)(c + NQ) * stride);
                 const float4 v2 = ld_cg4(src + (size_t)(c + 2 * NQ) * stride);
@@ -375,8 +408,10 @@ __device__ __forceinline__ void reduce_partials_slice(const float* __restrict__ 
             float4 t = scr4[tid];
             for (int qq = 1; qq < NQ; ++qq) t = f4_add(t, scr4[qq * n4 + tid]);
             __stcg(reinterpret_cast<float4*>(out + p0 + 4 * tid), t);
+            mine = t;
         }
         __syncthreads();
+        return true;
     } else {
         // wide slices (large networks): every thread owns whole columns
         for (int j = tid; j < n4; j += 256) {
@@ -394,7 +429,27 @@ __device__ __forceinline__ void reduce_partials_slice(const float* __restrict__ 
             __stcg(reinterpret_cast<float4*>(out + p0 + 4 * j), s);
         }
         __syncthreads();
+        return false;
     }
+}
+
+// CTA-private shared-memory image of a flat parameter vector <- global (through L2); ends with a CTA barrier
+__device__ __forceinline__ void load_param_image(float* Ws, const float* __restrict__ params, int P, int tid) {
+    constexpr int U = 8;
+    for (int p = 4 * tid; p < P; p += 4 * kStepThreads * U) {
+        float4 q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = p + 4 * kStepThreads * u;
+            q[u] = i < P ? ld_cg4(params + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = p + 4 * kStepThreads * u;
+            if (i < P) *reinterpret_cast<float4*>(Ws + i) = q[u];
+        }
+    }
+    __syncthreads();
 }
 
 // flat policy layout (segment starts in floats), mirrored by sg_policy_layout()

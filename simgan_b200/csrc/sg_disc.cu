@@ -40,6 +40,7 @@ struct DiscArgs {
     float* trace;
     float *gpart, *grad, *losspart;
     unsigned int* bar;
+    long long* prof;
 };
 
 struct DiscSmem {
@@ -232,10 +233,11 @@ __device__ void disc_tile(const DiscArgs& a, const float* __restrict__ W, int st
 }
 
 // ---- phase B: slice `cta` of the flat gradient (+ loss sums by CTA 0) --------------------------------
-__device__ void disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4) {
+// Returns true when thread tid < n4 holds float4 tid of the reduced slice in `mine` (narrow slices).
+__device__ bool disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4, float4& mine) {
     const int tid = threadIdx.x;
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
-    reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid);
+    const bool narrow = reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
     if (cta == 0 && tid < 32) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         for (int c = tid; c < a.nslots; c += 32) {
@@ -244,19 +246,34 @@ __device__ void disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4) {
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
         if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2); }
     }
-    __syncthreads();
+    return narrow;
 }
 
 // ---- Adam on slice `cta` (the discriminator has no gradient clipping: A2C/algo/gail.py:186-188) --------
-__device__ void disc_adam_slice(const DiscArgs& a, int step, int cta) {
+// `have`: thread tid < n4 holds float4 tid of the slice's gradient in `mine` (fused path).
+__device__ void disc_adam_slice(const DiscArgs& a, int step, int cta, bool have, float4 mine) {
     const int tid = threadIdx.x;
     const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
-    for (int p = p0 + tid; p < p1; p += kStepThreads) {
-        const float g = ld_cg(a.grad + p);
-        float pv = __ldcg(a.params + p), mv = __ldcg(a.m + p), vv = __ldcg(a.v + p);
-        adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
-        __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
+    if (have) {
+        const int pq = p0 + 4 * tid;
+        if (pq < p1) {
+            const float4 w4 = ld_cg4(a.params + pq), m4 = ld_cg4(a.m + pq), v4 = ld_cg4(a.v + pq);
+            float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+            const float g[4] = {mine.x, mine.y, mine.z, mine.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) adam_update(w[i], m[i], v[i], g[i], a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            __stcg(reinterpret_cast<float4*>(a.params + pq), make_float4(w[0], w[1], w[2], w[3]));
+            __stcg(reinterpret_cast<float4*>(a.m + pq), make_float4(m[0], m[1], m[2], m[3]));
+            __stcg(reinterpret_cast<float4*>(a.v + pq), make_float4(v[0], v[1], v[2], v[3]));
+        }
+    } else {
+        for (int p = p0 + tid; p < p1; p += kStepThreads) {
+            const float g = ld_cg(a.grad + p);
+            float pv = __ldcg(a.params + p), mv = __ldcg(a.m + p), vv = __ldcg(a.v + p);
+            adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
+        }
     }
     if (cta == 0 && tid == 0) {
         const float invB = 1.f / (float)a.B;
@@ -283,49 +300,33 @@ __device__ __forceinline__ void disc_poison_on_timeout(const DiscArgs& a) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
 }
 
-// CTA-private shared-memory image of the flat parameter vector <- global (through L2)
-__device__ __forceinline__ void load_param_image(float* Ws, const float* __restrict__ params, int P, int tid) {
-    constexpr int U = 4;
-    for (int p = 4 * tid; p < P; p += 4 * kStepThreads * U) {
-        float4 q[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = p + 4 * kStepThreads * u;
-            q[u] = i < P ? ld_cg4(params + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = p + 4 * kStepThreads * u;
-            if (i < P) *reinterpret_cast<float4*>(Ws + i) = q[u];
-        }
-    }
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(kStepThreads, 1) disc_resident_kernel(DiscArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    float* Ws = smem; float* tile = Ws + a.P;
-    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
-    for (int step = 0; step < a.nsteps; ++step) {
-        load_param_image(Ws, a.params, a.P, threadIdx.x);
-        disc_phaseA<LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
-        gb.sync();
-        disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile));
-        disc_adam_slice(a, step, blockIdx.x);
-        gb.sync();
-    }
-    disc_poison_on_timeout(a);
-}
-
+// RESIDENT: every CTA refreshes a private shared-memory image of the parameters at the start of each step
+// and the tile phase reads its weights from there; otherwise weights come from global memory through L2.
+template <bool RESIDENT>
 __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscArgs a) {
     extern __shared__ __align__(16) float smem[];
+    float* Ws = smem;
+    float* tile = RESIDENT ? smem + a.P : smem;
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    PhaseClock pc{a.prof, blockIdx.x == 0 && threadIdx.x == 0};
+    pc.start();
     for (int step = 0; step < a.nsteps; ++step) {
-        disc_phaseA<LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
+        if (RESIDENT) {
+            load_param_image(Ws, a.params, a.P, threadIdx.x);
+            pc.lap(0);
+            disc_phaseA<LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+        } else {
+            disc_phaseA<LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, tile);
+        }
+        pc.lap(1);
         gb.sync();
-        disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(smem));
-        disc_adam_slice(a, step, blockIdx.x);
+        pc.lap(2);
+        float4 mine;
+        const bool have = disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile), mine);
+        disc_adam_slice(a, step, blockIdx.x, have, mine);
+        pc.lap(3);
         gb.sync();
+        pc.lap(4);
     }
     disc_poison_on_timeout(a);
 }
@@ -335,9 +336,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_phaseA_kernel(DiscArgs a
 }
 __global__ void __launch_bounds__(kStepThreads) disc_phaseB_kernel(DiscArgs a) {
     __shared__ float4 scr4[kStepThreads];
-    disc_reduce_slice(a, blockIdx.x, scr4);
+    float4 mine;
+    disc_reduce_slice(a, blockIdx.x, scr4, mine);
 }
-__global__ void __launch_bounds__(kStepThreads) disc_phaseC_kernel(DiscArgs a, int step) { disc_adam_slice(a, step, blockIdx.x); }
+__global__ void __launch_bounds__(kStepThreads) disc_phaseC_kernel(DiscArgs a, int step) {
+    disc_adam_slice(a, step, blockIdx.x, false, make_float4(0.f, 0.f, 0.f, 0.f));
+}
 
 // ---- reward prediction ---------------------------------------------------------------------------
 // raw reward of predict_reward_combined (gail.py:203-205) for n_rows rows of (.,F); optionally the
@@ -506,7 +510,7 @@ static int disc_validate(const sg_disc_config* c) {
                "sg_disc: resident mode needs %zu bytes of shared memory", disc_resident_smem_bytes(c));
     return SG_OK;
 }
-struct DiscWs { size_t gpart, grad, losspart, bar, total; };
+struct DiscWs { size_t gpart, grad, losspart, bar, prof, total; };
 static DiscWs disc_ws(const sg_disc_config* c, int grid) {
     DiscLayout L = make_disc_layout(c->feat_dim, c->hidden);
     DiscWs w;
@@ -516,6 +520,7 @@ static DiscWs disc_ws(const sg_disc_config* c, int grid) {
     w.grad = take((size_t)(L.total + 4) * sizeof(float));
     w.losspart = take((size_t)grid * 4 * sizeof(float));
     w.bar = take(2 * sizeof(unsigned int));
+    w.prof = take(8 * sizeof(long long));
     w.total = o;
     return w;
 }
@@ -564,6 +569,11 @@ int64_t sg_disc_workspace_bytes(const sg_disc_config* cfg) {
     return (int64_t)disc_ws(cfg, disc_grid(cfg, nullptr)).total;
 }
 
+int64_t sg_disc_phase_cycles_offset(const sg_disc_config* cfg) {
+    if (disc_validate(cfg)) return -1;
+    return (int64_t)disc_ws(cfg, disc_grid(cfg, nullptr)).prof;
+}
+
 int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, float* adam_v, const float* expert,
                    const float* policy_feat, const int32_t* expert_idx, const int32_t* policy_idx, const float* alpha,
                    const float* step_size, const float* bc2_sqrt, float* trace, void* workspace,
@@ -593,14 +603,14 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     a.expert = expert; a.policy = policy_feat; a.alpha = alpha; a.eidx = expert_idx; a.pidx = policy_idx;
     a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
-    a.bar = (unsigned int*)(ws + w.bar);
+    a.bar = (unsigned int*)(ws + w.bar); a.prof = (long long*)(ws + w.prof);
     const size_t smem_tile = disc_tile_smem_floats(cfg) * sizeof(float);
     const size_t smem_res = disc_resident_smem_bytes(cfg);
     int mode = cfg->mode;
     if (mode == 0) mode = smem_res <= kDiscMaxDynSmem ? 3 : 2;
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
     if (mode == 3 || mode == 2) {
-        const void* fn = mode == 3 ? (const void*)disc_resident_kernel : (const void*)disc_persistent_kernel;
+        const void* fn = mode == 3 ? (const void*)disc_persistent_kernel<true> : (const void*)disc_persistent_kernel<false>;
         const size_t smem = mode == 3 ? smem_res : smem_tile;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;

@@ -11,15 +11,12 @@
 //
 // Kernel variants (sg_ppo_config.mode):
 //   resident   (mode 0 when it fits, mode 3 forced) ONE persistent cooperative kernel for all steps of
-//              the call; every CTA keeps a private image of the parameters AND the Adam moments in
-//              shared memory, applies the identical clip+Adam update redundantly after all-gathering
-//              the reduced gradient, and reads its weights from shared memory in the tile phase.
-//              Two grid barriers per optimizer step.
-//   persistent (mode 0 otherwise, mode 2 forced) same single launch, parameters stay in global memory
-//              (read through L2), Adam is partitioned by slice; three grid barriers per step.
+//              the call, three grid barriers per step; every CTA refreshes a private shared-memory image
+//              of the flat parameter vector after each Adam step and the tile phase reads its weights
+//              from shared memory.
+//   persistent (mode 0 otherwise, mode 2 forced) same single launch, weights read from global through L2.
 //   phased     (mode 1) one launch per phase; the data-parallel path (host allreduce callback).
-// persistent and phased are bit-identical; resident differs only by fp32 reassociation of nothing --
-// it runs the same arithmetic in the same order -- and is bit-identical too.
+// All three run the same arithmetic in the same order and are bit-identical.
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
 
@@ -40,6 +37,7 @@ struct PpoArgs {
     float *gpart, *grad, *losspart, *scal;
     double* ssq;
     unsigned int* bar;
+    long long* prof;      // per-phase clock64 totals of CTA 0 (sg_ppo_phase_cycles)
 };
 
 template <int R>
@@ -233,11 +231,12 @@ __device__ __forceinline__ float eff_grad(const PpoArgs& a, int p, float g) {
 
 // ---- phase B: slice `cta` of the flat gradient (+ loss sums and the entropy scalar by CTA 0) ---------
 // `ls` = logstd of the CURRENT parameters (before this step's Adam), read with WL.
+// Returns true when thread tid < n4 holds float4 tid of the reduced slice in `mine` (narrow slices).
 template <class WL>
-__device__ void ppo_reduce_slice(const PpoArgs& a, int cta, float4* scr4, const float* ls) {
+__device__ bool ppo_reduce_slice(const PpoArgs& a, int cta, float4* scr4, const float* ls, float4& mine) {
     const int tid = threadIdx.x;
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
-    reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid);
+    const bool narrow = reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
     if (cta == 0 && tid < 32) {
         // loss sums over the partial slots: lane-strided, then a fixed butterfly
         float s0 = 0.f, s1 = 0.f;
@@ -245,34 +244,31 @@ __device__ void ppo_reduce_slice(const PpoArgs& a, int cta, float4* scr4, const 
         s0 = warp_sum(s0); s1 = warp_sum(s1);
         if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.scal, gaussian_entropy<WL>(ls, a.A)); }
     }
+    return narrow;
 }
 
-// sum of squares (fp64) of slice `cta` of the effective gradient -> ssq[cta].  Reads the (possibly
-// allreduced) flat gradient back through L2 so the fused and the phased paths do identical arithmetic.
-__device__ void ppo_ssq_slice(const PpoArgs& a, int cta, double* red) {
+__device__ __forceinline__ double ssq4(const PpoArgs& a, int p, float4 g) {
+    const float gx = eff_grad(a, p, g.x), gy = eff_grad(a, p + 1, g.y), gz = eff_grad(a, p + 2, g.z), gw = eff_grad(a, p + 3, g.w);
+    double s = (double)gx * (double)gx;
+    s += (double)gy * (double)gy; s += (double)gz * (double)gz; s += (double)gw * (double)gw;
+    return s;
+}
+
+// sum of squares (fp64) of slice `cta` of the effective gradient -> ssq[cta].  `have`: thread tid < n4
+// already holds float4 tid of the slice in `mine` (fused path); otherwise the (possibly allreduced) flat
+// gradient is read back through L2.  Thread <-> element mapping and arithmetic are the same either way.
+__device__ void ppo_ssq_slice(const PpoArgs& a, int cta, double* red, bool have, float4 mine) {
     const int tid = threadIdx.x;
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
     double s = 0.0;
-    for (int p = p0 + 4 * tid; p < p1; p += 4 * kStepThreads) {
-        const float4 g = ld_cg4(a.grad + p);
-        const float gx = eff_grad(a, p, g.x), gy = eff_grad(a, p + 1, g.y), gz = eff_grad(a, p + 2, g.z), gw = eff_grad(a, p + 3, g.w);
-        s += (double)gx * (double)gx; s += (double)gy * (double)gy; s += (double)gz * (double)gz; s += (double)gw * (double)gw;
+    if (have) {
+        const int p = p0 + 4 * tid;
+        if (p < p1) s += ssq4(a, p, mine);
+    } else {
+        for (int p = p0 + 4 * tid; p < p1; p += 4 * kStepThreads) s += ssq4(a, p, ld_cg4(a.grad + p));
     }
     const double tot = block_sum_256(s, red);
     if (tid == 0) __stcg(a.ssq + cta, tot);
-}
-
-// global gradient norm from the slice partials (identical in every CTA) -> clip factor of clip_grad_norm_
-__device__ __forceinline__ float ppo_clip_factor(const PpoArgs& a, double* red, float* norm_out) {
-    const int tid = threadIdx.x;
-    double s = 0.0;
-    for (int c = tid; c < a.nslices; c += kStepThreads) s += __ldcg(a.ssq + c);
-    const double tot = block_sum_256(s, red);
-    const float norm = (float)sqrt(tot);
-    float clip = a.max_norm / (norm + 1e-6f);
-    if (clip > 1.f) clip = 1.f;
-    *norm_out = norm;
-    return clip;
 }
 
 __device__ __forceinline__ void ppo_write_trace(const PpoArgs& a, int step, float norm) {
@@ -284,53 +280,44 @@ __device__ __forceinline__ void ppo_write_trace(const PpoArgs& a, int step, floa
     tr[3] = norm;
 }
 
-// ---- phase C, partitioned: clip + Adam on slice `cta` of the global parameter vector -----------------
-__device__ void ppo_adam_slice(const PpoArgs& a, int step, int cta, double* red) {
+// ---- phase C: global-norm clip + Adam on slice `cta` of the parameter vector ----------------------------
+// Narrow slices (`have`): thread tid < n4 updates float4 tid of the slice, gradient in `mine`; the parameter
+// and moment loads are issued before the norm is formed so that one L2 round trip covers everything.
+__device__ void ppo_adam_slice(const PpoArgs& a, int step, int cta, double* red, bool have, float4 mine) {
     const int tid = threadIdx.x;
-    float norm;
-    const float clip = ppo_clip_factor(a, red, &norm);
-    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
-    const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
-    for (int p = p0 + tid; p < p1; p += kStepThreads) {
-        const float g = eff_grad(a, p, ld_cg(a.grad + p)) * clip;
-        float pv = __ldcg(a.params + p), mv = __ldcg(a.m + p), vv = __ldcg(a.v + p);
-        adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
-        __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
-    }
-}
-
-// ---- phase C, redundant: every CTA updates its private shared-memory image of params / moments -------
-__device__ void ppo_adam_resident(const PpoArgs& a, int step, int cta, float* Ws, float* Ms, float* Vs, double* red) {
-    const int tid = threadIdx.x;
-    float norm;
-    const float clip = ppo_clip_factor(a, red, &norm);
-    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
     const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
-    constexpr int U = 4;
-    for (int p = 4 * tid; p < a.P; p += 4 * kStepThreads * U) {
-        float4 g[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int q = p + 4 * kStepThreads * u;
-            g[u] = q < a.P ? ld_cg4(a.grad + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int q = p + 4 * kStepThreads * u;
-            if (q >= a.P) break;
-            const float gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
-            float4 pw = *reinterpret_cast<float4*>(Ws + q), pm = *reinterpret_cast<float4*>(Ms + q), pv = *reinterpret_cast<float4*>(Vs + q);
-            float w[4] = {pw.x, pw.y, pw.z, pw.w}, m[4] = {pm.x, pm.y, pm.z, pm.w}, v[4] = {pv.x, pv.y, pv.z, pv.w};
+    const int pq = p0 + 4 * tid;
+    const bool mineok = have && pq < p1;
+    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = w4, v4 = w4;
+    if (mineok) { w4 = ld_cg4(a.params + pq); m4 = ld_cg4(a.m + pq); v4 = ld_cg4(a.v + pq); }
+    // global gradient norm from the slice partials, identical in every CTA (clip_grad_norm_, ppo.py:143-144)
+    double s = 0.0;
+    for (int c = tid; c < a.nslices; c += kStepThreads) s += __ldcg(a.ssq + c);
+    const double tot = block_sum_256(s, red);
+    const float norm = (float)sqrt(tot);
+    float clip = a.max_norm / (norm + 1e-6f);
+    if (clip > 1.f) clip = 1.f;
+    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
+    if (have) {
+        if (mineok) {
+            float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+            const float g[4] = {mine.x, mine.y, mine.z, mine.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                adam_update(w[i], m[i], v[i], eff_grad(a, q + i, gg[i]) * clip, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
-            *reinterpret_cast<float4*>(Ws + q) = make_float4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<float4*>(Ms + q) = make_float4(m[0], m[1], m[2], m[3]);
-            *reinterpret_cast<float4*>(Vs + q) = make_float4(v[0], v[1], v[2], v[3]);
+                adam_update(w[i], m[i], v[i], eff_grad(a, pq + i, g[i]) * clip, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            __stcg(reinterpret_cast<float4*>(a.params + pq), make_float4(w[0], w[1], w[2], w[3]));
+            __stcg(reinterpret_cast<float4*>(a.m + pq), make_float4(m[0], m[1], m[2], m[3]));
+            __stcg(reinterpret_cast<float4*>(a.v + pq), make_float4(v[0], v[1], v[2], v[3]));
+        }
+    } else {
+        for (int p = p0 + tid; p < p1; p += kStepThreads) {
+            const float g = eff_grad(a, p, ld_cg(a.grad + p)) * clip;
+            float pv = __ldcg(a.params + p), mv = __ldcg(a.m + p), vv = __ldcg(a.v + p);
+            adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
         }
     }
-    __syncthreads();
 }
 
 __device__ __forceinline__ void poison_trace_on_timeout(const PpoArgs& a) {
@@ -338,50 +325,43 @@ __device__ __forceinline__ void poison_trace_on_timeout(const PpoArgs& a) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
 }
 
-template <int R>
-__global__ void __launch_bounds__(kStepThreads, 1) ppo_resident_kernel(PpoArgs a) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ double red[kStepThreads / 32];
-    const int tid = threadIdx.x;
-    float* Ws = smem; float* Ms = Ws + a.P; float* Vs = Ms + a.P; float* tile = Vs + a.P;
-    for (int p = 4 * tid; p < a.P; p += 4 * kStepThreads) {
-        *reinterpret_cast<float4*>(Ws + p) = ld_cg4(a.params + p);
-        *reinterpret_cast<float4*>(Ms + p) = ld_cg4(a.m + p);
-        *reinterpret_cast<float4*>(Vs + p) = ld_cg4(a.v + p);
-    }
-    __syncthreads();
-    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
-    for (int step = 0; step < a.nsteps; ++step) {
-        ppo_phaseA<R, LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
-        gb.sync();
-        ppo_reduce_slice<LdShared>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.L.ls);
-        ppo_ssq_slice(a, blockIdx.x, red);
-        gb.sync();
-        ppo_adam_resident(a, step, blockIdx.x, Ws, Ms, Vs, red);
-    }
-    if (blockIdx.x == 0) {
-        for (int p = 4 * tid; p < a.P; p += 4 * kStepThreads) {
-            __stcg(reinterpret_cast<float4*>(a.params + p), *reinterpret_cast<float4*>(Ws + p));
-            __stcg(reinterpret_cast<float4*>(a.m + p), *reinterpret_cast<float4*>(Ms + p));
-            __stcg(reinterpret_cast<float4*>(a.v + p), *reinterpret_cast<float4*>(Vs + p));
-        }
-    }
-    poison_trace_on_timeout(a);
-}
-
-template <int R>
+// RESIDENT: every CTA refreshes a private shared-memory image of the parameters after each Adam step and
+// the tile phase reads its weights from there; otherwise weights are read from global memory through L2.
+template <int R, bool RESIDENT>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[kStepThreads / 32];
+    float* Ws = smem;
+    float* tile = RESIDENT ? smem + a.P : smem;
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    PhaseClock pc{a.prof, blockIdx.x == 0 && threadIdx.x == 0};
+    pc.start();
     for (int step = 0; step < a.nsteps; ++step) {
-        ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
+        float4 mine;
+        bool have;
+        if (RESIDENT) {
+            load_param_image(Ws, a.params, a.P, threadIdx.x);
+            pc.lap(0);
+            ppo_phaseA<R, LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+            pc.lap(1);
+            gb.sync();
+            pc.lap(2);
+            have = ppo_reduce_slice<LdShared>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.L.ls, mine);
+        } else {
+            ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, tile);
+            pc.lap(1);
+            gb.sync();
+            pc.lap(2);
+            have = ppo_reduce_slice<LdGlobal>(a, blockIdx.x, reinterpret_cast<float4*>(tile), a.params + a.L.ls, mine);
+        }
+        ppo_ssq_slice(a, blockIdx.x, red, have, mine);
+        pc.lap(3);
         gb.sync();
-        ppo_reduce_slice<LdGlobal>(a, blockIdx.x, reinterpret_cast<float4*>(smem), a.params + a.L.ls);
-        ppo_ssq_slice(a, blockIdx.x, red);
+        pc.lap(4);
+        ppo_adam_slice(a, step, blockIdx.x, red, have, mine);
+        pc.lap(5);
         gb.sync();
-        ppo_adam_slice(a, step, blockIdx.x, red);
-        gb.sync();
+        pc.lap(6);
     }
     poison_trace_on_timeout(a);
 }
@@ -393,15 +373,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_phaseA_kernel(PpoArgs a, 
 }
 __global__ void __launch_bounds__(kStepThreads) ppo_phaseB_kernel(PpoArgs a) {
     __shared__ float4 scr4[kStepThreads];
-    ppo_reduce_slice<LdGlobal>(a, blockIdx.x, scr4, a.params + a.L.ls);
+    float4 mine;
+    ppo_reduce_slice<LdGlobal>(a, blockIdx.x, scr4, a.params + a.L.ls, mine);
 }
 __global__ void __launch_bounds__(kStepThreads) ppo_ssq_kernel(PpoArgs a) {
     __shared__ double red[kStepThreads / 32];
-    ppo_ssq_slice(a, blockIdx.x, red);
+    ppo_ssq_slice(a, blockIdx.x, red, false, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 __global__ void __launch_bounds__(kStepThreads) ppo_phaseC_kernel(PpoArgs a, int step) {
     __shared__ double red[kStepThreads / 32];
-    ppo_adam_slice(a, step, blockIdx.x, red);
+    ppo_adam_slice(a, step, blockIdx.x, red, false, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
 static int ppo_tiles(const sg_ppo_config* c) { return (c->row_end - c->row_begin + kRows - 1) / kRows; }
@@ -422,7 +403,7 @@ static size_t ppo_tile_smem_floats(const sg_ppo_config* c) {
 }
 static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
-    return (3 * (size_t)L.total + ppo_tile_smem_floats(c)) * sizeof(float);
+    return ((size_t)L.total + ppo_tile_smem_floats(c)) * sizeof(float);
 }
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus static shared memory headroom
 
@@ -444,7 +425,7 @@ static int ppo_validate(const sg_ppo_config* c) {
 }
 
 struct PpoWs {
-    size_t gpart, grad, losspart, scal, ssq, bar, total;
+    size_t gpart, grad, losspart, scal, ssq, bar, prof, total;
 };
 static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
@@ -457,6 +438,7 @@ static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     w.scal = take(4 * sizeof(float));
     w.ssq = take((size_t)grid * sizeof(double));
     w.bar = take(2 * sizeof(unsigned int));
+    w.prof = take(8 * sizeof(long long));
     w.total = o;
     return w;
 }
@@ -471,6 +453,11 @@ extern "C" {
 int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg) {
     if (ppo_validate(cfg)) return -1;
     return (int64_t)ppo_ws(cfg, ppo_grid(cfg, nullptr)).total;
+}
+
+int64_t sg_ppo_phase_cycles_offset(const sg_ppo_config* cfg) {
+    if (ppo_validate(cfg)) return -1;
+    return (int64_t)ppo_ws(cfg, ppo_grid(cfg, nullptr)).prof;
 }
 
 int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float* adam_v, const float* obs,
@@ -512,7 +499,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     a.obs = obs; a.actions = actions; a.vpred = value_preds; a.ret = returns; a.oldlp = old_logp; a.advstats = adv_stats;
     a.perm = perm; a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
-    a.scal = (float*)(ws + w.scal); a.ssq = (double*)(ws + w.ssq); a.bar = (unsigned int*)(ws + w.bar);
+    a.scal = (float*)(ws + w.scal); a.ssq = (double*)(ws + w.ssq); a.bar = (unsigned int*)(ws + w.bar); a.prof = (long long*)(ws + w.prof);
 
     const size_t smem_tile = ppo_tile_smem_floats(cfg) * sizeof(float);
     const size_t smem_res = ppo_resident_smem_bytes(cfg);
@@ -522,7 +509,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
 
     if (mode == 3 || mode == 2) {
-        const void* fn = mode == 3 ? (const void*)ppo_resident_kernel<kRows> : (const void*)ppo_persistent_kernel<kRows>;
+        const void* fn = mode == 3 ? (const void*)ppo_persistent_kernel<kRows, true> : (const void*)ppo_persistent_kernel<kRows, false>;
         const size_t smem = mode == 3 ? smem_res : smem_tile;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
