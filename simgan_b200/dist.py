@@ -34,7 +34,7 @@ class DataParallel(object):
 
     def shard(self, n_rows):
         b, e = shard_bounds(n_rows, self.rank, self.world)
-        if e <= b:
+        if n_rows < self.world:          # some rank would get an empty shard: refuse on EVERY rank
             raise ValueError("minibatch of %d rows cannot be split over %d ranks" % (n_rows, self.world))
         return b, e
 

@@ -1,0 +1,225 @@
+"""Host-side logic of the reference-shaped classes (no GPU): RNG-stream emulation, Adam scalars, CPU policy
+path used by env workers, construction order, pickling / module aliasing, loud failure without CUDA."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader, TensorDataset
+from torch.utils.data.sampler import BatchSampler, SubsetRandomSampler
+
+import simgan_b200 as sg
+from simgan_b200 import _lib, compat, dist as sg_dist
+from simgan_b200.algo.adam import FusedAdam
+from oracle import ppo_gail_oracle as orc
+from oracle import ref_shim
+from oracle.ref_shim import BoxSpace
+
+
+def test_adam_schedule_matches_torch_scalars():
+    opt = FusedAdam([], lr=3e-4, betas=(0.9, 0.999), eps=1e-5)
+    opt.step_count = 7
+    sch = opt.schedule(5)
+    for i in range(5):
+        t = 8 + i
+        assert sch[0, i] == np.float32(3e-4 / (1 - 0.9 ** t))
+        assert sch[1, i] == np.float32((1 - 0.999 ** t) ** 0.5)
+    # one real torch.optim.Adam step against the kernel's op order restated on the host
+    p = torch.tensor([0.3, -1.2, 2.0]); g = torch.tensor([0.5, -0.25, 1e-3])
+    ref = p.clone().requires_grad_(True)
+    o = torch.optim.Adam([ref], lr=3e-4, eps=1e-5)
+    ref.grad = g.clone()
+    o.step()
+    opt2 = FusedAdam([], lr=3e-4, eps=1e-5)
+    ss, bc2 = opt2.schedule(1)[:, 0]
+    m = torch.zeros(3).lerp(g, 1 - 0.9)
+    v = torch.zeros(3).mul(0.999).addcmul(g, g, value=1 - 0.999)
+    mine = p + (-float(ss) * m) / (v.sqrt() / float(bc2) + 1e-5)
+    assert torch.equal(mine, ref.detach())
+
+
+@pytest.mark.parametrize("n_expert,S,B", [(1000, 512, 128), (300, 2048, 128), (130, 128, 32)])
+def test_disc_epoch_index_stream_matches_dataloader_zip(n_expert, S, B):
+    """draw_epoch_indices == the draws zip(DataLoader(shuffle), feed_forward_generator) + rand(B,1) make
+    (A2C/algo/gail.py:157-163, :72), including where the CPU generator is left afterwards."""
+    data = torch.arange(n_expert, dtype=torch.float32).unsqueeze(1)
+    loader = DataLoader(TensorDataset(data), batch_size=B, shuffle=True, drop_last=True)
+    torch.manual_seed(5)
+    ref_e, ref_p, ref_a = [], [], []
+
+    def rollout_gen():           # generator body runs at the first next(), like the reference's generator
+        sampler = BatchSampler(SubsetRandomSampler(range(S)), B, drop_last=True)
+        for idx in sampler:
+            yield idx
+    for eb, pb in zip(loader, rollout_gen()):
+        ref_e.append(eb[0][:, 0].long())
+        ref_p.append(torch.tensor(pb))
+        ref_a.append(torch.rand(B, 1)[:, 0])
+    after_ref = torch.rand(3)
+    torch.manual_seed(5)
+    e, p, a = sg.Discriminator.draw_epoch_indices(n_expert, B, True, S)
+    after = torch.rand(3)
+    n = len(ref_e)
+    assert e.shape == (n, B) and p.shape == (n, B) and a.shape == (n, B)
+    assert torch.equal(e, torch.stack(ref_e)) and torch.equal(p, torch.stack(ref_p))
+    assert torch.equal(a, torch.stack(ref_a))
+    if n_expert // B <= S // B:
+        # zip stops on the loader side first: the streams leave the generator in the same place
+        assert torch.equal(after, after_ref)
+
+
+def test_ppo_permutations_are_the_batch_sampler_stream():
+    pol = sg.Policy((14,), BoxSpace(7), base_kwargs={"recurrent": False, "hidden_size": 64})
+    agent = sg.PPO(pol, 0.2, 3, 4, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    S = 203
+    torch.manual_seed(9)
+    perm = agent.draw_permutations(S).clone()
+    torch.manual_seed(9)
+    for e in range(3):
+        chunks = list(BatchSampler(SubsetRandomSampler(range(S)), S // 4, drop_last=True))
+        assert len(chunks) == 4
+        flat = torch.tensor([i for c in chunks for i in c])
+        assert torch.equal(perm[e, :flat.numel()].long(), flat)
+
+
+def test_construction_order_and_cpu_policy_path_match_oracle():
+    torch.manual_seed(3)
+    pol = sg.Policy((14,), BoxSpace(7), base_kwargs={"recurrent": False, "hidden_size": 64})
+    d = sg.Discriminator(25, 100, torch.device("cpu"))
+    torch.manual_seed(3)
+    p = orc.init_policy(14, 64, 7)
+    dp = orc.init_disc(25, 100)
+    for q, k in zip(pol.hot_path_parameters(), orc.POLICY_KEYS):
+        assert torch.equal(q.data.reshape(-1), p[k].reshape(-1)), k
+    for q, k in zip(d.hot_path_parameters(), orc.DISC_KEYS):
+        assert torch.equal(q.data.reshape(-1), dp[k].reshape(-1)), k
+    assert [n for n, _ in pol.named_parameters()] == [
+        "base.actor.0.weight", "base.actor.0.bias", "base.actor.2.weight", "base.actor.2.bias",
+        "base.critic.0.weight", "base.critic.0.bias", "base.critic.2.weight", "base.critic.2.bias",
+        "base.critic_linear.weight", "base.critic_linear.bias", "dist.fc_mean.weight", "dist.fc_mean.bias",
+        "dist.logstd._bias"]
+    # batch-1 CPU inference, the way env workers call it (hopper_env_combined_policy.py:213-216)
+    x = torch.randn(1, 14)
+    with torch.no_grad():
+        v, a, lp, _ = pol.act(x, torch.zeros(1, 1), torch.ones(1, 1), deterministic=True)
+        v2, lp2, ent, _ = pol.evaluate_actions(x, None, None, a)
+    vo, ao, lpo = orc.policy_act(p, x, deterministic=True)
+    assert torch.equal(v, vo) and torch.equal(a, ao) and torch.equal(lp, lpo)
+    assert torch.equal(v2, vo) and torch.equal(lp2, lpo)
+    assert pol.is_recurrent is False and pol.recurrent_hidden_state_size == 1
+    pol.reset_variance(BoxSpace(7), -1.5)
+    assert float(pol.dist.logstd._bias.detach()[0]) == -1.5
+    pol.reset_critic((14,))
+    assert pol.base.critic[0].out_features == 64
+
+
+def test_whole_object_pickles_round_trip():
+    pol = sg.Policy((11,), BoxSpace(3), base_kwargs={"recurrent": False, "hidden_size": 64})
+    d = sg.Discriminator(25, 100, torch.device("cpu"))
+    buf, buf_d = io.BytesIO(), io.BytesIO()
+    torch.save([pol, None], buf)            # main_gail_dyn_ppo.py:307-316 saves [actor_critic, ob_rms]
+    torch.save(d, buf_d)
+    buf.seek(0)
+    buf_d.seek(0)
+    pol2, _ = torch.load(buf, weights_only=False)
+    d2 = torch.load(buf_d, weights_only=False)
+    x = torch.randn(2, 11)
+    with torch.no_grad():
+        assert torch.equal(pol.act(x, None, None, deterministic=True)[1], pol2.act(x, None, None, deterministic=True)[1])
+    for a, b in zip(d.parameters(), d2.parameters()):
+        assert torch.equal(a, b)
+
+
+def test_alias_modules_resolve_to_this_package():
+    compat.install()
+    try:
+        import third_party.a2c_ppo_acktr.model as m
+        from third_party.a2c_ppo_acktr import algo, utils
+        from third_party.a2c_ppo_acktr.algo import gail
+        from third_party.a2c_ppo_acktr.storage import RolloutStorage
+        from third_party.a2c_ppo_acktr.baselines.common.running_mean_std import RunningMeanStd
+        assert m.Policy is sg.Policy and algo.PPO is sg.PPO and gail.Discriminator is sg.Discriminator
+        assert RolloutStorage is sg.RolloutStorage and RunningMeanStd is sg.RunningMeanStd
+        assert utils.update_linear_schedule is sg.utils.update_linear_schedule
+    finally:
+        compat.uninstall()
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (GPU box)")
+def test_reference_checkpoint_loads_into_our_classes():
+    """The reference's shipped behaviour policy (a whole-object pickle of ITS Policy class) un-pickles into
+    simgan_b200.Policy once the aliases are installed, and acts identically on the CPU."""
+    path = os.path.join(ref_shim.REF_ROOT, "trained_models_hopper_bullet_new11", "ppo", "HopperURDFEnv-v3.pt")
+    ref = ref_shim.load()
+    saved = {k: v for k, v in __import__("sys").modules.items() if k.startswith("third_party")}
+    try:
+        import sys
+        sys.modules.update(ref.modules)
+        theirs, _ = torch.load(path, weights_only=False, map_location="cpu")
+        for k in list(sys.modules):
+            if k.startswith("third_party") or k in ("pybullet",) or k.startswith("my_pybullet_envs"):
+                del sys.modules[k]
+        compat.install()
+        ours, _ = torch.load(path, weights_only=False, map_location="cpu")
+    finally:
+        compat.uninstall()
+        import sys
+        for k in list(sys.modules):
+            if k.startswith("third_party"):
+                del sys.modules[k]
+        sys.modules.update(saved)
+    assert type(ours) is sg.Policy and type(theirs) is not sg.Policy
+    x = torch.randn(5, 11)
+    with torch.no_grad():
+        vo, ao, lo, _ = ours.act(x, torch.zeros(5, 1), torch.ones(5, 1), deterministic=True)
+        vt, at, lt, _ = theirs.act(x, torch.zeros(5, 1), torch.ones(5, 1), deterministic=True)
+    assert torch.equal(vo, vt) and torch.equal(ao, at) and torch.equal(lo, lt)
+    assert (ours.obs_dim, ours.hidden_size, ours.act_dim) == (11, 64, 3)
+
+
+def test_hot_path_refuses_to_run_without_cuda():
+    pol = sg.Policy((14,), BoxSpace(7), base_kwargs={"recurrent": False, "hidden_size": 64})
+    agent = sg.PPO(pol, 0.2, 1, 2, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    rs = sg.RolloutStorage(8, 2, (14,), BoxSpace(7), 1, 25)
+    with pytest.raises(_lib.SgError, match="no CPU fallback"):
+        rs.compute_returns(torch.zeros(2, 1), True, 0.99, 0.95)
+    with pytest.raises(_lib.SgError, match="no CPU fallback"):
+        agent.update(rs)
+    with pytest.raises(_lib.SgError, match="no CPU fallback"):
+        list(rs.feed_forward_generator(None, num_mini_batch=2))
+    d = sg.Discriminator(25, 100, torch.device("cpu"))
+    with pytest.raises(_lib.SgError):
+        d.predict_reward_combined(torch.zeros(2, 25), 0.99, torch.ones(2, 1))
+    loader = DataLoader(TensorDataset(torch.zeros(256, 25)), batch_size=128, shuffle=True, drop_last=True)
+    with pytest.raises(_lib.SgError):
+        d.update_gail_dyn(loader, rs)
+
+
+def test_rollout_storage_host_staging_and_shapes():
+    T, N, O, A, F = 5, 3, 14, 7, 25
+    rs = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, F)
+    buf = orc.new_buffer(T, N, O, A, F)
+    assert {k: tuple(getattr(rs, k).shape) for k in buf} == {k: tuple(v.shape) for k, v in buf.items()}
+    g = torch.Generator().manual_seed(0)
+    step = 0
+    for _ in range(T + 2):       # wraps around like the reference (storage.py:84)
+        args = [torch.randn(N, O, generator=g), torch.zeros(N, 1), torch.randn(N, A, generator=g),
+                torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g), torch.randn(N, 1, generator=g),
+                torch.ones(N, 1), torch.ones(N, 1), torch.randn(N, F, generator=g)]
+        rs.insert(*args)
+        step = orc.buffer_insert(buf, step, *args)
+    rs.after_update()
+    orc.buffer_after_update(buf)
+    for k, v in buf.items():
+        assert torch.equal(getattr(rs, k), v), k
+
+
+@pytest.mark.parametrize("n,world", [(1024, 8), (128, 3), (7, 7), (1000, 6)])
+def test_shard_bounds_partition(n, world):
+    edges = [sg_dist.shard_bounds(n, r, world) for r in range(world)]
+    assert edges[0][0] == 0 and edges[-1][1] == n
+    for (a, b), (c, d) in zip(edges, edges[1:]):
+        assert b == c and b > a
+    sizes = [b - a for a, b in edges]
+    assert max(sizes) - min(sizes) <= 1
