@@ -1,0 +1,95 @@
+"""Data-parallel (minibatch-sharded) updates on >= 2 GPUs: G-GPU result == 1-GPU result within fp32
+reassociation tolerance (SURVEY.md section 8e -- there is no reference counterpart for multi-GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _run_case(g, dp_on, dev):
+    import gpu_util as gu
+    import simgan_b200 as sg
+    from simgan_b200 import dist as sg_dist
+    from torch.utils.data import DataLoader, TensorDataset
+    gu.DEV = dev
+    pol = gu.make_policy(g.policy(), g.O, g.H, g.A)
+    agent = sg.PPO(pol, 0.2, g.ppo_epoch, g.nmb, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    d = gu.make_disc(g.disc(), g.F, g.HD)
+    buf = g.buffer()
+    buf["rewards"].copy_(g.t("relabel_rewards"))
+    buf["returns"].copy_(g.t("gae_returns"))
+    buf["value_preds"][-1] = g.t("next_value")
+    rs = gu.make_storage(buf, g.O, g.A, g.F)
+    expert = g.t("expert").to(dev)
+    loader = DataLoader(TensorDataset(expert), batch_size=g.gail_batch, shuffle=True, drop_last=len(expert) > g.gail_batch)
+    if dp_on:
+        sg_dist.attach(ppo=agent, disc=d)
+    else:
+        agent.kernel_mode = 1
+        d.kernel_mode = 1
+    dl = d.update_gail_dyn(loader, rs, replay=g.disc_replay(0))
+    pl = agent.update(rs, permutations=g.t("ppo_perm"))
+    return (np.array(dl), np.array(pl), d.last_trace.clone(), agent.last_trace.clone(),
+            pol.flat_params().cpu().clone(), d.flat_params().cpu().clone())
+
+
+def _worker(rank, world, port, case, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.cuda.set_device(rank)
+    dev = "cuda:%d" % rank
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        from golden_util import Golden
+        torch.set_num_threads(1)
+        g = Golden(case)
+        res = _run_case(g, True, dev)
+        torch.cuda.synchronize()
+        # every rank ends with identical parameters (same clip+Adam epilogue on the same reduced gradient)
+        for t in (res[4], res[5]):
+            ref = t.to(dev).clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(ref.cpu(), t), "ranks diverged"
+        if rank == 0:
+            dist.barrier()
+            one = _run_case(g, False, dev)
+            for a, b in zip(res[:2], one[:2]):
+                assert np.all(np.abs(a - b) <= 1e-5 * np.maximum(np.abs(b), 0.05)), (a, b)
+            assert torch.allclose(res[2], one[2], rtol=2e-5, atol=1e-6)
+            tr, tr1 = res[3], one[3]
+            scale = tr1.abs().max(dim=0).values.clamp_min(0.5)
+            assert bool(((tr - tr1).abs() <= 2e-5 * scale).all())
+            assert torch.allclose(res[4], one[4], rtol=1e-4, atol=2e-6)
+            assert torch.allclose(res[5], one[5], rtol=1e-4, atol=2e-6)
+            open(out, "w").write("ok")
+        else:
+            dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["hopper_cfg1_seed0.npz", "laika_dims_seed2.npz"])
+def test_data_parallel_matches_single_gpu(case, tmp_path):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    world = 2
+    out = str(tmp_path / "ok")
+    mp.spawn(_worker, args=(world, _free_port(), case, out), nprocs=world, join=True)
+    assert os.path.exists(out)
