@@ -108,8 +108,9 @@ typedef struct sg_ppo_config {
 } sg_ppo_config;
 
 int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg);
-/* Diagnostics: byte offset inside the workspace of 8 int64 per-phase clock64 totals of CTA 0 of the last
- * persistent launch {param image, tile phase, barrier 1, reduce+ssq, barrier 2, clip+Adam, barrier 3, -}. */
+/* Diagnostics: byte offset inside the workspace of the per-CTA, per-phase clock64 totals of the last persistent
+ * launch: int64 [n_ctas][8] with slots {param image, tile phase, barrier 1, reduce+ssq, barrier 2, clip+Adam,
+ * barrier 3, -}; n_ctas = min(#tiles, #SMs). */
 int64_t sg_ppo_phase_cycles_offset(const sg_ppo_config* cfg);
 
 /* PPO.update (A2C/algo/ppo.py:65-157) for cfg->ppo_epoch epochs.

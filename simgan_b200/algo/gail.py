@@ -167,6 +167,10 @@ class Discriminator(nn.Module):
         ws, off = self.__dict__["_prof_view"]
         return ws[off:off + 64].view(torch.int64)[:5].cpu().tolist()
 
+    def phase_cycles_all(self, n_ctas):
+        ws, off = self.__dict__["_prof_view"]
+        return ws[off:off + 64 * n_ctas].view(torch.int64).view(n_ctas, 8).cpu()
+
     def update_gail_dyn(self, expert_loader, rollouts, replay=None):
         """gail.py:154-193.  ``expert_loader`` is the caller's DataLoader over TensorDataset(expert (N_exp,F))
         (main_gail_dyn_ppo.py:165-175); its dataset tensor is used in place on the device and its

@@ -69,6 +69,11 @@ class PPO(object):
         ws, off = self._prof_view
         return ws[off:off + 64].view(torch.int64)[:7].cpu().tolist()
 
+    def phase_cycles_all(self, n_ctas):
+        """(n_ctas, 8) per-CTA phase totals of the last persistent launch."""
+        ws, off = self._prof_view
+        return ws[off:off + 64 * n_ctas].view(torch.int64).view(n_ctas, 8).cpu()
+
     def update(self, rollouts, permutations=None):
         """PPO.update (ppo.py:65-157).  ``permutations`` (ppo_epoch, S) overrides the sampler draw (used by
         parity tests to replay a recorded index stream)."""

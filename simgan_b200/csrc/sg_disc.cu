@@ -23,6 +23,7 @@
 //   dW2 += zb2 h1^T  ;  db2 += zb2    ;  hb1 += W2^T zb2     ;  zb1 = hb1*(1-h1^2)
 //   dW1 += zb1 x^^T  ;  db1 += zb1
 #include "sg_common.cuh"
+#include "sg_disc_reg.cuh"
 
 namespace sg {
 
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscAr
     float* Ws = smem;
     float* tile = RESIDENT ? smem + a.P : smem;
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
-    PhaseClock pc{a.prof, blockIdx.x == 0 && threadIdx.x == 0};
+    PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     for (int step = 0; step < a.nsteps; ++step) {
         if (RESIDENT) {
@@ -330,6 +331,41 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscAr
     }
     disc_poison_on_timeout(a);
 }
+// Register-resident variant (H = 4*HQ known at compile time, H <= 128): W2 lives in registers, the rest of the
+// parameters in a small shared image; both are refreshed from global memory after every Adam step.
+template <int HQ>
+__global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const DiscRegImage I = make_disc_reg_image(a.F, a.H);
+    float* img = smem;
+    float* tile = smem + I.total;
+    DiscRegSmem sm;
+    sm.carve(tile, a.F, a.H);
+    DiscRegW2<HQ> w;
+    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
+    pc.start();
+    for (int step = 0; step < a.nsteps; ++step) {
+        disc_reg_fill<HQ>(w, img, a.params, a.L, I, threadIdx.x);
+        pc.lap(0);
+        bool acc = false;
+        for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+            disc_tile_reg<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc);
+            acc = true;
+        }
+        pc.lap(1);
+        gb.sync();
+        pc.lap(2);
+        float4 mine;
+        const bool have = disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile), mine);
+        disc_adam_slice(a, step, blockIdx.x, have, mine);
+        pc.lap(3);
+        gb.sync();
+        pc.lap(4);
+    }
+    disc_poison_on_timeout(a);
+}
+
 __global__ void __launch_bounds__(kStepThreads, 1) disc_phaseA_kernel(DiscArgs a, int step) {
     extern __shared__ __align__(16) float smem[];
     disc_phaseA<LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
@@ -493,7 +529,17 @@ static size_t disc_tile_smem_floats(const sg_disc_config* c) {
     size_t f = (size_t)DiscSmem::floats(c->feat_dim, c->hidden);
     return f < 4 * kStepThreads ? 4 * kStepThreads : f;      // phase B needs 256 float4 of scratch
 }
+static bool disc_reg_ok(const sg_disc_config* c) {
+    const int h = c->hidden;
+    return h == 48 || h == 64 || h == 100 || h == 128;      // instantiated widths of disc_reg_kernel
+}
+static size_t disc_reg_smem_bytes(const sg_disc_config* c) {
+    size_t tile = (size_t)DiscRegSmem::floats(c->feat_dim, c->hidden);
+    if (tile < 4 * kStepThreads) tile = 4 * kStepThreads;
+    return ((size_t)make_disc_reg_image(c->feat_dim, c->hidden).total + tile) * sizeof(float);
+}
 static size_t disc_resident_smem_bytes(const sg_disc_config* c) {
+    if (disc_reg_ok(c)) return disc_reg_smem_bytes(c);
     DiscLayout L = make_disc_layout(c->feat_dim, c->hidden);
     return ((size_t)L.total + disc_tile_smem_floats(c)) * sizeof(float);
 }
@@ -520,7 +566,7 @@ static DiscWs disc_ws(const sg_disc_config* c, int grid) {
     w.grad = take((size_t)(L.total + 4) * sizeof(float));
     w.losspart = take((size_t)grid * 4 * sizeof(float));
     w.bar = take(2 * sizeof(unsigned int));
-    w.prof = take(8 * sizeof(long long));
+    w.prof = take((size_t)grid * 8 * sizeof(long long));
     w.total = o;
     return w;
 }
@@ -610,7 +656,18 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     if (mode == 0) mode = smem_res <= kDiscMaxDynSmem ? 3 : 2;
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
     if (mode == 3 || mode == 2) {
-        const void* fn = mode == 3 ? (const void*)disc_persistent_kernel<true> : (const void*)disc_persistent_kernel<false>;
+        const void* fn = (const void*)disc_persistent_kernel<false>;
+        if (mode == 3) {
+            fn = (const void*)disc_persistent_kernel<true>;
+            if (disc_reg_ok(cfg)) {
+                switch (cfg->hidden) {
+                    case 48: fn = (const void*)disc_reg_kernel<12>; break;
+                    case 64: fn = (const void*)disc_reg_kernel<16>; break;
+                    case 100: fn = (const void*)disc_reg_kernel<25>; break;
+                    default: fn = (const void*)disc_reg_kernel<32>; break;
+                }
+            }
+        }
         const size_t smem = mode == 3 ? smem_res : smem_tile;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;

@@ -1,0 +1,343 @@
+// Register-resident discriminator tile (hidden width H = 4*HQ <= 128, known at compile time).
+//
+// The 2nd trunk layer W2 (H x H) is walked four times per optimizer step -- forward, dZ1/v1, ub2 and hb1
+// of the gradient-penalty double backward (A2C/algo/gail.py:67-89, 165-188) -- always against a handful of
+// rows, so the cost of those passes is the cost of fetching W2.  Here every thread keeps its slice of W2 in
+// REGISTERS for the whole step, once in row form and once in column form:
+//     thread t:  unit u = t >> 1, half kh = t & 1, quads [kh*Q0, kh*Q0+Q0) of the contraction (Q0 = ceil(HQ/2))
+//       wrow[i] = W2[u][k]   (k in my quads)   -> "F" passes  out[r][u] = sum_k x[r][k] W2[u][k]
+//       wcol[i] = W2[m][u]   (m in my quads)   -> "B" passes  out[r][u] = sum_m y[r][m] W2[m][u]
+// A pass is then RT broadcast LDS.128 of activations per quad against 4*RT FMAs, one xor-shuffle joins the two
+// halves, and no weight traffic at all.  W1 (H x F), w3 and the biases are read from a small natural image
+// in shared memory.  Same math, same slot bookkeeping as disc_tile (sg_disc.cu); summation order differs.
+#pragma once
+#include "sg_common.cuh"
+#include "sg_colgemm.cuh"
+
+namespace sg {
+
+struct DiscRegSmem {
+    float *X, *H1, *H2, *DD, *LOSS, *Y2, *L2t, *L1t, *U1, *Z2, *C3, *PB;
+    int ldf, ldh;
+    __host__ __device__ static int pb_floats(int F) { return 2 * round_up(F, 4) * 8; }     // pass-B partials
+    __host__ __device__ static int floats(int F, int H) {
+        const int ldf = round_up(F, 4), ldh = round_up(H, 4);
+        return 8 * ldf + 8 * ldh + 6 * ldh + 8 + 24 + 6 * ldh + 8 * ldh + 8 * ldh + 2 * ldh + 2 * ldh + 2 * ldh + pb_floats(F);
+    }
+    __device__ void carve(float* sm, int F, int H) {
+        ldf = round_up(F, 4); ldh = round_up(H, 4);
+        X = sm; sm += 8 * ldf;        // rows 0..5 inputs (e0 e1 p0 p1 m0 m1), rows 6,7 gbar
+        H1 = sm; sm += 8 * ldh;       // rows 0..5 h1, rows 6,7 vb1
+        H2 = sm; sm += 6 * ldh;
+        DD = sm; sm += 8;
+        LOSS = sm; sm += 24;
+        Y2 = sm; sm += 6 * ldh;       // rows 0..3 dz2 (e,p), rows 4,5 u2      (operand of pass A)
+        L2t = sm; sm += 8 * ldh;      // [H][8]: slots 0..3 dz2, 4,5 zb2, 6,7 u2
+        L1t = sm; sm += 8 * ldh;      // [H][8]: slots 0..3 dz1, 4,5 zb1, 6,7 u1
+        U1 = sm; sm += 2 * ldh;       // [2][ldh]  operand of pass B
+        Z2 = sm; sm += 2 * ldh;       // [2][ldh]  operand of pass E
+        C3 = sm; sm += 2 * ldh;       // dw3 terms of the penalty
+        PB = sm;
+    }
+};
+
+__device__ __forceinline__ float dsoftplusf(float z) { return fmaxf(z, 0.f) + log1pf(expf(-fabsf(z))); }
+__device__ __forceinline__ float dsigmoidf(float z) { return __fdiv_rn(1.f, 1.f + expf(-z)); }
+
+// flat image of everything except W2: [W1 | b1 | b2 | w3 | b3] with the offsets of DiscLayout minus the W2 block
+struct DiscRegImage {
+    int w1, b1, b2, w3, b3, total;
+};
+__host__ __device__ inline DiscRegImage make_disc_reg_image(int F, int H) {
+    DiscRegImage I;
+    int o = 0;
+    I.w1 = o; o += round_up(H * F, 4);
+    I.b1 = o; o += round_up(H, 4);
+    I.b2 = o; o += round_up(H, 4);
+    I.w3 = o; o += round_up(H, 4);
+    I.b3 = o; o += 4;
+    I.total = o;
+    return I;
+}
+
+template <int HQ>
+struct DiscRegW2 {
+    static constexpr int Q0 = (HQ + 1) / 2;
+    float wrow[Q0 * 4];
+    float wcol[Q0 * 4];
+};
+
+// (re)load this thread's register slices of W2 and the small shared image, straight from global through L2
+template <int HQ>
+__device__ __forceinline__ void disc_reg_fill(DiscRegW2<HQ>& w, float* __restrict__ img, const float* __restrict__ params,
+                                              const DiscLayout& L, const DiscRegImage& I, int tid) {
+    constexpr int H = 4 * HQ, Q0 = DiscRegW2<HQ>::Q0;
+    const int u = tid >> 1, kh = tid & 1;
+    const float* W2 = params + L.w2;
+    const bool live = u < H;
+#pragma unroll
+    for (int i = 0; i < Q0; ++i) {
+        const int q = kh * Q0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && q < HQ) v = ld_cg4(W2 + (size_t)u * H + 4 * q);
+        w.wrow[4 * i] = v.x; w.wrow[4 * i + 1] = v.y; w.wrow[4 * i + 2] = v.z; w.wrow[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < Q0 * 4; ++i) {
+        const int m = kh * Q0 * 4 + i;
+        w.wcol[i] = (live && m < H) ? ld_cg(W2 + (size_t)m * H + u) : 0.f;
+    }
+    // small image: segments before W2 (W1, b1) and after it (b2, w3, b3)
+    const int n1 = L.w2;                       // floats before the W2 block (multiple of 4)
+    const int n2 = L.total - L.b2;             // floats after it
+    for (int p = 4 * tid; p < n1 + n2; p += 4 * kStepThreads) {
+        const int src = p < n1 ? p : L.b2 + (p - n1);
+        *reinterpret_cast<float4*>(img + p) = ld_cg4(params + src);
+    }
+    __syncthreads();
+}
+
+// out[r] = sum over my quads of A[r][k] * wreg[k]; both lanes of a unit get the full sum
+template <int HQ, int NR>
+__device__ __forceinline__ void reg_pass(const float (&wreg)[DiscRegW2<HQ>::Q0 * 4], const float* __restrict__ A, int ld,
+                                         const int (&rows)[NR], int kh, float (&out)[NR]) {
+    constexpr int Q0 = DiscRegW2<HQ>::Q0;
+#pragma unroll
+    for (int j = 0; j < NR; ++j) out[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < Q0; ++i) {
+        int q = kh * Q0 + i;
+        q = q < HQ ? q : HQ - 1;               // phantom quad of the upper half: weights are zero, address stays valid
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(A + rows[j] * ld + 4 * q);
+            out[j] = fmaf(x.x, wreg[4 * i], out[j]); out[j] = fmaf(x.y, wreg[4 * i + 1], out[j]);
+            out[j] = fmaf(x.z, wreg[4 * i + 2], out[j]); out[j] = fmaf(x.w, wreg[4 * i + 3], out[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NR; ++j) out[j] += __shfl_xor_sync(0xffffffffu, out[j], 1);
+}
+
+// One tile = 2 (expert, policy, mixup) row triples.  `img` = small natural image (DiscRegImage), `w` = W2 slices.
+template <int HQ, class Args>
+__device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float* __restrict__ img, const DiscRegImage& I,
+                              int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
+                              DiscRegSmem& sm, bool acc) {
+    constexpr int H = 4 * HQ, TB = 2, R = 8;
+    const int tid = threadIdx.x, nth = kStepThreads;
+    const int F = a.F, ldf = sm.ldf, ldh = sm.ldh;
+    const int u = tid >> 1, kh = tid & 1;
+    const bool live = u < H;
+    const int row0 = a.row_begin + tile * TB;
+    const int32_t* eidx = a.eidx + (size_t)step * a.B;
+    const int32_t* pidx = a.pidx + (size_t)step * a.B;
+    const float* alpha = a.alpha + (size_t)step * a.B;
+    const float invB = 1.f / (float)a.B;
+    const float* W1 = img + I.w1; const float* B1 = img + I.b1; const float* B2 = img + I.b2;
+    const float* W3 = img + I.w3; const float* B3 = img + I.b3;
+
+    // ---- S0: rows [e0 e1 | p0 p1 | m0 m1 | 0 0], mixup = alpha*e + (1-alpha)*p (gail.py:72-75) -----------------
+    for (int e = tid; e < R * ldf; e += nth) {
+        const int r = e / ldf, k = e - r * ldf;
+        const int kind = r / TB, j = r - kind * TB;
+        const int row = row0 + j;
+        float x = 0.f;
+        if (kind < 3 && row < a.row_end && k < F) {
+            const float xe = a.expert[(size_t)eidx[row] * F + k];
+            const float xp = a.policy[(size_t)pidx[row] * F + k];
+            const float al = alpha[row];
+            x = kind == 0 ? xe : (kind == 1 ? xp : __fadd_rn(__fmul_rn(al, xe), __fmul_rn(__fsub_rn(1.f, al), xp)));
+        }
+        sm.X[e] = x;
+    }
+    __syncthreads();
+    // rows owned by this lane in 6-row stages: kh, kh+2, kh+4  (e_kh, p_kh, m_kh)
+    const int myrows[3] = {kh, kh + 2, kh + 4};
+    // ---- S1: layer 1 forward, W1 natural in shared memory -------------------------------------------------------
+    if (live) {
+        float s[3] = {0.f, 0.f, 0.f};
+        const float* wr = W1 + (size_t)u * F;
+        for (int k0 = 0; k0 < F; k0 += 4) {
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = (k0 + j < F) ? wr[k0 + j] : 0.f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float4 x = *reinterpret_cast<const float4*>(sm.X + myrows[i] * ldf + k0);
+                s[i] = fmaf(x.x, wv[0], s[i]); s[i] = fmaf(x.y, wv[1], s[i]); s[i] = fmaf(x.z, wv[2], s[i]); s[i] = fmaf(x.w, wv[3], s[i]);
+            }
+        }
+        const float b = B1[u];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) sm.H1[myrows[i] * ldh + u] = tanhf(s[i] + b);
+    }
+    __syncthreads();
+    // ---- S2: layer 2 forward ("F" pass on 6 rows) -----------------------------------------------------------------
+    {
+        const int rows6[6] = {0, 1, 2, 3, 4, 5};
+        float o[6];
+        reg_pass<HQ, 6>(w.wrow, sm.H1, ldh, rows6, kh, o);
+        if (live) {
+            const float b = B2[u];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sm.H2[myrows[i] * ldh + u] = tanhf((kh ? o[2 * i + 1] : o[2 * i]) + b);
+        }
+    }
+    __syncthreads();
+    // ---- S3: logits + BCE-with-logits seeds (gail.py:171-176): warp r handles row r ------------------------------------
+    {
+        const int wid = tid >> 5, lane = tid & 31;
+        if (wid < 6) {
+            float d = 0.f;
+            for (int n = lane; n < H; n += 32) d = fmaf(W3[n], sm.H2[wid * ldh + n], d);
+            d = warp_sum(d) + B3[0];
+            if (lane == 0) {
+                const int kind = wid / TB, j = wid - kind * TB;
+                const bool ok = (row0 + j) < a.row_end;
+                float dd = 0.f, le = 0.f, lp = 0.f;
+                if (ok && kind == 0) { dd = (dsigmoidf(d) - 1.f) * invB; le = dsoftplusf(-d); }
+                if (ok && kind == 1) { dd = dsigmoidf(d) * invB; lp = dsoftplusf(d); }
+                sm.DD[wid] = dd; sm.LOSS[wid] = le; sm.LOSS[8 + wid] = lp;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- S4: dz2 (e,p) and u2 (mixup) ---------------------------------------------------------------------------------
+    if (live) {
+        const float w3 = W3[u];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int r = myrows[i];
+            const float h2 = sm.H2[r * ldh + u];
+            const float base = w3 * (1.f - h2 * h2);
+            if (i < 2) {
+                const float y = sm.DD[r] * base;
+                sm.Y2[r * ldh + u] = y; sm.L2t[u * R + r] = y;
+            } else {
+                sm.Y2[r * ldh + u] = base; sm.L2t[u * R + 6 + kh] = base;       // u2 pairs with vb1 in slot 6+j
+            }
+        }
+    }
+    __syncthreads();
+    // ---- S5: pass A ("B" pass on 6 rows): dz1 for e,p rows; v1, u1 for the mixup rows ------------------------------------
+    float v1 = 0.f, h1m = 0.f;
+    {
+        const int rows6[6] = {0, 1, 2, 3, 4, 5};
+        float o[6];
+        reg_pass<HQ, 6>(w.wcol, sm.Y2, ldh, rows6, kh, o);
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = myrows[i];
+                const float h1 = sm.H1[r * ldh + u];
+                sm.L1t[u * R + r] = (kh ? o[2 * i + 1] : o[2 * i]) * (1.f - h1 * h1);
+            }
+            v1 = kh ? o[5] : o[4];
+            h1m = sm.H1[(4 + kh) * ldh + u];
+            const float u1 = v1 * (1.f - h1m * h1m);
+            sm.U1[kh * ldh + u] = u1;
+            sm.L1t[u * R + 6 + kh] = u1;                                           // u1 pairs with gbar in slot 6+j
+        }
+    }
+    __syncthreads();
+    // ---- S6: pass B: g[j][f] = sum_n u1[j][n] W1[n][f]  (input gradient of the mixup rows) ---------------------------------
+    {
+        const int nout = 2 * ldf;                          // (j, f) outputs, f padded to ldf
+        int nch = nth / nout; nch = nch < 1 ? 1 : (nch > 8 ? 8 : nch);
+        const int clen = (H + nch - 1) / nch;
+        for (int e = tid; e < nout * nch; e += nth) {
+            const int c = e / nout, o = e - c * nout;
+            const int j = o / ldf, f = o - j * ldf;
+            float s = 0.f;
+            if (f < F) {
+                const int n1 = min(H, (c + 1) * clen);
+                for (int n = c * clen; n < n1; ++n) s = fmaf(sm.U1[j * ldh + n], W1[(size_t)n * F + f], s);
+            }
+            sm.PB[c * nout + o] = s;
+        }
+        __syncthreads();
+        if (tid < 32 * TB) {
+            const int j = tid >> 5, lane = tid & 31;
+            float ssq = 0.f;
+            for (int f = lane; f < ldf; f += 32) {
+                float g = 0.f;
+                for (int c = 0; c < nch; ++c) g += sm.PB[c * nout + j * ldf + f];
+                sm.X[(6 + j) * ldf + f] = g;               // raw g for now (zero in the padding lanes)
+                ssq += g * g;
+            }
+            ssq = warp_sum(ssq);
+            const float nrm = sqrtf(ssq);
+            const bool ok = (row0 + j) < a.row_end;
+            // penalty lambda*mean((|g|-1)^2) -> gbar = (2 lambda / B)(n-1) g / n
+            const float coef = (ok && nrm > 0.f) ? (2.f * a.gp_lambda * invB) * (nrm - 1.f) / nrm : 0.f;
+            for (int f = lane; f < ldf; f += 32) sm.X[(6 + j) * ldf + f] *= coef;
+            if (lane == 0) sm.LOSS[16 + j] = ok ? (nrm - 1.f) * (nrm - 1.f) : 0.f;
+        }
+    }
+    __syncthreads();
+    // ---- S7: pass C: ub1 = gbar . W1^T -> vb1, hb1 (lane kh owns mixup row j = kh) --------------------------------------------
+    float hb1 = 0.f;
+    if (live) {
+        float s = 0.f;
+        const float* wr = W1 + (size_t)u * F;
+        const float* gb = sm.X + (6 + kh) * ldf;
+        for (int k0 = 0; k0 < F; k0 += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(gb + k0);
+            s = fmaf(x.x, wr[k0], s);
+            if (k0 + 1 < F) s = fmaf(x.y, wr[k0 + 1], s);
+            if (k0 + 2 < F) s = fmaf(x.z, wr[k0 + 2], s);
+            if (k0 + 3 < F) s = fmaf(x.w, wr[k0 + 3], s);
+        }
+        sm.H1[(6 + kh) * ldh + u] = s * (1.f - h1m * h1m);                          // vb1
+        hb1 = -2.f * s * v1 * h1m;
+    }
+    __syncthreads();
+    // ---- S8: pass D ("F" pass on the 2 vb1 rows): ub2 -> dw3 term, zb2 --------------------------------------------------------
+    {
+        const int rows2[2] = {6, 7};
+        float o[2];
+        reg_pass<HQ, 2>(w.wrow, sm.H1, ldh, rows2, kh, o);
+        if (live) {
+            const float ub2 = kh ? o[1] : o[0];
+            const float h2 = sm.H2[(4 + kh) * ldh + u];
+            const float om = 1.f - h2 * h2;
+            sm.C3[kh * ldh + u] = ub2 * om;
+            const float zb2 = -2.f * ub2 * W3[u] * h2 * om;
+            sm.Z2[kh * ldh + u] = zb2;
+            sm.L2t[u * R + 4 + kh] = zb2;
+        }
+    }
+    __syncthreads();
+    // ---- S9: pass E ("B" pass on the 2 zb2 rows): hb1 += zb2 . W2 ; zb1 = hb1*(1-h1^2) -------------------------------------------
+    {
+        const int rows2[2] = {0, 1};
+        float o[2];
+        reg_pass<HQ, 2>(w.wcol, sm.Z2, ldh, rows2, kh, o);
+        if (live) sm.L1t[u * R + 4 + kh] = (hb1 + (kh ? o[1] : o[0])) * (1.f - h1m * h1m);
+    }
+    __syncthreads();
+    // ---- S10: parameter gradients of this tile ---------------------------------------------------------------------------------------
+    outer_cols<R>(gout + a.L.w2, sm.L2t, sm.H1, ldh, H, H, tid, nth, acc);
+    rowsum_store<R>(gout + a.L.b2, sm.L2t, H, tid, nth, acc, 3 * TB);
+    if ((F & 3) == 0) outer_cols<R>(gout + a.L.w1, sm.L1t, sm.X, ldf, H, F, tid, nth, acc);
+    else outer_store<R, 1>(gout + a.L.w1, sm.L1t, sm.X, ldf, H, F, tid, nth, acc);
+    rowsum_store<R>(gout + a.L.b1, sm.L1t, H, tid, nth, acc, 3 * TB);
+    for (int n = tid; n < H; n += nth) {
+        float s = 0.f;
+        for (int r = 0; r < 2 * TB; ++r) s += sm.DD[r] * sm.H2[r * ldh + n];
+        for (int j = 0; j < TB; ++j) s += sm.C3[j * ldh + n];
+        __stcg(gout + a.L.w3 + n, acc ? s + __ldcg(gout + a.L.w3 + n) : s);
+    }
+    if (tid == nth - 1) {
+        float db3 = 0.f, le = 0.f, lp = 0.f, gp = 0.f;
+        for (int r = 0; r < 2 * TB; ++r) db3 += sm.DD[r];
+        for (int r = 0; r < TB; ++r) { le += sm.LOSS[r]; lp += sm.LOSS[8 + TB + r]; gp += sm.LOSS[16 + r]; }
+        if (acc) { db3 += __ldcg(gout + a.L.b3); le += lossout[0]; lp += lossout[1]; gp += lossout[2]; }
+        __stcg(gout + a.L.b3, db3);
+        lossout[0] = le; lossout[1] = lp; lossout[2] = gp;
+    }
+    __syncthreads();
+}
+
+}  // namespace sg

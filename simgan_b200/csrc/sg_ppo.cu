@@ -19,6 +19,7 @@
 // All three run the same arithmetic in the same order and are bit-identical.
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
+#include "sg_colgemm.cuh"
 
 namespace sg {
 
@@ -29,6 +30,7 @@ struct PpoArgs {
     float clip, ratio_lo, ratio_hi, c_v, c_e, max_norm;
     float one_minus_b1, b2, one_minus_b2, eps;
     PolicyLayout L;
+    PolicyLayout LI;      // layout of the shared-memory image (column-owner resident kernel): W2 blocks in NQ form
     float *params, *m, *v;
     const float *obs, *actions, *vpred, *ret, *oldlp, *advstats;
     const int32_t* perm;
@@ -224,6 +226,310 @@ __device__ __forceinline__ void ppo_phaseA(const PpoArgs& a, const float* W, int
     }
 }
 
+// =====================================================================================================
+// Column-owner tile (resident kernel, H % 4 == 0): same math as ppo_tile, organised so that a thread owns one
+// hidden unit for RT = R/RG of the tile's rows through every layer (sg_colgemm.cuh).  Threads 0..127 run the
+// actor, 128..255 the critic; inside a net, column lane cn = t % NC and row group rg = t / NC (NC*RG = 128).
+// =====================================================================================================
+__host__ __device__ inline PolicyLayout make_policy_image_layout(int O, int H, int A) {
+    PolicyLayout L;
+    int o = 0;
+    L.aw1 = o; o += round_up(H * O, 4);
+    L.ab1 = o; o += round_up(H, 4);
+    L.aw2 = o; o += nq_image_floats(H, H);
+    L.ab2 = o; o += round_up(H, 4);
+    L.cw1 = o; o += round_up(H * O, 4);
+    L.cb1 = o; o += round_up(H, 4);
+    L.cw2 = o; o += nq_image_floats(H, H);
+    L.cb2 = o; o += round_up(H, 4);
+    L.vw = o; o += round_up(H, 4);
+    L.vb = o; o += 4;
+    L.mw = o; o += round_up(A * H, 4);
+    L.mb = o; o += round_up(A, 4);
+    L.ls = o; o += round_up(A, 4);
+    L.total = o;
+    return L;
+}
+
+// global natural parameter vector -> shared-memory image (natural segments copied, W2 blocks scattered to NQ)
+__device__ __forceinline__ void load_policy_image(float* __restrict__ Wi, const float* __restrict__ params, const PolicyLayout& L,
+                                                  const PolicyLayout& LI, int H, int tid) {
+    const int HH = H * H;
+    const int d1 = LI.ab2 - L.ab2, d2 = LI.cb2 - L.cb2;
+    constexpr int U = 8;
+    for (int p = 4 * tid; p < L.total; p += 4 * kStepThreads * U) {
+        float4 q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = p + 4 * kStepThreads * u;
+            q[u] = i < L.total ? ld_cg4(params + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = p + 4 * kStepThreads * u;
+            if (i >= L.total) break;
+            int rel = -1, base = 0;
+            if (i >= L.aw2 && i < L.aw2 + HH) { rel = i - L.aw2; base = LI.aw2; }
+            else if (i >= L.cw2 && i < L.cw2 + HH) { rel = i - L.cw2; base = LI.cw2; }
+            if (rel >= 0) {
+                const int n = rel / H, k = rel - n * H;
+                float* d = Wi + base + nq_index(n, k, H);
+                d[0] = q[u].x; d[4] = q[u].y; d[8] = q[u].z; d[12] = q[u].w;
+            } else {
+                const int dst = i < L.aw2 ? i : (i < L.cw2 ? i + d1 : i + d2);
+                *reinterpret_cast<float4*>(Wi + dst) = q[u];
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int R>
+struct PpoSmemCol {
+    float *X, *ACT, *H1, *H2, *MU, *VAL, *ROW, *DMUt, *DVt, *DLSt, *DZ2, *DZ2t, *DZ1t;
+    int ldo, lda, ldh;
+    __host__ __device__ static int floats(int O, int H, int A) {
+        const int ldo = round_up(O, 4), lda = round_up(A, 4), ldh = round_up(H, 4);
+        return R * ldo + R * lda + 4 * R * ldh + R * lda + R + 8 * R + lda * R + R + lda * R + 6 * R * ldh;
+    }
+    __device__ void carve(float* sm, int O, int H, int A) {
+        ldo = round_up(O, 4); lda = round_up(A, 4); ldh = round_up(H, 4);
+        X = sm; sm += R * ldo;
+        ACT = sm; sm += R * lda;
+        H1 = sm; sm += 2 * R * ldh;
+        H2 = sm; sm += 2 * R * ldh;
+        MU = sm; sm += R * lda;
+        VAL = sm; sm += R;
+        ROW = sm; sm += 8 * R;
+        DMUt = sm; sm += lda * R;
+        DVt = sm; sm += R;
+        DLSt = sm; sm += lda * R;
+        DZ2 = sm; sm += 2 * R * ldh;      // [net][row][ldh]  (operand of the layer-2 back-propagation)
+        DZ2t = sm; sm += 2 * R * ldh;     // [net][unit][R]   (operand of the weight / bias gradients)
+        DZ1t = sm; sm += 2 * R * ldh;
+    }
+};
+
+template <int R, int RG>
+__device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int step, int tile, float* __restrict__ gout,
+                             float* __restrict__ lossout, PpoSmemCol<R>& sm, bool acc) {
+    constexpr int RT = R / RG;            // rows per thread
+    constexpr int NC = kHalf / RG;        // column lanes per net
+    constexpr int LPR = 32 / R;           // lanes per row in the loss warp
+    static_assert(R == 8 || R == 16, "loss warp maps R rows x 32/R lanes");
+    static_assert(RT % 4 == 0, "row groups are float4 multiples");
+    const int tid = threadIdx.x;
+    const int O = a.O, H = a.H, A = a.A;
+    const PolicyLayout& LI = a.LI;
+    const int ldo = sm.ldo, lda = sm.lda, ldh = sm.ldh;
+    const int epoch = step / a.nmb, mb = step - epoch * a.nmb;
+    const int32_t* idx = a.perm + (size_t)epoch * a.S + (size_t)mb * a.mbs;
+    const int row0 = a.row_begin + tile * R;
+    float* rRet = sm.ROW;            float* rVp = sm.ROW + R;     float* rOlp = sm.ROW + 2 * R;
+    float* rAdv = sm.ROW + 3 * R;    float* rValid = sm.ROW + 4 * R;
+
+    // ---- gather this tile's rows (flat sample id = t*N+n, A2C/storage.py:169-181) ----------------------
+    for (int e = tid; e < R * ldo; e += kStepThreads) {
+        const int r = e / ldo, k = e - r * ldo;
+        const int row = row0 + r;
+        sm.X[e] = (row < a.row_end && k < O) ? a.obs[(size_t)idx[row] * O + k] : 0.f;
+    }
+    for (int e = tid; e < R * lda; e += kStepThreads) {
+        const int r = e / lda, k = e - r * lda;
+        const int row = row0 + r;
+        sm.ACT[e] = (row < a.row_end && k < A) ? a.actions[(size_t)idx[row] * A + k] : 0.f;
+    }
+    if (tid >= kStepThreads - R) {
+        const int r = tid - (kStepThreads - R);
+        const int row = row0 + r;
+        const bool ok = row < a.row_end;
+        const int i = ok ? idx[row] : 0;
+        const float ret = ok ? a.ret[i] : 0.f, vp = ok ? a.vpred[i] : 0.f;
+        rRet[r] = ret; rVp[r] = vp; rOlp[r] = ok ? a.oldlp[i] : 0.f;
+        const float mean = a.advstats[0], sd = a.advstats[1];
+        rAdv[r] = ok ? __fdiv_rn(__fsub_rn(__fsub_rn(ret, vp), mean), __fadd_rn(sd, 1e-5f)) : 0.f;   // ppo.py:66-68
+        rValid[r] = ok ? 1.f : 0.f;
+    }
+    __syncthreads();
+
+    const int half = tid >> 7, t = tid & (kHalf - 1);
+    const int cn = t % NC, r0 = (t / NC) * RT;
+    const float* W1 = Wi + (half ? LI.cw1 : LI.aw1);
+    const float* B1 = Wi + (half ? LI.cb1 : LI.ab1);
+    const float* W2q = Wi + (half ? LI.cw2 : LI.aw2);
+    const float* B2 = Wi + (half ? LI.cb2 : LI.ab2);
+    float* h1 = sm.H1 + half * R * ldh;
+    float* h2 = sm.H2 + half * R * ldh;
+
+    // ---- forward layer 1 and 2 (A2C/model.py:255-264) --------------------------------------------------
+    for (int n = cn; n < H; n += NC) {
+        float acc1[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) acc1[i] = 0.f;
+        col_dot_nat<RT>(W1 + (size_t)n * O, O, sm.X, ldo, r0, acc1);
+        const float b = B1[n];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) h1[(r0 + i) * ldh + n] = tanhf(acc1[i] + b);
+    }
+    __syncthreads();
+    for (int n = cn; n < H; n += NC) {
+        float acc2[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) acc2[i] = 0.f;
+        col_dot_nq_fwd<RT>(W2q, H, n, h1, ldh, r0, acc2);
+        const float b = B2[n];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) h2[(r0 + i) * ldh + n] = tanhf(acc2[i] + b);
+    }
+    __syncthreads();
+    // ---- heads: Gaussian mean (A2C/distributions.py:109-110) and critic_linear -------------------------
+    {
+        const float* WH = Wi + (half ? LI.vw : LI.mw);
+        const float* BH = Wi + (half ? LI.vb : LI.mb);
+        const int NH = half ? 1 : A;
+        float* out = half ? sm.VAL : sm.MU;
+        const int ldout = half ? 1 : lda;
+        auto epih = [&](int r, int n, float s) { out[r * ldout + n] = s + BH[n]; };
+        gemm_xwT<R, 4, LdShared>(WH, h2, ldh, NH, H, t, kHalf, epih);
+    }
+    __syncthreads();
+
+    // ---- per-row losses and gradient seeds: one warp, LPR lanes per row -----------------------------------
+    const float* ls = Wi + LI.ls;
+    if (tid < 32) {
+        const int r = tid / LPR, sub = tid % LPR;
+        const bool ok = rValid[r] != 0.f;
+        const float invB = 1.f / (float)a.mbs;
+        float lp = 0.f;
+        for (int k = sub; k < A; k += LPR) {
+            const float sigma = expf(ls[k]);
+            const float var = sigma * sigma;
+            const float d = sm.ACT[r * lda + k] - sm.MU[r * lda + k];
+            lp += -(d * d) / (2.f * var) - logf(sigma) - SG_LOG_SQRT_2PI;
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+        float vl = 0.f, al = 0.f, dv = 0.f, coef = 0.f;
+        if (ok) {
+            const float ratio = expf(lp - rOlp[r]);
+            const float adv = rAdv[r];
+            const float s1 = ratio * adv;
+            const float s2 = fminf(fmaxf(ratio, a.ratio_lo), a.ratio_hi) * adv;
+            al = -fminf(s1, s2);
+            const float inr = (ratio >= a.ratio_lo && ratio <= a.ratio_hi) ? 1.f : 0.f;
+            const float gsel = s1 < s2 ? 1.f : (s2 < s1 ? inr : 0.5f + 0.5f * inr);     // torch.min / clamp backward
+            coef = -invB * gsel * adv * ratio;
+            const float v = sm.VAL[r], vp = rVp[r], ret = rRet[r];
+            if (a.clipped_vloss) {
+                const float diff = v - vp;
+                const float vc = vp + fminf(fmaxf(diff, -a.clip), a.clip);
+                const float e1 = v - ret, e2 = vc - ret;
+                const float l1 = e1 * e1, l2 = e2 * e2;
+                vl = 0.5f * fmaxf(l1, l2);
+                const float in2 = (diff >= -a.clip && diff <= a.clip) ? 1.f : 0.f;
+                const float g = l1 > l2 ? e1 : (l2 > l1 ? in2 * e2 : 0.5f * (e1 + in2 * e2));
+                dv = a.c_v * invB * g;
+            } else {
+                const float e1 = ret - v;
+                vl = 0.5f * e1 * e1;
+                dv = a.c_v * invB * (v - ret);
+            }
+        }
+        for (int k = sub; k < A; k += LPR) {
+            const float sigma = expf(ls[k]);
+            const float var = sigma * sigma;
+            const float d = sm.ACT[r * lda + k] - sm.MU[r * lda + k];
+            sm.DMUt[k * R + r] = ok ? coef * d / var : 0.f;
+            sm.DLSt[k * R + r] = ok ? coef * (d * d / var - 1.f) : 0.f;
+        }
+        if (sub == 0) sm.DVt[r] = dv;
+        float svl = sub == 0 ? vl : 0.f, sal = sub == 0 ? al : 0.f;
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) {
+            svl += __shfl_xor_sync(0xffffffffu, svl, o);
+            sal += __shfl_xor_sync(0xffffffffu, sal, o);
+        }
+        if (tid == 0) {
+            if (acc) { svl += lossout[0]; sal += lossout[1]; }
+            lossout[0] = svl; lossout[1] = sal;
+        }
+    }
+    __syncthreads();
+
+    // ---- backward through the heads: dZ2 = (dHead . Whead) * (1 - h2^2) -------------------------------------
+    float* dz2 = sm.DZ2 + half * R * ldh;
+    float* dz2t = sm.DZ2t + half * R * ldh;
+    float* dz1t = sm.DZ1t + half * R * ldh;
+    const float* Wh = Wi + (half ? LI.vw : LI.mw);
+    for (int k = cn; k < H; k += NC) {
+        float s[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) s[i] = 0.f;
+        if (half) {
+            const float w = Wh[k];
+#pragma unroll
+            for (int i = 0; i < RT; ++i) s[i] = sm.DVt[r0 + i] * w;
+        } else {
+            for (int aa = 0; aa < A; ++aa) {
+                const float w = Wh[aa * H + k];
+#pragma unroll
+                for (int i = 0; i < RT; ++i) s[i] = fmaf(sm.DMUt[aa * R + r0 + i], w, s[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const float h = h2[(r0 + i) * ldh + k];
+            s[i] *= (1.f - h * h);
+            dz2[(r0 + i) * ldh + k] = s[i];
+            dz2t[k * R + r0 + i] = s[i];
+        }
+    }
+    __syncthreads();
+    // ---- layer-2 back-propagation dZ1 = (dZ2 . W2) * (1 - h1^2), then every gradient that needs dZ2 ---------
+    for (int k = cn; k < H; k += NC) {
+        float s[RT];
+#pragma unroll
+        for (int i = 0; i < RT; ++i) s[i] = 0.f;
+        col_dot_nq_bwd<RT>(W2q, H, H, k, dz2, ldh, r0, s);
+#pragma unroll
+        for (int i = 0; i < RT; ++i) {
+            const float h = h1[(r0 + i) * ldh + k];
+            dz1t[k * R + r0 + i] = s[i] * (1.f - h * h);
+        }
+    }
+    {
+        const float* Dh = half ? sm.DVt : sm.DMUt;
+        const int NH = half ? 1 : A;
+        outer_cols<R>(gout + (half ? a.L.vw : a.L.mw), Dh, h2, ldh, NH, H, t, kHalf, acc);
+        rowsum_store<R>(gout + (half ? a.L.vb : a.L.mb), Dh, NH, t, kHalf, acc);
+        if (!half) rowsum_store<R>(gout + a.L.ls, sm.DLSt, A, t, kHalf, acc);
+        outer_cols<R>(gout + (half ? a.L.cw2 : a.L.aw2), dz2t, h1, ldh, H, H, t, kHalf, acc);
+        rowsum_store<R>(gout + (half ? a.L.cb2 : a.L.ab2), dz2t, H, t, kHalf, acc);
+    }
+    __syncthreads();
+    {
+        float* gW1 = gout + (half ? a.L.cw1 : a.L.aw1);
+        if ((O & 3) == 0) outer_cols<R>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
+        else outer_store<R, 1>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
+        rowsum_store<R>(gout + (half ? a.L.cb1 : a.L.ab1), dz1t, H, t, kHalf, acc);
+    }
+    __syncthreads();   // smem is reused by the next tile
+}
+
+template <int R>
+__device__ __forceinline__ void ppo_phaseA_col(const PpoArgs& a, const float* Wi, int step, int cta, int ncta, float* smem) {
+    PpoSmemCol<R> sm;
+    sm.carve(smem, a.O, a.H, a.A);
+    bool acc = false;
+    for (int tile = cta; tile < a.ntiles; tile += ncta) {
+        float* g = a.gpart + (size_t)cta * a.P;
+        float* l = a.losspart + cta * 4;
+        if (a.H > 64) ppo_tile_col<R, 1>(a, Wi, step, tile, g, l, sm, acc);
+        else ppo_tile_col<R, 2>(a, Wi, step, tile, g, l, sm, acc);
+        acc = true;
+    }
+}
+
 // effective gradient = d loss/d theta of (c_v*L_V + L_pi - c_e*H): the entropy term only touches logstd
 __device__ __forceinline__ float eff_grad(const PpoArgs& a, int p, float g) {
     return (p >= a.L.ls && p < a.L.ls + a.A) ? g - a.c_e : g;
@@ -327,19 +633,28 @@ __device__ __forceinline__ void poison_trace_on_timeout(const PpoArgs& a) {
 
 // RESIDENT: every CTA refreshes a private shared-memory image of the parameters after each Adam step and
 // the tile phase reads its weights from there; otherwise weights are read from global memory through L2.
-template <int R, bool RESIDENT>
+// RESIDENT 2 = column-owner tile with the NQ weight image (H % 4 == 0), 1 = generic tile on a natural image.
+template <int R, int RESIDENT>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[kStepThreads / 32];
     float* Ws = smem;
-    float* tile = RESIDENT ? smem + a.P : smem;
+    float* tile = RESIDENT == 2 ? smem + a.LI.total : (RESIDENT == 1 ? smem + a.P : smem);
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
-    PhaseClock pc{a.prof, blockIdx.x == 0 && threadIdx.x == 0};
+    PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     for (int step = 0; step < a.nsteps; ++step) {
         float4 mine;
         bool have;
-        if (RESIDENT) {
+        if (RESIDENT == 2) {
+            load_policy_image(Ws, a.params, a.L, a.LI, a.H, threadIdx.x);
+            pc.lap(0);
+            ppo_phaseA_col<R>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+            pc.lap(1);
+            gb.sync();
+            pc.lap(2);
+            have = ppo_reduce_slice<LdShared>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.LI.ls, mine);
+        } else if (RESIDENT == 1) {
             load_param_image(Ws, a.params, a.P, threadIdx.x);
             pc.lap(0);
             ppo_phaseA<R, LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
@@ -401,7 +716,14 @@ static size_t ppo_tile_smem_floats(const sg_ppo_config* c) {
     size_t f = (size_t)PpoSmem<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
     return f < 4 * kStepThreads ? 4 * kStepThreads : f;      // phase B needs 256 float4 of scratch
 }
+static bool ppo_col_ok(const sg_ppo_config* c) { return (c->hidden & 3) == 0; }
 static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
+    if (ppo_col_ok(c)) {
+        PolicyLayout LI = make_policy_image_layout(c->obs_dim, c->hidden, c->act_dim);
+        size_t tile = (size_t)PpoSmemCol<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
+        if (tile < 4 * kStepThreads) tile = 4 * kStepThreads;
+        return ((size_t)LI.total + tile) * sizeof(float);
+    }
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
     return ((size_t)L.total + ppo_tile_smem_floats(c)) * sizeof(float);
 }
@@ -438,7 +760,7 @@ static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     w.scal = take(4 * sizeof(float));
     w.ssq = take((size_t)grid * sizeof(double));
     w.bar = take(2 * sizeof(unsigned int));
-    w.prof = take(8 * sizeof(long long));
+    w.prof = take((size_t)grid * 8 * sizeof(long long));
     w.total = o;
     return w;
 }
@@ -480,6 +802,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     a.S = cfg->T * cfg->N;
     a.L = make_policy_layout(a.O, a.H, a.A);
     a.P = a.L.total;
+    a.LI = make_policy_image_layout(a.O, a.H, a.A);
     a.nmb = cfg->num_mini_batch; a.mbs = cfg->mini_batch_size;
     a.nsteps = cfg->ppo_epoch * cfg->num_mini_batch;
     a.row_begin = cfg->row_begin; a.row_end = cfg->row_end;
@@ -509,7 +832,8 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
 
     if (mode == 3 || mode == 2) {
-        const void* fn = mode == 3 ? (const void*)ppo_persistent_kernel<kRows, true> : (const void*)ppo_persistent_kernel<kRows, false>;
+        const void* fn = mode == 3 ? (ppo_col_ok(cfg) ? (const void*)ppo_persistent_kernel<kRows, 2> : (const void*)ppo_persistent_kernel<kRows, 1>)
+                                   : (const void*)ppo_persistent_kernel<kRows, 0>;
         const size_t smem = mode == 3 ? smem_res : smem_tile;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
