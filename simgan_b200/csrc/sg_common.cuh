@@ -355,16 +355,18 @@ struct PhaseClock {
 
 // Deterministic CTA-wide sum of one double per thread (256 threads): xor-butterfly inside each warp,
 // then the 8 warp sums added in warp order by every thread.  `red` = 8 doubles of shared memory.
-__device__ __forceinline__ double block_sum_256(double v, double* red) {
+template <int NT = 256>
+__device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);
     __syncthreads();                       // protects `red` against the previous use
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
     double tot = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < NT / 32; ++w) tot += red[w];
     return tot;
 }
+__device__ __forceinline__ double block_sum_256(double v, double* red) { return block_sum<256>(v, red); }
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
@@ -373,6 +375,8 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float
 // `scr4` = 256 float4 of shared memory.  Ends with a CTA barrier (the slice of `out` is visible to the
 // whole CTA through L2 afterwards).  Narrow slices (<= 128 float4): thread tid < n4 finalises float4 tid of
 // the slice and gets it back in `mine` (returns true), so callers can fuse work on the reduced values.
+// KEEP: `scr4` has NT + 128 float4 and the reduced narrow slice is also left in scr4[NT .. NT+n4).
+template <int NT = 256, bool KEEP = false>
 __device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ part, size_t stride, int nslots, int p0,
                                                       int p1, float* __restrict__ out, float4* scr4, int tid,
                                                       float4& mine) {
@@ -380,13 +384,20 @@ __device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ 
     mine = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n4 <= 0) { __syncthreads(); return true; }
     if (n4 <= 128) {
-        const int NQ = 256 / n4;
+        const int NQ = NT / n4;
         const int j = tid % n4, q = tid / n4;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < NQ) {
             const float* src = part + p0 + 4 * j;
             int c = q;
-            for (; c + 7 * NQ < nslots; c += 8 * NQ) {      // eight independent L2 loads in flight
+            for (; c + 15 * NQ < nslots; c += 16 * NQ) {    // sixteen independent L2 loads in flight
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = ld_cg4(src + (size_t)(c + u * NQ) * stride);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) s = f4_add(s, v[u]);
+            }
+            for (; c + 7 * NQ < nslots; c += 8 * NQ) {
                 float4 v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) v[u] = ld_cg4(src + (size_t)(c + u * NQ) * stride);
@@ -408,13 +419,14 @@ __device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ 
             float4 t = scr4[tid];
             for (int qq = 1; qq < NQ; ++qq) t = f4_add(t, scr4[qq * n4 + tid]);
             __stcg(reinterpret_cast<float4*>(out + p0 + 4 * tid), t);
+            if (KEEP) scr4[NT + tid] = t;
             mine = t;
         }
         __syncthreads();
         return true;
     } else {
         // wide slices (large networks): every thread owns whole columns
-        for (int j = tid; j < n4; j += 256) {
+        for (int j = tid; j < n4; j += NT) {
             const float* src = part + p0 + 4 * j;
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
             int c = 0;

@@ -235,17 +235,32 @@ __device__ void disc_tile(const DiscArgs& a, const float* __restrict__ W, int st
 
 // ---- phase B: slice `cta` of the flat gradient (+ loss sums by CTA 0) --------------------------------
 // Returns true when thread tid < n4 holds float4 tid of the reduced slice in `mine` (narrow slices).
+template <int NT = kStepThreads, bool KEEP = false>
 __device__ bool disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4, float4& mine) {
     const int tid = threadIdx.x;
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
-    const bool narrow = reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
-    if (cta == 0 && tid < 32) {
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c = tid; c < a.nslots; c += 32) {
-            s0 += ld_cg(a.losspart + c * 4); s1 += ld_cg(a.losspart + c * 4 + 1); s2 += ld_cg(a.losspart + c * 4 + 2);
+    // CTA 0 also sums the loss partials: its LAST warp issues those loads first so that they ride along with the
+    // slice loads instead of adding a serial L2 round trip to the CTA every other CTA waits for.
+    constexpr int LW = NT / 32 - 1, MAXC = 5;              // up to 160 slots (>= #SMs)
+    const bool lossw = cta == 0 && (tid >> 5) == LW;
+    float l0[MAXC], l1[MAXC], l2[MAXC];
+    if (lossw) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = (tid & 31) + 32 * i;
+            const bool ok = c < a.nslots;
+            l0[i] = ok ? ld_cg(a.losspart + c * 4) : 0.f;
+            l1[i] = ok ? ld_cg(a.losspart + c * 4 + 1) : 0.f;
+            l2[i] = ok ? ld_cg(a.losspart + c * 4 + 2) : 0.f;
         }
+    }
+    const bool narrow = reduce_partials_slice<NT, KEEP>(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
+    if (lossw) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) { s0 += l0[i]; s1 += l1[i]; s2 += l2[i]; }
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2); }
+        if ((tid & 31) == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2); }
     }
     return narrow;
 }
@@ -276,12 +291,57 @@ __device__ void disc_adam_slice(const DiscArgs& a, int step, int cta, bool have,
             __stcg(a.params + p, pv); __stcg(a.m + p, mv); __stcg(a.v + p, vv);
         }
     }
-    if (cta == 0 && tid == 0) {
-        const float invB = 1.f / (float)a.B;
-        const float le = ld_cg(a.grad + a.P) * invB, lp = ld_cg(a.grad + a.P + 1) * invB;
-        const float gp = a.gp_lambda * ld_cg(a.grad + a.P + 2) * invB;
-        float* tr = a.trace + (size_t)step * 3;
-        tr[0] = (le + lp) + gp; tr[1] = le; tr[2] = lp;
+    if (cta == 0) {
+        __syncthreads();                       // loss sums were stored by the last warp (fused path)
+        if (tid == 0) {
+            const float invB = 1.f / (float)a.B;
+            const float le = ld_cg(a.grad + a.P) * invB, lp = ld_cg(a.grad + a.P + 1) * invB;
+            const float gp = a.gp_lambda * ld_cg(a.grad + a.P + 2) * invB;
+            float* tr = a.trace + (size_t)step * 3;
+            tr[0] = (le + lp) + gp; tr[1] = le; tr[2] = lp;
+        }
+    }
+}
+
+// Phase B of the register-resident kernel: slice reduction + Adam with ONE parameter per thread.  The
+// parameter / moment loads are issued before the partial sums are fetched (one L2 round trip covers both) and
+// the reduced gradient is handed over through shared memory.  Same arithmetic per element as disc_adam_slice.
+template <int NT>
+__device__ void disc_reduce_adam_fused(const DiscArgs& a, int step, int cta, float4* scr4) {
+    const int tid = threadIdx.x;
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    const int n4 = (p1 - p0) >> 2;
+    const bool narrow = n4 <= 128 && (p1 - p0) <= NT;       // one parameter per thread, gradient via shared memory
+    const int pe = p0 + tid;
+    const bool own = narrow && pe < p1;
+    float pv = 0.f, mv = 0.f, vv = 0.f;
+    if (own) { pv = __ldcg(a.params + pe); mv = __ldcg(a.m + pe); vv = __ldcg(a.v + pe); }
+    float4 mine;
+    disc_reduce_slice<NT, true>(a, cta, scr4, mine);
+    const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
+    if (narrow) {
+        if (own) {
+            const float g = reinterpret_cast<const float*>(scr4 + NT)[tid];
+            adam_update(pv, mv, vv, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            __stcg(a.params + pe, pv); __stcg(a.m + pe, mv); __stcg(a.v + pe, vv);
+        }
+    } else {
+        for (int p = p0 + tid; p < p1; p += NT) {
+            const float g = ld_cg(a.grad + p);
+            float w = __ldcg(a.params + p), m = __ldcg(a.m + p), v = __ldcg(a.v + p);
+            adam_update(w, m, v, g, a.one_minus_b1, a.b2, a.one_minus_b2, ss, bc2, a.eps);
+            __stcg(a.params + p, w); __stcg(a.m + p, m); __stcg(a.v + p, v);
+        }
+    }
+    if (cta == 0) {
+        __syncthreads();                       // loss sums were stored by the last warp
+        if (tid == 0) {
+            const float invB = 1.f / (float)a.B;
+            const float le = ld_cg(a.grad + a.P) * invB, lp = ld_cg(a.grad + a.P + 1) * invB;
+            const float gp = a.gp_lambda * ld_cg(a.grad + a.P + 2) * invB;
+            float* tr = a.trace + (size_t)step * 3;
+            tr[0] = (le + lp) + gp; tr[1] = le; tr[2] = lp;
+        }
     }
 }
 
@@ -356,9 +416,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
         pc.lap(1);
         gb.sync();
         pc.lap(2);
-        float4 mine;
-        const bool have = disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile), mine);
-        disc_adam_slice(a, step, blockIdx.x, have, mine);
+        disc_reduce_adam_fused<kStepThreads>(a, step, blockIdx.x, reinterpret_cast<float4*>(tile));
         pc.lap(3);
         gb.sync();
         pc.lap(4);
@@ -535,7 +593,7 @@ static bool disc_reg_ok(const sg_disc_config* c) {
 }
 static size_t disc_reg_smem_bytes(const sg_disc_config* c) {
     size_t tile = (size_t)DiscRegSmem::floats(c->feat_dim, c->hidden);
-    if (tile < 4 * kStepThreads) tile = 4 * kStepThreads;
+    if (tile < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);     // phase B scratch: NT + 128 float4
     return ((size_t)make_disc_reg_image(c->feat_dim, c->hidden).total + tile) * sizeof(float);
 }
 static size_t disc_resident_smem_bytes(const sg_disc_config* c) {
@@ -657,6 +715,7 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
     if (mode == 3 || mode == 2) {
         const void* fn = (const void*)disc_persistent_kernel<false>;
+        int threads = kStepThreads;
         if (mode == 3) {
             fn = (const void*)disc_persistent_kernel<true>;
             if (disc_reg_ok(cfg)) {
@@ -671,10 +730,10 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
         const size_t smem = mode == 3 ? smem_res : smem_tile;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepThreads, smem));
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
         SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_disc_update: cooperative grid of %d CTAs does not fit", grid);
         void* kargs[] = {(void*)&a};
-        SG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+        SG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), kargs, smem, s));
         count_launches(1);
     } else {
         SG_CUDA(cudaFuncSetAttribute(disc_phaseA_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tile));

@@ -538,17 +538,35 @@ __device__ __forceinline__ float eff_grad(const PpoArgs& a, int p, float g) {
 // ---- phase B: slice `cta` of the flat gradient (+ loss sums and the entropy scalar by CTA 0) ---------
 // `ls` = logstd of the CURRENT parameters (before this step's Adam), read with WL.
 // Returns true when thread tid < n4 holds float4 tid of the reduced slice in `mine` (narrow slices).
-template <class WL>
+template <class WL, bool KEEP = false>
 __device__ bool ppo_reduce_slice(const PpoArgs& a, int cta, float4* scr4, const float* ls, float4& mine) {
     const int tid = threadIdx.x;
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
-    const bool narrow = reduce_partials_slice(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
-    if (cta == 0 && tid < 32) {
-        // loss sums over the partial slots: lane-strided, then a fixed butterfly
+    // CTA 0 also sums the loss partials and forms the entropy: its LAST warp issues those loads first so that
+    // they ride along with the slice loads instead of adding serial L2 round trips to the CTA everyone waits for.
+    constexpr int LW = kStepThreads / 32 - 1, MAXC = 5;    // up to 160 slots (>= #SMs)
+    const bool lossw = cta == 0 && (tid >> 5) == LW;
+    float l0[MAXC], l1[MAXC];
+    if (lossw) {
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) {
+            const int c = (tid & 31) + 32 * i;
+            const bool ok = c < a.nslots;
+            l0[i] = ok ? ld_cg(a.losspart + c * 4) : 0.f;
+            l1[i] = ok ? ld_cg(a.losspart + c * 4 + 1) : 0.f;
+        }
+    }
+    const bool narrow = reduce_partials_slice<kStepThreads, KEEP>(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
+    if (lossw) {
         float s0 = 0.f, s1 = 0.f;
-        for (int c = tid; c < a.nslots; c += 32) { s0 += ld_cg(a.losspart + c * 4); s1 += ld_cg(a.losspart + c * 4 + 1); }
+#pragma unroll
+        for (int i = 0; i < MAXC; ++i) { s0 += l0[i]; s1 += l1[i]; }
         s0 = warp_sum(s0); s1 = warp_sum(s1);
-        if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.scal, gaussian_entropy<WL>(ls, a.A)); }
+        // entropy of the diagonal Gaussian, summed over the action dim (A2C/distributions.py:55-56): one lane per action
+        float e = 0.f;
+        for (int k = tid & 31; k < a.A; k += 32) e += 0.5f + 0.5f * SG_LOG_2PI + logf(expf(WL::ld(ls + k)));
+        e = warp_sum(e);
+        if ((tid & 31) == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.scal, e); }
     }
     return narrow;
 }
@@ -626,6 +644,41 @@ __device__ void ppo_adam_slice(const PpoArgs& a, int step, int cta, double* red,
     }
 }
 
+// Persistent kernels, narrow slices: ONE parameter per thread.  prefetch() runs in phase B (before grid barrier
+// 2: the slice belongs to this CTA, so its parameter / moment loads need not wait for the barrier) and keeps
+// {g, p, m, v} in registers; apply() runs after the barrier once the global norm is known.
+struct PpoOwnElem {
+    float g, p, m, v;
+    int idx;          // flat parameter index or -1
+};
+__device__ __forceinline__ PpoOwnElem ppo_own_prefetch(const PpoArgs& a, int cta, const float4* scr4) {
+    const int tid = threadIdx.x;
+    const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
+    PpoOwnElem e;
+    e.idx = (p0 + tid < p1) ? p0 + tid : -1;
+    e.g = e.p = e.m = e.v = 0.f;
+    if (e.idx >= 0) {
+        e.g = reinterpret_cast<const float*>(scr4 + kStepThreads)[tid];
+        e.p = __ldcg(a.params + e.idx); e.m = __ldcg(a.m + e.idx); e.v = __ldcg(a.v + e.idx);
+    }
+    return e;
+}
+__device__ void ppo_adam_own(const PpoArgs& a, int step, int cta, double* red, PpoOwnElem e) {
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (int c = tid; c < a.nslices; c += kStepThreads) s += __ldcg(a.ssq + c);
+    const double tot = block_sum_256(s, red);
+    const float norm = (float)sqrt(tot);
+    float clip = a.max_norm / (norm + 1e-6f);
+    if (clip > 1.f) clip = 1.f;
+    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
+    if (e.idx >= 0) {
+        adam_update(e.p, e.m, e.v, eff_grad(a, e.idx, e.g) * clip, a.one_minus_b1, a.b2, a.one_minus_b2, a.step_size[step],
+                    a.bc2_sqrt[step], a.eps);
+        __stcg(a.params + e.idx, e.p); __stcg(a.m + e.idx, e.m); __stcg(a.v + e.idx, e.v);
+    }
+}
+
 __device__ __forceinline__ void poison_trace_on_timeout(const PpoArgs& a) {
     // a timed-out grid barrier poisons the trace so the host raises instead of trusting the result
     if (blockIdx.x == 0 && threadIdx.x == 0 && *(volatile unsigned int*)(a.bar + 1) != 0u) a.trace[0] = __int_as_float(0x7fc00000);
@@ -643,6 +696,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
+    const bool own1 = a.SL <= kStepThreads && a.SL <= 512;      // narrow slice, one parameter per thread
     for (int step = 0; step < a.nsteps; ++step) {
         float4 mine;
         bool have;
@@ -653,7 +707,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
             pc.lap(1);
             gb.sync();
             pc.lap(2);
-            have = ppo_reduce_slice<LdShared>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.LI.ls, mine);
+            have = ppo_reduce_slice<LdShared, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.LI.ls, mine);
         } else if (RESIDENT == 1) {
             load_param_image(Ws, a.params, a.P, threadIdx.x);
             pc.lap(0);
@@ -661,19 +715,22 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
             pc.lap(1);
             gb.sync();
             pc.lap(2);
-            have = ppo_reduce_slice<LdShared>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.L.ls, mine);
+            have = ppo_reduce_slice<LdShared, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.L.ls, mine);
         } else {
             ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, tile);
             pc.lap(1);
             gb.sync();
             pc.lap(2);
-            have = ppo_reduce_slice<LdGlobal>(a, blockIdx.x, reinterpret_cast<float4*>(tile), a.params + a.L.ls, mine);
+            have = ppo_reduce_slice<LdGlobal, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), a.params + a.L.ls, mine);
         }
+        PpoOwnElem own;
+        if (own1) own = ppo_own_prefetch(a, blockIdx.x, reinterpret_cast<const float4*>(tile));
         ppo_ssq_slice(a, blockIdx.x, red, have, mine);
         pc.lap(3);
         gb.sync();
         pc.lap(4);
-        ppo_adam_slice(a, step, blockIdx.x, red, have, mine);
+        if (own1) ppo_adam_own(a, step, blockIdx.x, red, own);
+        else ppo_adam_slice(a, step, blockIdx.x, red, have, mine);
         pc.lap(5);
         gb.sync();
         pc.lap(6);
@@ -714,14 +771,14 @@ static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
 
 static size_t ppo_tile_smem_floats(const sg_ppo_config* c) {
     size_t f = (size_t)PpoSmem<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
-    return f < 4 * kStepThreads ? 4 * kStepThreads : f;      // phase B needs 256 float4 of scratch
+    return f < 4 * (kStepThreads + 128) ? 4 * (kStepThreads + 128) : f;      // phase B needs 256+128 float4 of scratch
 }
 static bool ppo_col_ok(const sg_ppo_config* c) { return (c->hidden & 3) == 0; }
 static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
     if (ppo_col_ok(c)) {
         PolicyLayout LI = make_policy_image_layout(c->obs_dim, c->hidden, c->act_dim);
         size_t tile = (size_t)PpoSmemCol<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
-        if (tile < 4 * kStepThreads) tile = 4 * kStepThreads;
+        if (tile < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);
         return ((size_t)LI.total + tile) * sizeof(float);
     }
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
