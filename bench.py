@@ -227,11 +227,18 @@ def run_cuda(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON record): library banners (e.g. "NCCL version ...") printed while
+    # the benchmark runs are routed to stderr at the file-descriptor level.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
     torch.set_num_threads(1)                               # main_gail_dyn_ppo.py:64
@@ -341,7 +348,8 @@ def run_cuda(args):
                    "hidden": c["H"], "feat_dim": c["F"], "disc_hidden": c["HD"], "ppo_epoch": HYPER["ppo_epoch"],
                    "num_mini_batch": HYPER["num_mini_batch"], "gail_epoch": HYPER["gail_epoch"],
                    "gail_batch": HYPER["gail_batch"], "optimizer_steps_per_step": w.opt_steps,
-                   "parallelism": "single GPU" if world == 1 else "minibatch data-parallel dp%d, 1 grad allreduce/step" % world,
+                   "parallelism": "single GPU" if world == 1 else
+                   "minibatch data-parallel dp%d, 1 gradient exchange/step (%s)" % (world, w.agent.dp.transport if w.agent.dp else "-"),
                    "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step, max over ranks"},
         "iters_per_s": args.steps / (ms_total * 1e-3),
         "samples_per_s": HYPER["ppo_epoch"] * w.S * args.steps / (ms_total * 1e-3),
@@ -359,7 +367,10 @@ def run_cuda(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = run_reference(args, quiet=True, budget_s=20.0)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(out))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -105,6 +105,8 @@ typedef struct sg_ppo_config {
     int mode;                 /* 0 = auto (resident if the parameter image fits in shared memory, else
                                  persistent), 1 = one launch per phase, 2 = persistent (weights through L2),
                                  3 = resident (weights in shared memory) */
+    void* dp_ctx;             /* sg_dp_create context: fused peer-memory gradient exchange inside the persistent
+                                 kernel (modes 0/2/3; every rank must pass shards of equal size); NULL = none */
 } sg_ppo_config;
 
 int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg);
@@ -130,6 +132,19 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
                   const float* adv_stats, const int32_t* perm, const float* step_size, const float* bc2_sqrt,
                   float* trace, void* workspace, sg_allreduce_fn allreduce_cb, void* allreduce_user, void* stream);
 
+/* ---- data-parallel exchange over NVLink peer memory (no reference counterpart) ---------- */
+/* One context per optimizer per rank.  sg_dp_create allocates this rank's exchange buffer (room for a flat
+ * gradient of max_floats); the 64-byte CUDA IPC handle from sg_dp_local_handle is exchanged between the ranks
+ * by the caller (any transport), concatenated in rank order and handed to sg_dp_open_peers.  A context passed
+ * as cfg->dp_ctx makes the persistent kernels exchange the locally reduced gradient slices with P2P stores,
+ * system-scope flags and a rank-ordered sum inside their reduce phase (one kernel, no collective call).
+ * In that mode the per-step loss columns of `trace` hold this rank's PARTIAL sums (add them over ranks). */
+int sg_dp_create(int rank, int world, int max_floats, void** out_ctx);
+int sg_dp_local_handle(void* ctx, unsigned char* out64);
+int sg_dp_open_peers(void* ctx, const unsigned char* handles_world_x_64);
+int sg_dp_capacity(void* ctx);
+int sg_dp_destroy(void* ctx);
+
 /* ---- GAIL discriminator -------------------------------------------------------------------- */
 typedef struct sg_disc_config {
     int feat_dim, hidden;
@@ -140,6 +155,7 @@ typedef struct sg_disc_config {
     int first_adam_step;
     int row_begin, row_end;   /* data-parallel shard of every minibatch */
     int mode;                 /* as sg_ppo_config.mode */
+    void* dp_ctx;             /* as sg_ppo_config.dp_ctx */
 } sg_disc_config;
 
 int64_t sg_disc_workspace_bytes(const sg_disc_config* cfg);

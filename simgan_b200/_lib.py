@@ -26,13 +26,14 @@ class PpoConfig(C.Structure):
                 ("clip_param", C.c_double), ("value_loss_coef", C.c_double), ("entropy_coef", C.c_double),
                 ("max_grad_norm", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
                 ("use_clipped_value_loss", C.c_int), ("first_adam_step", C.c_int),
-                ("row_begin", C.c_int), ("row_end", C.c_int), ("mode", C.c_int)]
+                ("row_begin", C.c_int), ("row_end", C.c_int), ("mode", C.c_int), ("dp_ctx", C.c_void_p)]
 
 
 class DiscConfig(C.Structure):
     _fields_ = [("feat_dim", C.c_int), ("hidden", C.c_int), ("batch_size", C.c_int), ("n_steps", C.c_int),
                 ("gp_lambda", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("adam_eps", C.c_double),
-                ("first_adam_step", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("mode", C.c_int)]
+                ("first_adam_step", C.c_int), ("row_begin", C.c_int), ("row_end", C.c_int), ("mode", C.c_int),
+                ("dp_ctx", C.c_void_p)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p)
@@ -57,6 +58,11 @@ SIGNATURES = {
     "sg_ppo_workspace_bytes": (C.c_int64, [C.POINTER(PpoConfig)]),
     "sg_ppo_phase_cycles_offset": (C.c_int64, [C.POINTER(PpoConfig)]),
     "sg_ppo_update": (C.c_int, [C.POINTER(PpoConfig)] + [c_void] * 14 + [ALLREDUCE_FN, c_void, c_void]),
+    "sg_dp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "sg_dp_local_handle": (C.c_int, [c_void, C.c_char_p]),
+    "sg_dp_open_peers": (C.c_int, [c_void, C.c_char_p]),
+    "sg_dp_capacity": (C.c_int, [c_void]),
+    "sg_dp_destroy": (C.c_int, [c_void]),
     "sg_disc_workspace_bytes": (C.c_int64, [C.POINTER(DiscConfig)]),
     "sg_disc_phase_cycles_offset": (C.c_int64, [C.POINTER(DiscConfig)]),
     "sg_disc_update": (C.c_int, [C.POINTER(DiscConfig)] + [c_void] * 12 + [ALLREDUCE_FN, c_void, c_void]),

@@ -121,7 +121,11 @@ class Discriminator(nn.Module):
         cfg.beta1, cfg.beta2, cfg.adam_eps = g["betas"][0], g["betas"][1], g["eps"]
         cfg.first_adam_step = opt.step_count + 1
         cfg.row_begin, cfg.row_end = (0, B) if self.dp is None else self.dp.shard(B)
-        cfg.mode = self.kernel_mode if self.dp is None else 1
+        p2p = self.dp is not None and self.dp.p2p_ok(B)
+        cfg.mode = self.kernel_mode if (self.dp is None or p2p) else 1
+        if cfg.mode == 1 and p2p:
+            cfg.mode = 0
+        cfg.dp_ctx = self.dp.context("disc", flat.numel()) if p2p else None
         lib = _lib.lib()
         need = lib.sg_disc_workspace_bytes(C.byref(cfg))
         if need < 0:
@@ -139,7 +143,7 @@ class Discriminator(nn.Module):
         sched = torch.from_numpy(opt.schedule(n)).to(dev)
         trace = torch.empty(n, 3, device=dev)
         cb, user = _lib.NULL_ALLREDUCE, None
-        if self.dp is not None:
+        if self.dp is not None and not p2p:
             cb = self.dp.make_callback(ws)
         tok = _lib.timer.start("disc_update")
         rc = lib.sg_disc_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(expert),
@@ -150,6 +154,8 @@ class Discriminator(nn.Module):
         _lib.check(rc, "sg_disc_update")
         opt.step_count += n
         self.__dict__["_prof_view"] = (ws, int(lib.sg_disc_phase_cycles_offset(C.byref(cfg))))
+        if p2p:
+            self.dp.sum_trace_(trace, 3)      # all three loss columns are per-rank partial sums
         tr = trace.cpu()
         if not bool(torch.isfinite(tr).all()):
             raise _lib.SgError("sg_disc_update produced non-finite losses (grid barrier timeout or diverged update)")

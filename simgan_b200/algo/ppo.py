@@ -103,7 +103,11 @@ class PPO(object):
         cfg.use_clipped_value_loss = int(bool(self.use_clipped_value_loss))
         cfg.first_adam_step = opt.step_count + 1
         cfg.row_begin, cfg.row_end = (0, mbs) if self.dp is None else self.dp.shard(mbs)
-        cfg.mode = self.kernel_mode if self.dp is None else 1
+        p2p = self.dp is not None and self.dp.p2p_ok(mbs)
+        cfg.mode = self.kernel_mode if (self.dp is None or p2p) else 1
+        if cfg.mode == 1 and p2p:
+            cfg.mode = 0
+        cfg.dp_ctx = self.dp.context("ppo", flat.numel()) if p2p else None
 
         lib = _lib.lib()
         stream = _lib.current_stream()
@@ -123,7 +127,7 @@ class PPO(object):
         trace = torch.empty(n_steps, 4, device=dev)
 
         cb, user = _lib.NULL_ALLREDUCE, None
-        if self.dp is not None:
+        if self.dp is not None and not p2p:
             cb = self.dp.make_callback(ws)
         tok = _lib.timer.start("ppo_update")
         rc = lib.sg_ppo_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
@@ -135,6 +139,8 @@ class PPO(object):
         opt.step_count += n_steps
 
         self._prof_view = (ws, int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
+        if p2p:
+            self.dp.sum_trace_(trace, 2)      # value / action loss columns are per-rank partial sums
         tr = trace.cpu()            # the one host sync of the update
         if not bool(torch.isfinite(tr).all()):
             raise _lib.SgError("sg_ppo_update produced non-finite losses (grid barrier timeout or diverged update)")

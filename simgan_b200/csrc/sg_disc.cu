@@ -23,9 +23,14 @@
 //   dW2 += zb2 h1^T  ;  db2 += zb2    ;  hb1 += W2^T zb2     ;  zb1 = hb1*(1-h1^2)
 //   dW1 += zb1 x^^T  ;  db1 += zb1
 #include "sg_common.cuh"
+#include <string.h>
+
 #include "sg_disc_reg.cuh"
+#include "sg_dp.cuh"
 
 namespace sg {
+
+DpView dp_view(const void* ctx);
 
 constexpr int kTB = 2;            // (expert, policy, mixup) triples per CTA tile
 constexpr int kDR = 4 * kTB;      // row slots of a tile: [expert | policy | mixup | penalty-pair]
@@ -42,6 +47,9 @@ struct DiscArgs {
     float *gpart, *grad, *losspart;
     unsigned int* bar;
     long long* prof;
+    int first_adam_step;
+    int dp_on;            // fused peer-memory gradient exchange (sg_dp.cuh)
+    DpView dp;
 };
 
 struct DiscSmem {
@@ -318,6 +326,9 @@ __device__ void disc_reduce_adam_fused(const DiscArgs& a, int step, int cta, flo
     if (own) { pv = __ldcg(a.params + pe); mv = __ldcg(a.m + pe); vv = __ldcg(a.v + pe); }
     float4 mine;
     disc_reduce_slice<NT, true>(a, cta, scr4, mine);
+    if (a.dp_on)
+        dp_exchange_slice<NT>(a.dp, a.grad, p0, p1, cta, (unsigned int)(a.first_adam_step + step),
+                              n4 <= 128 ? reinterpret_cast<float*>(scr4 + NT) : nullptr);
     const float ss = a.step_size[step], bc2 = a.bc2_sqrt[step];
     if (narrow) {
         if (own) {
@@ -383,7 +394,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscAr
         gb.sync();
         pc.lap(2);
         float4 mine;
-        const bool have = disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile), mine);
+        bool have = disc_reduce_slice(a, blockIdx.x, reinterpret_cast<float4*>(tile), mine);
+        if (a.dp_on) {
+            const int p0 = min(a.P, (int)blockIdx.x * a.SL), p1 = min(a.P, p0 + a.SL);
+            dp_exchange_slice<kStepThreads>(a.dp, a.grad, p0, p1, blockIdx.x, (unsigned int)(a.first_adam_step + step), nullptr);
+            have = false;                  // re-read the exchanged totals from the flat gradient
+        }
         disc_adam_slice(a, step, blockIdx.x, have, mine);
         pc.lap(3);
         gb.sync();
@@ -687,6 +703,7 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     SG_REQUIRE(params && adam_m && adam_v && expert && policy_feat && expert_idx && policy_idx && alpha && step_size &&
                    bc2_sqrt && trace && workspace, "sg_disc_update: null pointer");
     SG_REQUIRE(!(allreduce_cb && cfg->mode != 1), "sg_disc_update: the allreduce callback needs mode 1");
+    SG_REQUIRE(!(cfg->dp_ctx && (cfg->mode == 1 || allreduce_cb)), "sg_disc_update: dp_ctx needs a persistent mode and no callback");
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 0;
     const int grid = disc_grid(cfg, &sms);
@@ -708,6 +725,14 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
     a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
     a.bar = (unsigned int*)(ws + w.bar); a.prof = (long long*)(ws + w.prof);
+    a.first_adam_step = cfg->first_adam_step;
+    a.dp_on = cfg->dp_ctx != nullptr;
+    if (a.dp_on) {
+        a.dp = dp_view(cfg->dp_ctx);
+        SG_REQUIRE(a.dp.cap >= a.P + 4 && grid < kDpMaxSlices, "sg_disc_update: dp context too small (%d floats)", a.dp.cap);
+    } else {
+        memset(&a.dp, 0, sizeof(a.dp));
+    }
     const size_t smem_tile = disc_tile_smem_floats(cfg) * sizeof(float);
     const size_t smem_res = disc_resident_smem_bytes(cfg);
     int mode = cfg->mode;

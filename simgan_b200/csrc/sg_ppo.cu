@@ -20,8 +20,13 @@
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
 #include "sg_colgemm.cuh"
+#include <string.h>
+
+#include "sg_dp.cuh"
 
 namespace sg {
+
+DpView dp_view(const void* ctx);
 
 struct PpoArgs {
     int O, H, A, S, P;
@@ -40,6 +45,8 @@ struct PpoArgs {
     double* ssq;
     unsigned int* bar;
     long long* prof;      // per-phase clock64 totals of CTA 0 (sg_ppo_phase_cycles)
+    int dp_on;            // fused peer-memory gradient exchange (sg_dp.cuh)
+    DpView dp;
 };
 
 template <int R>
@@ -723,6 +730,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
             pc.lap(2);
             have = ppo_reduce_slice<LdGlobal, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), a.params + a.L.ls, mine);
         }
+        if (a.dp_on) {
+            // data parallel: swap my locally reduced slice with the peers' over NVLink, keep the rank-ordered total
+            const int p0 = min(a.P, (int)blockIdx.x * a.SL), p1 = min(a.P, p0 + a.SL);
+            float4* scr4 = reinterpret_cast<float4*>(tile);
+            dp_exchange_slice<kStepThreads>(a.dp, a.grad, p0, p1, blockIdx.x, (unsigned int)(a.first_adam_step + step),
+                                            have ? reinterpret_cast<float*>(scr4 + kStepThreads) : nullptr);
+            if (have) mine = (4 * (int)threadIdx.x < p1 - p0) ? scr4[kStepThreads + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         PpoOwnElem own;
         if (own1) own = ppo_own_prefetch(a, blockIdx.x, reinterpret_cast<const float4*>(tile));
         ppo_ssq_slice(a, blockIdx.x, red, have, mine);
@@ -848,6 +863,7 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     SG_REQUIRE(params && adam_m && adam_v && obs && actions && value_preds && returns && old_logp && adv_stats && perm &&
                    step_size && bc2_sqrt && trace && workspace, "sg_ppo_update: null pointer");
     SG_REQUIRE(!(allreduce_cb && cfg->mode != 1), "sg_ppo_update: the allreduce callback needs mode 1");
+    SG_REQUIRE(!(cfg->dp_ctx && (cfg->mode == 1 || allreduce_cb)), "sg_ppo_update: dp_ctx needs a persistent mode and no callback");
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 0;
     const int grid = ppo_grid(cfg, &sms);
@@ -880,6 +896,13 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     a.perm = perm; a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
     a.scal = (float*)(ws + w.scal); a.ssq = (double*)(ws + w.ssq); a.bar = (unsigned int*)(ws + w.bar); a.prof = (long long*)(ws + w.prof);
+    a.dp_on = cfg->dp_ctx != nullptr;
+    if (a.dp_on) {
+        a.dp = dp_view(cfg->dp_ctx);
+        SG_REQUIRE(a.dp.cap >= a.P + 4 && a.nslices < kDpMaxSlices, "sg_ppo_update: dp context too small (%d floats, %d slices)", a.dp.cap, a.nslices);
+    } else {
+        memset(&a.dp, 0, sizeof(a.dp));
+    }
 
     const size_t smem_tile = ppo_tile_smem_floats(cfg) * sizeof(float);
     const size_t smem_res = ppo_resident_smem_bytes(cfg);

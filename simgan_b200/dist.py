@@ -6,6 +6,15 @@ index permutation from its identically-seeded CPU generator, processes the conti
 ``[row_begin,row_end)`` of every minibatch, and the flat gradient (+ loss sums) is summed with ONE
 allreduce per optimizer step between the reduce phase and the clip+Adam epilogue, which every rank then
 runs identically (no parameter broadcast).
+
+Two transports for that exchange:
+
+* ``p2p`` (default on CUDA): the persistent step kernel itself pushes its locally reduced gradient slices into
+  the peers' exchange buffers over NVLink (CUDA IPC peer pointers), publishes them with system-scope flags and
+  adds the world's slices in rank order -- no collective call and no extra launch per step
+  (csrc/sg_dp.cuh).  Needs shards of equal size on every rank.
+* ``nccl``: one launch per phase and a ``torch.distributed.all_reduce`` of the flat gradient between the reduce
+  and the clip+Adam phase (C callback ``sg_allreduce_fn``); also what the gloo CPU tests exercise.
 """
 import ctypes as C
 
@@ -23,14 +32,58 @@ def shard_bounds(n_rows, rank, world):
 
 
 class DataParallel(object):
-    def __init__(self, group=None):
+    def __init__(self, group=None, transport=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        if transport is None:
+            transport = "p2p" if (torch.cuda.is_available() and dist.get_backend(group) == "nccl") else "nccl"
+        assert transport in ("p2p", "nccl")
+        self.transport = transport
         self.n_allreduce = 0
         self._cb = None
+        self._ctx = {}           # key -> sg_dp context (one per optimizer)
+
+    # ---- fused peer-memory exchange -----------------------------------------------------------------------
+    def p2p_ok(self, n_rows):
+        """The in-kernel exchange needs identical shard sizes (identical grids / slice tables) on every rank."""
+        return self.transport == "p2p" and n_rows % self.world == 0
+
+    def context(self, key, n_floats):
+        """Create (once) the exchange context of one optimizer: allocate this rank's buffer, swap the CUDA IPC
+        handles with the peers and map their buffers.  Collective: every rank must call it in the same order."""
+        ctx = self._ctx.get(key)
+        lib = _lib.lib()
+        if ctx is not None and lib.sg_dp_capacity(ctx) >= n_floats + 4:
+            return ctx
+        if ctx is not None:
+            lib.sg_dp_destroy(ctx)
+        ctx = C.c_void_p()
+        _lib.check(lib.sg_dp_create(self.rank, self.world, int(n_floats) + 4, C.byref(ctx)), "sg_dp_create")
+        mine = C.create_string_buffer(64)
+        _lib.check(lib.sg_dp_local_handle(ctx, mine), "sg_dp_local_handle")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=self.group)
+        blob = b"".join(handles)
+        _lib.check(lib.sg_dp_open_peers(ctx, blob), "sg_dp_open_peers")
+        dist.barrier(group=self.group)
+        self._ctx[key] = ctx
+        return ctx
+
+    def sum_trace_(self, trace, n_cols):
+        """Per-step loss columns of a p2p-mode trace are this rank's partial sums: add them over the ranks."""
+        part = trace[:, :n_cols].contiguous()
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        trace[:, :n_cols] = part
+        return trace
+
+    def close(self):
+        lib = _lib.lib()
+        for ctx in self._ctx.values():
+            lib.sg_dp_destroy(ctx)
+        self._ctx = {}
 
     def shard(self, n_rows):
         b, e = shard_bounds(n_rows, self.rank, self.world)
@@ -65,11 +118,11 @@ class DataParallel(object):
         return self._cb
 
 
-def attach(ppo=None, disc=None, group=None):
+def attach(ppo=None, disc=None, group=None, transport=None):
     """Enable data-parallel updates on a PPO and/or Discriminator object when world_size > 1."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
-    dp = DataParallel(group)
+    dp = DataParallel(group, transport)
     if ppo is not None:
         ppo.dp = dp
     if disc is not None:

@@ -20,7 +20,7 @@ def _free_port():
     return port
 
 
-def _run_case(g, dp_on, dev):
+def _run_case(g, dp_on, dev, transport=None):
     import gpu_util as gu
     import simgan_b200 as sg
     from simgan_b200 import dist as sg_dist
@@ -37,7 +37,8 @@ def _run_case(g, dp_on, dev):
     expert = g.t("expert").to(dev)
     loader = DataLoader(TensorDataset(expert), batch_size=g.gail_batch, shuffle=True, drop_last=len(expert) > g.gail_batch)
     if dp_on:
-        sg_dist.attach(ppo=agent, disc=d)
+        dp = sg_dist.attach(ppo=agent, disc=d, transport=transport)
+        assert dp.transport == transport
     else:
         agent.kernel_mode = 1
         d.kernel_mode = 1
@@ -47,7 +48,7 @@ def _run_case(g, dp_on, dev):
             pol.flat_params().cpu().clone(), d.flat_params().cpu().clone())
 
 
-def _worker(rank, world, port, case, out):
+def _worker(rank, world, port, case, out, transport):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import sys
@@ -59,7 +60,7 @@ def _worker(rank, world, port, case, out):
         from golden_util import Golden
         torch.set_num_threads(1)
         g = Golden(case)
-        res = _run_case(g, True, dev)
+        res = _run_case(g, True, dev, transport)
         torch.cuda.synchronize()
         # every rank ends with identical parameters (same clip+Adam epilogue on the same reduced gradient)
         for t in (res[4], res[5]):
@@ -84,12 +85,13 @@ def _worker(rank, world, port, case, out):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("case", ["hopper_cfg1_seed0.npz", "laika_dims_seed2.npz"])
-def test_data_parallel_matches_single_gpu(case, tmp_path):
+def test_data_parallel_matches_single_gpu(case, transport, tmp_path):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     world = 2
     out = str(tmp_path / "ok")
-    mp.spawn(_worker, args=(world, _free_port(), case, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), case, out, transport), nprocs=world, join=True)
     assert os.path.exists(out)
