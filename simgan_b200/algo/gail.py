@@ -76,6 +76,8 @@ class Discriminator(nn.Module):
         state["_ws"] = None
         state.pop("_prof_view", None)
         state.pop("_rms_dev", None)
+        state.pop("_predraw", None)
+        state.pop("_stage", None)
         return state
 
     # ---- update --------------------------------------------------------------------------------------------
@@ -108,7 +110,27 @@ class Discriminator(nn.Module):
         return (e_perm[:n * batch_size].view(n, batch_size), p_perm[:n * batch_size].view(n, batch_size),
                 alpha.view(n, batch_size))
 
-    def _run_update(self, expert, policy_feat, e_idx, p_idx, alpha):
+    # ---- speculative index draws ---------------------------------------------------------------------------------
+    # The caller runs gail_epoch back-to-back epochs (main_gail_dyn_ppo.py:255-256).  While the kernel of one epoch
+    # runs, the host draws the streams the NEXT call would draw -- then rewinds the CPU generator, so nothing has
+    # been consumed as far as any other code can tell.  The next call takes the pre-drawn streams only if the
+    # generator is still exactly where the speculation started (and the sizes match) and then fast-forwards it to
+    # where the reference's own draws would have left it; otherwise the speculation is discarded.
+    def _speculate_next_draw(self, *key):
+        before = torch.get_rng_state()
+        draw = self.draw_epoch_indices(*key)
+        after = torch.get_rng_state()
+        torch.set_rng_state(before)
+        self.__dict__["_predraw"] = (key, before, after, draw)
+
+    def _take_or_draw(self, key):
+        pre = self.__dict__.pop("_predraw", None)
+        if pre is not None and pre[0] == key and torch.equal(torch.get_rng_state(), pre[1]):
+            torch.set_rng_state(pre[2])
+            return pre[3]
+        return self.draw_epoch_indices(*key)
+
+    def _run_update(self, expert, policy_feat, e_idx, p_idx, alpha, speculate=None):
         flat = self.flat_params()
         dev = flat.device
         n, B = e_idx.shape
@@ -134,12 +156,18 @@ class Discriminator(nn.Module):
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
             self.__dict__["_ws"] = ws
-        # one pinned staging block: [expert_idx | policy_idx] int32 and alpha fp32
-        stage_i = torch.empty(2, n, B, dtype=torch.int32).pin_memory()
+        # cached pinned staging block: [expert_idx | policy_idx] int32 and alpha fp32
+        st = self.__dict__.get("_stage")
+        if st is None or st[0].shape != (2, n, B) or st[2].device != dev:
+            st = (torch.empty(2, n, B, dtype=torch.int32).pin_memory(), torch.empty(n, B, dtype=torch.float32).pin_memory(),
+                  torch.empty(2, n, B, dtype=torch.int32, device=dev), torch.empty(n, B, dtype=torch.float32, device=dev))
+            self.__dict__["_stage"] = st
+        stage_i, stage_a, idx_dev, alpha_dev = st
         stage_i[0].copy_(e_idx)
         stage_i[1].copy_(p_idx)
-        idx_dev = stage_i.to(dev, non_blocking=True)
-        alpha_dev = alpha.contiguous().pin_memory().to(dev, non_blocking=True)
+        stage_a.copy_(alpha)
+        idx_dev.copy_(stage_i, non_blocking=True)
+        alpha_dev.copy_(stage_a, non_blocking=True)
         sched = torch.from_numpy(opt.schedule(n)).to(dev)
         trace = torch.empty(n, 3, device=dev)
         cb, user = _lib.NULL_ALLREDUCE, None
@@ -154,6 +182,8 @@ class Discriminator(nn.Module):
         _lib.check(rc, "sg_disc_update")
         opt.step_count += n
         self.__dict__["_prof_view"] = (ws, int(lib.sg_disc_phase_cycles_offset(C.byref(cfg))))
+        if speculate is not None:
+            self._speculate_next_draw(*speculate)     # host draws the next epoch's streams while the GPU runs this one
         if p2p:
             self.dp.sum_trace_(trace, 3)      # all three loss columns are per-rank partial sums
         tr = trace.cpu()
@@ -192,13 +222,14 @@ class Discriminator(nn.Module):
         F = rollouts.obs_feat.shape[-1]
         assert expert.shape[1] == F == self.feat_dim
         policy_feat = rollouts.obs_feat[1:].reshape(S, F)       # next_obs_feat rows (storage.py:172, gail.py:166)
+        key = None
         if replay is None:
-            e_idx, p_idx, alpha = self.draw_epoch_indices(expert.shape[0], expert_loader.batch_size,
-                                                          bool(expert_loader.drop_last), S)
+            key = (expert.shape[0], expert_loader.batch_size, bool(expert_loader.drop_last), S)
+            e_idx, p_idx, alpha = self._take_or_draw(key)
         else:
             e_idx, p_idx, alpha = [x if torch.is_tensor(x) else torch.stack([torch.as_tensor(r).reshape(-1) for r in x])
                                    for x in replay]
-        return self._run_update(expert, policy_feat, e_idx, p_idx, alpha)
+        return self._run_update(expert, policy_feat, e_idx, p_idx, alpha, speculate=key)
 
     def update(self, expert_loader, rollouts, obsfilt=None, is_gail_dyn=False, a_dim=None):
         """Legacy (state, action)-split variant (gail.py:91-152): the D input is cat([state, action]) on

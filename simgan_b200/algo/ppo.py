@@ -42,6 +42,7 @@ class PPO(object):
         self.last_trace = None          # (n_steps, 4) {value_loss, action_loss, entropy, grad_norm}
         self._ws = None
         self._stage = None
+        self._perm_dev = None
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _workspace(self, cfg, dev):
@@ -56,12 +57,10 @@ class PPO(object):
         """ppo_epoch x torch.randperm(S) on the CPU default generator -- the sampler stream of
         feed_forward_generator (storage.py:158-162), one draw per epoch (ppo.py:79-80)."""
         n = self.ppo_epoch
-        if self._stage is None or self._stage.shape != (n, S):
-            self._stage = torch.empty(n, S, dtype=torch.int32).pin_memory() if torch.cuda.is_available() \
-                else torch.empty(n, S, dtype=torch.int32)
+        out = torch.empty(n, S, dtype=torch.int32)
         for e in range(n):
-            self._stage[e].copy_(torch.randperm(S))
-        return self._stage
+            out[e].copy_(torch.randperm(S))
+        return out
 
     def phase_cycles(self):
         """Diagnostics: per-phase SM-clock totals of CTA 0 of the last persistent launch
@@ -117,25 +116,38 @@ class PPO(object):
         stat_ws = torch.empty(int(lib.sg_adv_stats_workspace_bytes(S)), dtype=torch.uint8, device=dev)
         _lib.check(lib.sg_adv_stats(_lib.ptr(rollouts.returns), _lib.ptr(rollouts.value_preds), S, _lib.ptr(stats),
                                     _lib.ptr(stat_ws), stream), "sg_adv_stats")
-        # sampler index stream + Adam scalars -> device
-        if permutations is None:
-            perm_host = self.draw_permutations(S)
-        else:
-            perm_host = torch.as_tensor(permutations).to(torch.int32).reshape(self.ppo_epoch, S)
-        perm = perm_host.to(dev, non_blocking=True)
+        # Adam scalars -> device; sampler index stream: one torch.randperm(S) per epoch on the CPU default generator
+        # (storage.py:158-162).  Epochs are launched one by one so that the host draws epoch e+1 while the GPU
+        # runs epoch e (the launches are asynchronous; nothing below synchronises until the trace is read).
         sched = torch.from_numpy(opt.schedule(n_steps)).to(dev)
         trace = torch.empty(n_steps, 4, device=dev)
+        nmb = self.num_mini_batch
+        if self._stage is None or self._stage.shape != (self.ppo_epoch, S):
+            self._stage = torch.empty(self.ppo_epoch, S, dtype=torch.int32)
+            if torch.cuda.is_available():
+                self._stage = self._stage.pin_memory()
+        if self._perm_dev is None or self._perm_dev.shape != (self.ppo_epoch, S) or self._perm_dev.device != dev:
+            self._perm_dev = torch.empty(self.ppo_epoch, S, dtype=torch.int32, device=dev)
+        if permutations is not None:
+            permutations = torch.as_tensor(permutations).to(torch.int32).reshape(self.ppo_epoch, S)
 
         cb, user = _lib.NULL_ALLREDUCE, None
         if self.dp is not None and not p2p:
             cb = self.dp.make_callback(ws)
-        tok = _lib.timer.start("ppo_update")
-        rc = lib.sg_ppo_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
-                               _lib.ptr(rollouts.actions), _lib.ptr(rollouts.value_preds), _lib.ptr(rollouts.returns),
-                               _lib.ptr(rollouts.action_log_probs), _lib.ptr(stats), _lib.ptr(perm),
-                               _lib.ptr(sched[0]), _lib.ptr(sched[1]), _lib.ptr(trace), _lib.ptr(ws), cb, user, stream)
-        _lib.timer.stop(tok)
-        _lib.check(rc, "sg_ppo_update")
+        cfg.ppo_epoch = 1
+        for e in range(self.ppo_epoch):
+            self._stage[e].copy_(torch.randperm(S) if permutations is None else permutations[e])
+            self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
+            cfg.first_adam_step = opt.step_count + 1 + e * nmb
+            tok = _lib.timer.start("ppo_update")
+            rc = lib.sg_ppo_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
+                                   _lib.ptr(rollouts.actions), _lib.ptr(rollouts.value_preds), _lib.ptr(rollouts.returns),
+                                   _lib.ptr(rollouts.action_log_probs), _lib.ptr(stats), _lib.ptr(self._perm_dev[e]),
+                                   _lib.ptr(sched[0, e * nmb:]), _lib.ptr(sched[1, e * nmb:]), _lib.ptr(trace[e * nmb:]),
+                                   _lib.ptr(ws), cb, user, stream)
+            _lib.timer.stop(tok)
+            _lib.check(rc, "sg_ppo_update")
+        cfg.ppo_epoch = self.ppo_epoch
         opt.step_count += n_steps
 
         self._prof_view = (ws, int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))

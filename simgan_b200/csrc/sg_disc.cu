@@ -464,8 +464,10 @@ __global__ void __launch_bounds__(kStepThreads) disc_reward_kernel(const float* 
     constexpr int R = kRows;
     extern __shared__ __align__(16) float smem[];
     const int ldf = round_up(F, 4), ldh = round_up(H, 4);
-    float* X = smem; float* H1 = X + R * ldf; float* H2 = H1 + R * ldh; float* D = H2 + R * ldh;
+    float* Ws = smem;                                   // parameter image: read once per CTA, reused by every tile
+    float* X = Ws + L.total; float* H1 = X + R * ldf; float* H2 = H1 + R * ldh; float* D = H2 + R * ldh;
     const int tid = threadIdx.x;
+    load_param_image(Ws, params, L.total, tid);
     for (int tile = blockIdx.x; tile * R < n_rows; tile += gridDim.x) {
         const int row0 = tile * R;
         for (int e = tid; e < R * ldf; e += kStepThreads) {
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(kStepThreads) disc_reward_kernel(const float* 
             X[e] = (row0 + r < n_rows && k < F) ? d_in[(size_t)(row0 + r) * F + k] : 0.f;
         }
         __syncthreads();
-        disc_tile_forward<R, LdGlobal>(params, L, F, H, X, ldf, H1, H2, ldh, D, tid);
+        disc_tile_forward<R, LdShared>(Ws, L, F, H, X, ldf, H1, H2, ldh, D, tid);
         if (tid < R && row0 + tid < n_rows) {
             const int row = row0 + tid;
             const float s = sigmoidf(D[tid]);
@@ -488,30 +490,58 @@ __global__ void __launch_bounds__(kStepThreads) disc_reward_kernel(const float* 
 
 // returns_t = returns_{t-1}*gamma*masks[t] + raw_t per env column; keeps every step's returns for the
 // running statistics (gail.py:206-209 called with masks[step], main_gail_dyn_ppo.py:276-280).
-__global__ void __launch_bounds__(128) relabel_scan_kernel(const float* __restrict__ raw, const float* __restrict__ masks,
+// One CTA per 32 columns; all threads stream chunks of steps through double-buffered shared memory with
+// cp.async while the first `cols` threads walk the recurrence (see returns_scan_staged_kernel).
+constexpr int kRTC = 32;
+__device__ __forceinline__ void rl_cp_async4(float* dst_smem, const float* src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__global__ void __launch_bounds__(256) relabel_scan_kernel(const float* __restrict__ raw, const float* __restrict__ masks,
                                                            float* __restrict__ ret_all, float* __restrict__ disc_returns,
                                                            int T, int N, float gamma, int has_returns) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float ret = has_returns ? disc_returns[n] : 0.f;
-    constexpr int U = 8;
-    for (int t0 = 0; t0 < T; t0 += U) {
-        float r[U], m[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t0 + u;
-            r[u] = t < T ? raw[(size_t)t * N + n] : 0.f;
-            m[u] = t < T ? masks[(size_t)t * N + n] : 0.f;
+    __shared__ float sR[2][kRTC][32], sM[2][kRTC][32], sO[kRTC][32];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * 32;
+    const int cols = min(32, N - n0);
+    const int nchunks = (T + kRTC - 1) / kRTC;
+    auto issue = [&](int k) {
+        const int b = k & 1;
+        for (int e = tid; e < kRTC * 32; e += 256) {
+            const int tt = e >> 5, c = e & 31;
+            const int t = k * kRTC + tt;
+            if (c < cols && t < T) {
+                rl_cp_async4(&sR[b][tt][c], raw + (size_t)t * N + n0 + c);
+                rl_cp_async4(&sM[b][tt][c], masks + (size_t)t * N + n0 + c);
+            }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t0 + u;
-            if (t >= T) break;
-            ret = (has_returns || t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), m[u]), r[u]) : r[u];
-            ret_all[(size_t)t * N + n] = ret;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float ret = 0.f;
+    if (tid < cols && has_returns) ret = disc_returns[n0 + tid];
+    issue(0);
+    for (int k = 0; k < nchunks; ++k) {
+        if (k + 1 < nchunks) { issue(k + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int b = k & 1;
+        if (tid < cols) {
+#pragma unroll 4
+            for (int tt = 0; tt < kRTC; ++tt) {
+                const int t = k * kRTC + tt;
+                if (t >= T) break;
+                ret = (has_returns || t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), sM[b][tt][tid]), sR[b][tt][tid]) : sR[b][tt][tid];
+                sO[tt][tid] = ret;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kRTC * 32; e += 256) {
+            const int tt = e >> 5, c = e & 31;
+            const int t = k * kRTC + tt;
+            if (c < cols && t < T) ret_all[(size_t)t * N + n0 + c] = sO[tt][c];
         }
     }
-    disc_returns[n] = ret;
+    if (tid < cols) disc_returns[n0 + tid] = ret;
 }
 
 // numpy's float32 pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum), so that
@@ -556,25 +586,44 @@ __global__ void __launch_bounds__(128) relabel_moments_kernel(const float* __res
     mean_returns[t] = mean;
 }
 
-// the sequential float64 Chan merge (running_mean_std.py:45-56); scale[t] = sqrt(var_t + 1e-7)
-__global__ void relabel_rms_kernel(const float* __restrict__ bmean, const float* __restrict__ bvar, int T, int N,
-                                   double* __restrict__ rms, double* __restrict__ scale) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// the sequential float64 Chan merge (running_mean_std.py:45-56); scale[t] = sqrt(var_t + 1e-7).
+// The chain itself is inherently serial (one thread); the other threads of the CTA stage the per-step batch
+// moments in shared memory, a chunk ahead, so that no global-memory latency sits inside the chain.
+constexpr int kRmsChunk = 1024;
+__global__ void __launch_bounds__(256) relabel_rms_kernel(const float* __restrict__ bmean, const float* __restrict__ bvar, int T, int N,
+                                                          double* __restrict__ rms, double* __restrict__ scale) {
+    __shared__ float sMean[2][kRmsChunk], sVar[2][kRmsChunk];
+    __shared__ double sScale[kRmsChunk];
+    const int tid = threadIdx.x;
     double mean = rms[0], var = rms[1], count = rms[2];
     const double bc = (double)N;
-    for (int t = 0; t < T; ++t) {
-        // explicit round-to-nearest ops: no FMA contraction, numpy evaluates these one by one
-        const double delta = __dsub_rn((double)bmean[t], mean);
-        const double tot = __dadd_rn(count, bc);
-        const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, bc), tot));
-        const double m_a = __dmul_rn(var, count);
-        const double m_b = (double)__fmul_rn(bvar[t], (float)N);     // float32 * int stays float32 in numpy
-        const double corr = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), bc), tot);
-        const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), corr);
-        mean = new_mean; var = __ddiv_rn(m2, tot); count = tot;
-        scale[t] = sqrt(__dadd_rn(var, 1e-7));
+    const int nchunks = (T + kRmsChunk - 1) / kRmsChunk;
+    for (int e = tid; e < kRmsChunk && e < T; e += 256) { sMean[0][e] = bmean[e]; sVar[0][e] = bvar[e]; }
+    __syncthreads();
+    for (int k = 0; k < nchunks; ++k) {
+        const int b = k & 1, t0 = k * kRmsChunk, len = min(kRmsChunk, T - t0);
+        if (tid == 0) {
+            for (int i = 0; i < len; ++i) {
+                // explicit round-to-nearest ops: no FMA contraction, numpy evaluates these one by one
+                const double delta = __dsub_rn((double)sMean[b][i], mean);
+                const double tot = __dadd_rn(count, bc);
+                const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, bc), tot));
+                const double m_a = __dmul_rn(var, count);
+                const double m_b = (double)__fmul_rn(sVar[b][i], (float)N);     // float32 * int stays float32 in numpy
+                const double corr = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), bc), tot);
+                const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), corr);
+                mean = new_mean; var = __ddiv_rn(m2, tot); count = tot;
+                sScale[i] = sqrt(__dadd_rn(var, 1e-7));
+            }
+        } else if (k + 1 < nchunks) {
+            const int t1 = t0 + kRmsChunk;
+            for (int e = tid - 1; e < kRmsChunk && t1 + e < T; e += 255) { sMean[b ^ 1][e] = bmean[t1 + e]; sVar[b ^ 1][e] = bvar[t1 + e]; }
+        }
+        __syncthreads();
+        for (int e = tid; e < len; e += 256) scale[t0 + e] = sScale[e];
+        __syncthreads();
     }
-    rms[0] = mean; rms[1] = var; rms[2] = count;
+    if (tid == 0) { rms[0] = mean; rms[1] = var; rms[2] = count; }
 }
 
 // rewards[t] = float32(clip(float64(raw)/sqrt(var_t+1e-7), -10, 10))   (main_gail_dyn_ppo.py:288-292)
@@ -662,15 +711,18 @@ static RelabelWs relabel_ws(int T, int N) {
 static int launch_reward(const float* params, int F, int H, const float* d_in, int n_rows, float offset, float* reward,
                          float* returns, const float* masks, float gamma, int has_returns, cudaStream_t s) {
     DiscLayout L = make_disc_layout(F, H);
-    const size_t smem = (size_t)(kRows * round_up(F, 4) + 2 * kRows * round_up(H, 4) + kRows) * sizeof(float);
-    SG_REQUIRE(smem <= 200 * 1024, "disc reward: tile needs %zu bytes of shared memory", smem);
+    const size_t smem = (size_t)(L.total + kRows * round_up(F, 4) + 2 * kRows * round_up(H, 4) + kRows) * sizeof(float);
+    SG_REQUIRE(smem <= 220 * 1024, "disc reward: tile + parameter image need %zu bytes of shared memory", smem);
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         SG_CUDA(cudaFuncSetAttribute(disc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     int tiles = (n_rows + kRows - 1) / kRows;
-    int grid = tiles < 1184 ? tiles : 1184;
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int per_sm = smem > 100 * 1024 ? 1 : 2;       // resident CTAs by shared memory
+    int grid = tiles < per_sm * sms ? tiles : per_sm * sms;
     disc_reward_kernel<<<grid, kStepThreads, smem, s>>>(params, L, F, H, d_in, n_rows, offset, reward, returns, masks, gamma, has_returns);
     count_launches(1);
     SG_CUDA(cudaGetLastError());
@@ -798,9 +850,9 @@ static int relabel_from_raw(const float* raw, const float* masks, float* rewards
     float* bmean = (float*)(ws + w.bmean);
     float* bvar = (float*)(ws + w.bvar);
     double* scale = (double*)(ws + w.scale);
-    relabel_scan_kernel<<<(N + 127) / 128, 128, 0, s>>>(raw, masks, ret_all, disc_returns, T, N, (float)gamma, has_returns);
+    relabel_scan_kernel<<<(N + 31) / 32, 256, 0, s>>>(raw, masks, ret_all, disc_returns, T, N, (float)gamma, has_returns);
     relabel_moments_kernel<<<(T + 127) / 128, 128, 0, s>>>(ret_all, T, N, bmean, bvar, mean_returns);
-    relabel_rms_kernel<<<1, 32, 0, s>>>(bmean, bvar, T, N, rms_state, scale);
+    relabel_rms_kernel<<<1, 256, 0, s>>>(bmean, bvar, T, N, rms_state, scale);
     long long total = (long long)T * N;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 1184) blocks = 1184;

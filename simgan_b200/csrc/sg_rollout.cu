@@ -67,6 +67,100 @@ __global__ void __launch_bounds__(128) returns_scan_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Staged variant for narrow buffers (N small: too few env columns to hide the load latency of a serial
+// chain with thread-level prefetch).  One CTA per 32 columns; ALL 256 threads stream chunks of kTC steps of the
+// four input arrays into double-buffered shared memory with cp.async (coalesced 128-byte row segments) while
+// the first `cols` threads walk the recurrence out of shared memory; results are written back coalesced.
+// Same arithmetic, same order: bit-identical to returns_scan_kernel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTC = 32;
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
+
+template <int MODE>
+__global__ void __launch_bounds__(256) returns_scan_staged_kernel(const float* __restrict__ rewards, float* __restrict__ vpred,
+                                                                  const float* __restrict__ masks,
+                                                                  const float* __restrict__ bad, float* __restrict__ ret,
+                                                                  const float* __restrict__ next_value, int T, int N,
+                                                                  float g, float gl) {
+    constexpr bool GAE = (MODE <= 1), PROPER = (MODE == 0 || MODE == 2);
+    __shared__ float sR[2][kTC][32], sV[2][kTC][32], sM[2][kTC][32], sB[2][kTC][32], sO[kTC][32];
+    const int tid = threadIdx.x;
+    const int n0 = blockIdx.x * 32;
+    const int cols = min(32, N - n0);
+    const int nchunks = (T + kTC - 1) / kTC;
+    // chunk k covers steps t in [T - (k+1)*kTC, T - k*kTC) (clipped at 0); slot tt <-> t = tbase + tt
+    auto issue = [&](int k) {
+        const int b = k & 1;
+        const int tbase = T - (k + 1) * kTC;
+        for (int e = tid; e < kTC * 32; e += 256) {
+            const int tt = e >> 5, c = e & 31;
+            const int t = tbase + tt;
+            if (c < cols && t >= 0) {
+                const size_t i0 = (size_t)t * N + n0 + c, i1 = (size_t)(t + 1) * N + n0 + c;
+                cp_async4(&sR[b][tt][c], rewards + i0);
+                cp_async4(&sV[b][tt][c], vpred + i0);
+                cp_async4(&sM[b][tt][c], masks + i1);
+                if (PROPER) cp_async4(&sB[b][tt][c], bad + i1);
+            }
+        }
+        cp_async_commit();
+    };
+    float carry = 0.f, v_next = 0.f;
+    if (tid < cols) {
+        const float nv = next_value[n0 + tid];
+        v_next = nv;
+        if (GAE) { vpred[(size_t)T * N + n0 + tid] = nv; carry = 0.f; }
+        else { ret[(size_t)T * N + n0 + tid] = nv; carry = nv; }
+    }
+    issue(0);
+    for (int k = 0; k < nchunks; ++k) {
+        if (k + 1 < nchunks) { issue(k + 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const int b = k & 1;
+        const int tbase = T - (k + 1) * kTC;
+        if (tid < cols) {
+            const int c = tid;
+#pragma unroll 4
+            for (int tt = kTC - 1; tt >= 0; --tt) {
+                if (tbase + tt < 0) break;
+                const float r = sR[b][tt][c], v = sV[b][tt][c], m = sM[b][tt][c];
+                const float bb = PROPER ? sB[b][tt][c] : 1.f;
+                float out;
+                if (GAE) {
+                    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, v_next), m)), v);
+                    carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m), carry));
+                    if (PROPER) carry = __fmul_rn(carry, bb);
+                    out = __fadd_rn(carry, v);
+                    v_next = v;
+                } else if (PROPER) {
+                    const float a = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(carry, g), m), r), bb);
+                    out = __fadd_rn(a, __fmul_rn(__fsub_rn(1.f, bb), v));
+                    carry = out;
+                } else {
+                    out = __fadd_rn(__fmul_rn(__fmul_rn(carry, g), m), r);
+                    carry = out;
+                }
+                sO[tt][c] = out;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < kTC * 32; e += 256) {
+            const int tt = e >> 5, c = e & 31;
+            const int t = tbase + tt;
+            if (c < cols && t >= 0) ret[(size_t)t * N + n0 + c] = sO[tt][c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // advantage statistics: mean and unbiased std of (returns - value_preds)[:S]  (A2C/algo/ppo.py:66-68)
 // fp64 accumulation; stage 1 = per-CTA partial (sum, sumsq), stage 2 = one CTA finalises.
 // ------------------------------------------------------------------------------------------------
@@ -191,6 +285,20 @@ int sg_compute_returns(const float* rewards, float* value_preds, const float* ma
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     const int threads = 128, blocks = (N + threads - 1) / threads;
     const int mode = use_gae ? (use_proper_time_limits ? 0 : 1) : (use_proper_time_limits ? 2 : 3);
+    if (N > 0) {
+        // the serial chain cannot hide its own loads -> staged shared-memory pipeline (any N; the per-thread
+        // prefetch kernel below is kept as the simple reference implementation)
+        const int sb = (N + 31) / 32;
+        switch (mode) {
+            case 0: returns_scan_staged_kernel<0><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+            case 1: returns_scan_staged_kernel<1><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+            case 2: returns_scan_staged_kernel<2><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+            default: returns_scan_staged_kernel<3><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        }
+        count_launches(1);
+        SG_CUDA(cudaGetLastError());
+        return SG_OK;
+    }
     switch (mode) {
         case 0: returns_scan_kernel<0><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
         case 1: returns_scan_kernel<1><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
