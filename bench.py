@@ -314,7 +314,7 @@ def run_cuda(args):
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     roof = None
     if dom is not None:
-        per_launch = {"ppo_update": (work["ppo_flops"], work["ppo_bytes"], 1),
+        per_launch = {"ppo_update": (work["ppo_flops"], work["ppo_bytes"], HYPER["ppo_epoch"]),     # one launch per epoch
                       "disc_update": (work["disc_flops"], work["disc_bytes"], HYPER["gail_epoch"]),
                       "disc_relabel": (work["relabel_flops"], work["relabel_bytes"], 1),
                       "compute_returns": (0, work["gae_bytes"], 1)}[dom]
@@ -331,7 +331,7 @@ def run_cuda(args):
             ach = fl / nl / t_s / 1e12
             roof = dict(bound="tensor", achieved=ach, peak=tc_peak, unit="TFLOP/s", frac=ach / tc_peak, traffic=traffic,
                         hbm_achieved_gbs=by / nl / t_s / 1e9, hbm_peak_gbs=hbm_peak)
-        steps_in_launch = {"ppo_update": HYPER["ppo_epoch"] * HYPER["num_mini_batch"], "disc_update": w.n_disc_batches,
+        steps_in_launch = {"ppo_update": HYPER["num_mini_batch"], "disc_update": w.n_disc_batches,
                            "disc_relabel": 1, "compute_returns": 1}[dom]
         roof.update(kernel=dom, peak_source=peak_src, share_of_step=kernels[dom]["ms_per_step"] / ms_per_step,
                     algorithmic_bytes_per_launch=by / nl, algorithmic_flops_per_launch=fl / nl,

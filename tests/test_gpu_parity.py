@@ -409,3 +409,135 @@ def test_full_update_phase_dropin(case):
     assert abs(out[2] - ref[2]) <= 1e-4 * abs(ref[2])
     rs.after_update()
     assert torch.equal(rs.obs[0], rs.obs[-1])
+
+
+# ------------------------------------------------------------------------------ full BASELINE sizes (cfg 2)
+def _cfg2_workload(seed=3):
+    """T=2048, N=16 Hopper sizes: synthetic rollout from the oracle's generator + the real expert rows."""
+    import os
+    from golden_util import GOLDEN_DIR
+    torch.manual_seed(seed)
+    p = orc.init_policy(14, 64, 7)
+    d = orc.init_disc(25, 100)
+    expert = torch.from_numpy(np.load(os.path.join(GOLDEN_DIR, "hopper_expert_sas_f32.npy")))
+    buf = orc.synth_rollout(2048, 16, 14, 7, 25, p, seed=seed, feat_bank=expert)
+    return p, d, expert, buf
+
+
+def test_full_size_disc_steps_and_relabel_vs_oracle():
+    """cfg 2 sizes: the first 6 discriminator minibatches of an epoch step by step, then the whole-rollout relabel
+    (32 768 rows) and GAE, against the oracle run on the same streams."""
+    from torch.utils.data import DataLoader, TensorDataset
+    p, dpar, expert, buf = _cfg2_workload()
+    S, B, n = 2048 * 16, 128, 6
+    g = torch.Generator().manual_seed(5)
+    e_idx = torch.randperm(expert.shape[0], generator=g)[:n * B].view(n, B)
+    p_idx = torch.randperm(S, generator=g)[:n * B].view(n, B)
+    alpha = torch.rand(n, B, generator=g)
+    ora = orc.DiscOracle(dpar)
+    trace = []
+    ora.update_epoch(expert, buf, batch_size=B, replay=(list(e_idx), list(p_idx), [a.view(B, 1) for a in alpha]), trace=trace)
+    d = gu.make_disc(dpar, 25, 100)
+    rs = gu.make_storage(buf, 14, 7, 25)
+    loader = DataLoader(TensorDataset(expert.to(gu.DEV)), batch_size=B, shuffle=True, drop_last=True)
+    d.update_gail_dyn(loader, rs, replay=(e_idx, p_idx, alpha))
+    tr, tr_o = d.last_trace.double().numpy(), np.array(trace)
+    assert tr.shape == tr_o.shape == (n, 3)
+    assert np.all(np.abs(tr - tr_o) <= LOSS_RTOL * np.abs(tr_o)), np.abs(tr - tr_o) / np.abs(tr_o)
+    # relabel + GAE over the full buffer with the updated discriminator
+    o_rms = orc.RunningMeanStd(shape=())
+    r_sa = orc.alive_bonus_offset(buf["masks"], 2048, 16, 87.8)
+    orc.relabel_rewards(ora, o_rms, buf, 0.99, -r_sa)
+    nv = orc.policy_forward(p, buf["obs"][-1])[0]
+    orc.compute_returns(buf, nv, True, 0.99, 0.95, True)
+    rms = sg.RunningMeanStd(shape=())
+    d.relabel_rollout(rs, 0.99, -r_sa, rms)
+    rs.compute_returns(nv.to(gu.DEV), True, 0.99, 0.95, True)
+    ref = buf["rewards"]
+    assert float((rs.rewards.cpu() - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    assert abs(float(rms.var) - float(o_rms.var)) <= 1e-4 * float(o_rms.var) and float(rms.count) == float(o_rms.count)
+    ret_ref = buf["returns"][:-1]
+    assert float((rs.returns.cpu()[:-1] - ret_ref).abs().max()) <= 2e-4 * float(ret_ref.abs().max())
+    # size-independent property: GAE is exactly reproducible from the kernel's own rewards (bit-exact recurrence)
+    buf2 = {k: getattr(rs, k).cpu().clone() for k in buf}
+    orc.compute_returns(buf2, nv, True, 0.99, 0.95, True)
+    assert torch.equal(buf2["returns"][:-1], rs.returns.cpu()[:-1])
+
+
+def test_full_size_ppo_epoch_vs_oracle():
+    """cfg 2 sizes: one PPO epoch = 32 minibatches of 1024 rows, per-step losses and gradient norms vs the oracle."""
+    p, dpar, expert, buf = _cfg2_workload(seed=4)
+    buf["rewards"].copy_(torch.randn(2048, 16, 1, generator=torch.Generator().manual_seed(1)).clamp(-3, 3))
+    nv = orc.policy_forward(p, buf["obs"][-1])[0]
+    orc.compute_returns(buf, nv, True, 0.99, 0.95, True)
+    hyper = orc.PPOHyper(ppo_epoch=1, num_mini_batch=32)
+    ora = orc.PPOOracle(p, hyper)
+    perm = torch.randperm(2048 * 16, generator=torch.Generator().manual_seed(9))
+    trace = []
+    ora.update(buf, index_chunks=[[perm[i * 1024:(i + 1) * 1024] for i in range(32)]], trace=trace)
+    pol = gu.make_policy(p, 14, 64, 7)
+    agent = sg.PPO(pol, 0.2, 1, 32, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    rs = gu.make_storage(buf, 14, 7, 25)
+    agent.update(rs, permutations=perm.view(1, -1))
+    tr, tr_o = agent.last_trace.double().numpy(), np.array(trace)
+    scale = np.abs(tr_o).max(axis=0)
+    scale[1] = max(scale[1], 0.5)
+    assert np.all(np.abs(tr - tr_o) <= LOSS_RTOL * scale + 1e-6), np.abs(tr - tr_o).max(axis=0) / scale
+    pm, po = gu.policy_params(pol), ora.params()
+    for k in orc.POLICY_KEYS:
+        assert torch.allclose(pm[k], po[k].reshape(-1), rtol=1e-3, atol=2e-5), k
+
+
+# --------------------------------------------------------------------------------------------- edge cases
+def test_ragged_minibatch_tail_and_single_env():
+    """S not divisible by num_mini_batch (tail rows dropped like BatchSampler(drop_last=True)), rows-per-minibatch
+    not a multiple of the 8-row tile, a single env column."""
+    torch.manual_seed(0)
+    T, N, O, A, H = 37, 1, 5, 2, 16
+    p = orc.init_policy(O, H, A)
+    buf = orc.synth_rollout(T, N, O, A, 3, p, seed=2, ep_len=7.0)
+    nv = orc.policy_forward(p, buf["obs"][-1])[0]
+    orc.compute_returns(buf, nv, True, 0.99, 0.95, True)
+    hyper = orc.PPOHyper(ppo_epoch=2, num_mini_batch=5)              # 37 // 5 = 7 rows, 2 dropped per epoch
+    ora = orc.PPOOracle(p, hyper)
+    pol = gu.make_policy(p, O, H, A)
+    agent = sg.PPO(pol, 0.2, 2, 5, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    rs = gu.make_storage(buf, O, A, 3)
+    torch.manual_seed(42)
+    out_o = ora.update(buf)
+    torch.manual_seed(42)
+    out = agent.update(rs)
+    assert abs(out[0] - out_o[0]) <= 2e-4 * abs(out_o[0]) and abs(out[2] - out_o[2]) <= 1e-4 * abs(out_o[2])
+    assert agent.last_trace.shape == (10, 4)
+
+
+def test_num_mini_batch_larger_than_samples_raises():
+    pol = gu.make_policy(orc.init_policy(5, 16, 2), 5, 16, 2)
+    agent = sg.PPO(pol, 0.2, 1, 64, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    buf = orc.synth_rollout(4, 2, 5, 2, 3, orc.init_policy(5, 16, 2), seed=0)
+    rs = gu.make_storage(buf, 5, 2, 3)
+    with pytest.raises(AssertionError, match="PPO requires"):
+        agent.update(rs)
+
+
+def test_disc_epoch_bounded_by_shorter_stream_and_small_rollout():
+    """zip(expert_loader, rollout sampler) stops at the shorter side (gail.py:162-163); a rollout smaller than one
+    discriminator batch yields no step and the reference's division by n=0."""
+    from torch.utils.data import DataLoader, TensorDataset
+    torch.manual_seed(0)
+    dpar = orc.init_disc(9, 48)
+    expert = torch.randn(70, 9)
+    buf = orc.synth_rollout(25, 2, 4, 2, 9, orc.init_policy(4, 16, 2), seed=1)       # S = 50 -> 3 batches of 16
+    d = gu.make_disc(dpar, 9, 48)
+    rs = gu.make_storage(buf, 4, 2, 9)
+    loader = DataLoader(TensorDataset(expert.to(gu.DEV)), batch_size=16, shuffle=True, drop_last=True)   # 4 expert batches
+    ora = orc.DiscOracle(dpar)
+    torch.manual_seed(7)
+    out_o = ora.update_epoch(expert, buf, batch_size=16)
+    torch.manual_seed(7)
+    out = d.update_gail_dyn(loader, rs)
+    assert d.last_trace.shape[0] == 3
+    assert all(abs(a - b) <= LOSS_RTOL * abs(b) for a, b in zip(out, out_o))
+    loader_big = DataLoader(TensorDataset(expert.to(gu.DEV)), batch_size=64, shuffle=True, drop_last=True)
+    with pytest.raises(ZeroDivisionError):
+        d.update_gail_dyn(loader_big, rs)

@@ -223,3 +223,33 @@ def test_shard_bounds_partition(n, world):
         assert b == c and b > a
     sizes = [b - a for a, b in edges]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_expert_loaders_match_oracle_and_golden():
+    from golden_util import GOLDEN_DIR
+    path = os.path.join(GOLDEN_DIR, "mini_expert.pkl")
+    torch.manual_seed(0)
+    cols = sg.load_sas_wpast_from_pickle(path, downsample_freq=2, load_num_trajs=3)
+    after = torch.rand(2)
+    torch.manual_seed(0)
+    cols_o = orc.load_sas_wpast(path, downsample_freq=2, load_num_trajs=3)
+    assert torch.equal(torch.rand(2), after)                      # same generator consumption
+    assert len(cols) == len(cols_o) == 21
+    for a, b in zip(cols, cols_o):
+        assert np.array_equal(a, b)
+    merged = sg.select_and_merge_sas(cols)
+    assert np.array_equal(merged, np.load(os.path.join(GOLDEN_DIR, "mini_expert_merged.npy")))
+    # single-transition form used per env step by the caller (main_gail_dyn_ppo.py:220-226)
+    one = [c[5].tolist() for c in cols]
+    assert np.array_equal(sg.select_and_merge_sas(one), merged[5])
+    # longer history windows
+    m2 = sg.select_and_merge_sas(cols, s_idx=np.array([0, 2]), a_idx=np.array([0, 1]))
+    assert np.array_equal(m2, orc.merge_sas(cols_o, s_idx=(0, 2), a_idx=(0, 1)))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (GPU box)")
+def test_expert_tensor_reproduces_the_committed_fixture():
+    from golden_util import GOLDEN_DIR
+    torch.manual_seed(0)
+    x = sg.expert_tensor(os.path.join(ref_shim.REF_ROOT, "hopper_new11_deform_n200_3.pkl"), "cpu")
+    assert np.array_equal(x.numpy(), np.load(os.path.join(GOLDEN_DIR, "hopper_expert_sas_f32.npy")))
