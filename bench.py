@@ -173,6 +173,51 @@ class Workload(object):
         return tuple(dl) + tuple(pl)
 
 
+def fake_env_collection(w):
+    """Collection loop (HOT LOOP A, main_gail_dyn_ppo.py:209-236) against a FAKE vec-env: the per-step env outputs
+    are pre-generated NumPy arrays on the host (PyBullet / gym are not installed; no physics is simulated), so this
+    measures only the feed boundary: staging + H2D + insert/act kernel + D2H + the per-step sync."""
+    import simgan_b200 as sg
+    c, r = w.c, w.rollouts
+    T, N = c["T"], c["N"]
+    steps = min(T, 512)
+    obs = w.host["obs"].numpy(); feat = w.host["obs_feat"].numpy()
+    done = (w.host["masks"].numpy()[:, :, 0] == 0); bad = (w.host["bad_masks"].numpy()[:, :, 0] == 0)
+    rew = np.zeros(N, dtype=np.float32)
+    feeder = sg.RolloutFeeder(w.policy, r)
+    feeder.begin()
+    for t in range(8):
+        feeder.step(obs[t + 1], rew, done[t + 1], bad[t + 1], feat[t + 1])
+    torch.cuda.synchronize()
+    r.step = 0
+    t0 = time.perf_counter()
+    feeder.begin()
+    for t in range(steps):
+        feeder.step(obs[t + 1], rew, done[t + 1], bad[t + 1], feat[t + 1])
+    torch.cuda.synchronize()
+    fused = time.perf_counter() - t0
+    # the same loop through the drop-in calls (Policy.act + RolloutStorage.insert), as an unmodified caller would run it
+    r.step = 0
+    t0 = time.perf_counter()
+    for t in range(steps):
+        with torch.no_grad():
+            value, action, logp, hxs = w.policy.act(r.obs[t], r.recurrent_hidden_states[t], r.masks[t])
+        action.cpu().numpy()
+        o = torch.from_numpy(obs[t + 1]).float().to(w.device)
+        m = torch.from_numpy(1.0 - done[t + 1].astype(np.float32)).unsqueeze(1)
+        b = torch.from_numpy(1.0 - bad[t + 1].astype(np.float32)).unsqueeze(1)
+        r.insert(o, hxs, action, logp, value, torch.from_numpy(rew).unsqueeze(1), m, b, torch.from_numpy(feat[t + 1]))
+    torch.cuda.synchronize()
+    dropin = time.perf_counter() - t0
+    r.step = 0
+    w.upload()
+    torch.cuda.synchronize()
+    return {"value": steps * N / fused, "unit": "env steps/s", "us_per_vec_step": 1e6 * fused / steps,
+            "dropin_act_insert_value": steps * N / dropin, "dropin_us_per_vec_step": 1e6 * dropin / steps,
+            "num_envs": N, "vec_steps_timed": steps,
+            "note": "FAKE vec-env (pre-generated host arrays, no PyBullet physics): feed-boundary cost only"}
+
+
 def sample_clocks_start():
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -296,6 +341,7 @@ def run_cuda(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    env_steps = fake_env_collection(w) if world == 1 else None
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -358,6 +404,7 @@ def run_cuda(args):
                 "d2h_bytes_per_step": 4 * (4 * HYPER["ppo_epoch"] * HYPER["num_mini_batch"] + 3 * HYPER["gail_epoch"] * w.n_disc_batches) + 24 + 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "env_steps": env_steps,
         "kernels": kernels, "roofline": roof, "clocks": clocks,
         "losses_last_step": [float(x) for x in losses],
         "phase_cycles_last_launch": {"ppo": dict(zip(["image", "tile", "bar1", "reduce_ssq", "bar2", "clip_adam", "bar3"],

@@ -89,6 +89,22 @@ int sg_policy_forward(const float* params, int obs_dim, int hidden, int act_dim,
                       const float* noise, const float* actions_in, float* value, float* action, float* logp,
                       float* entropy, void* stream);
 
+/* Rollout feed step = the body of the collection loop (A2C/main_gail_dyn_ppo.py:209-236) in ONE launch:
+ * RolloutStorage.insert (A2C/storage.py:70-84) of the staged env outputs of step `step` + Policy.act
+ * (A2C/model.py:89-101) on the new observations.
+ *   staged     device copy of ONE packed block [obs' (N,O) | sas_feat (N,F) | reward (N) | mask (N) | bad_mask (N)]
+ *              (sg_rollout_stage_floats floats; the host fills a pinned twin and issues one async H2D copy)
+ *   noise      (N,A) standard normal draws or NULL for the deterministic mode
+ *   step       slot being completed (0..T-1), or -1 at the start of a rollout (no insert, act on obs[0])
+ *   effects    obs/obs_feat/masks/bad_masks/hxs[step+1], rewards[step]  <- staged
+ *              value_preds[step+1]; actions/action_log_probs[step+1] (when step+1 < T)  <- act(obs[step+1])
+ *              action_out (N,A): the actions for the host envs (one async D2H copy) */
+int64_t sg_rollout_stage_floats(int obs_dim, int feat_dim, int N);
+int sg_rollout_feed(const float* params, int obs_dim, int hidden, int act_dim, int feat_dim, int N, int T, int step,
+                    const float* staged, const float* noise, float* obs, float* obs_feat, float* hxs, float* rewards,
+                    float* value_preds, float* action_log_probs, float* actions, float* masks, float* bad_masks,
+                    float* action_out, void* stream);
+
 /* ---- PPO ----------------------------------------------------------------------------------- */
 typedef struct sg_ppo_config {
     int obs_dim, hidden, act_dim;

@@ -269,6 +269,92 @@ __global__ void __launch_bounds__(kStepThreads) policy_forward_kernel(const floa
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Rollout feed step (A2C/main_gail_dyn_ppo.py:209-236 + A2C/envs.py:199-210 + A2C/storage.py:70-84), one launch
+// per environment step:
+//   insert   the staged env outputs of step `step` (obs', sas_feat, reward, mask, bad_mask; one packed block that
+//            arrived with ONE async H2D copy) go to slot step+1 (obs, obs_feat, masks, bad_masks, hxs) and slot
+//            step (rewards); actions / log-probs / values of slot `step` were written when they were computed.
+//   act      Policy.act on the new observations -> value_preds[step+1], actions[step+1], action_log_probs[step+1]
+//            (when step+1 < T) and the action block the host envs read back with ONE async D2H copy.
+// step = -1 is the start of a rollout: no insert, act on obs[0].
+// ------------------------------------------------------------------------------------------------
+struct FeedArgs {
+    const float* params;
+    PolicyLayout L;
+    int O, H, A, F, N, T, step;
+    const float *staged, *noise;
+    float *obs, *obs_feat, *hxs, *rewards, *value_preds, *action_log_probs, *actions, *masks, *bad_masks, *action_out;
+};
+
+template <int R>
+__global__ void __launch_bounds__(kStepThreads) rollout_feed_kernel(FeedArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    PolicyTile<R> T;
+    T.carve(smem, a.O, a.H, a.A);
+    const int tid = threadIdx.x;
+    const int O = a.O, A = a.A, F = a.F, N = a.N;
+    const int slot = a.step + 1;                         // slot the new observations go to / are acted on
+    const float* st_obs = a.staged;                      // [N*O | N*F | N | N | N]
+    const float* st_feat = st_obs + (size_t)N * O;
+    const float* st_rew = st_feat + (size_t)N * F;
+    const float* st_mask = st_rew + N;
+    const float* st_bad = st_mask + N;
+    const bool do_act = slot < a.T || a.step < 0 || true;    // value of obs[T] doubles as next_value
+    for (int tile = blockIdx.x; tile * R < N; tile += gridDim.x) {
+        const int row0 = tile * R;
+        const float* src_obs = a.step >= 0 ? st_obs : a.obs;       // step -1: act on obs[0] already in the buffer
+        for (int e = tid; e < R * T.ldo; e += kStepThreads) {
+            const int r = e / T.ldo, k = e - r * T.ldo;
+            const int row = row0 + r;
+            float x = 0.f;
+            if (row < N && k < O) {
+                x = src_obs[(size_t)row * O + k];
+                if (a.step >= 0) a.obs[((size_t)slot * N + row) * O + k] = x;
+            }
+            T.X[e] = x;
+        }
+        if (a.step >= 0) {
+            for (int e = tid; e < R * F; e += kStepThreads) {
+                const int r = e / F, k = e - r * F;
+                const int row = row0 + r;
+                if (row < N) a.obs_feat[((size_t)slot * N + row) * F + k] = st_feat[(size_t)row * F + k];
+            }
+            if (tid < R && row0 + tid < N) {
+                const int row = row0 + tid;
+                a.rewards[(size_t)a.step * N + row] = st_rew[row];
+                a.masks[(size_t)slot * N + row] = st_mask[row];
+                a.bad_masks[(size_t)slot * N + row] = st_bad[row];
+                a.hxs[(size_t)slot * N + row] = 0.f;                   // non-recurrent policies carry zeros (storage.py:78)
+            }
+        }
+        __syncthreads();
+        if (do_act) {
+            policy_tile_forward<R>(a.params, a.L, O, a.H, A, T, tid);
+            for (int e = tid; e < R * A; e += kStepThreads) {
+                const int r = e / A, k = e - r * A;
+                const int row = row0 + r;
+                float act = 0.f;
+                if (row < N) {
+                    const float mu = T.MU[r * T.lda + k];
+                    act = a.noise ? __fadd_rn(__fmul_rn(a.noise[(size_t)row * A + k], expf(ld_cg(a.params + a.L.ls + k))), mu) : mu;
+                    a.action_out[(size_t)row * A + k] = act;
+                    if (slot < a.T) a.actions[((size_t)slot * N + row) * A + k] = act;
+                }
+                T.ACT[r * T.lda + k] = act;
+            }
+            __syncthreads();
+            if (tid < R && row0 + tid < N) {
+                const int row = row0 + tid;
+                a.value_preds[(size_t)slot * N + row] = T.VAL[tid];
+                if (slot < a.T)
+                    a.action_log_probs[(size_t)slot * N + row] = gaussian_logp_row(T.MU + tid * T.lda, T.ACT + tid * T.lda, a.params + a.L.ls, A);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace sg
 
 using namespace sg;
@@ -380,6 +466,38 @@ int sg_policy_forward(const float* params, int obs_dim, int hidden, int act_dim,
     int grid = tiles < 1184 ? tiles : 1184;
     policy_forward_kernel<kRows><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(params, L, obs_dim, hidden, act_dim, obs, B,
                                                                                      noise, actions_in, value, action, logp, entropy);
+    count_launches(1);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
+}
+
+int64_t sg_rollout_stage_floats(int obs_dim, int feat_dim, int N) { return (int64_t)N * (obs_dim + feat_dim + 3); }
+
+int sg_rollout_feed(const float* params, int obs_dim, int hidden, int act_dim, int feat_dim, int N, int T, int step,
+                    const float* staged, const float* noise, float* obs, float* obs_feat, float* hxs, float* rewards,
+                    float* value_preds, float* action_log_probs, float* actions, float* masks, float* bad_masks,
+                    float* action_out, void* stream) {
+    SG_REQUIRE(params && obs && obs_feat && hxs && rewards && value_preds && action_log_probs && actions && masks && bad_masks &&
+                   action_out, "sg_rollout_feed: null pointer");
+    SG_REQUIRE(obs_dim > 0 && hidden > 0 && act_dim > 0 && feat_dim >= 0 && N > 0 && T > 0, "sg_rollout_feed: non-positive sizes");
+    SG_REQUIRE(step >= -1 && step < T, "sg_rollout_feed: step %d outside [-1,%d)", step, T);
+    SG_REQUIRE(step < 0 || staged, "sg_rollout_feed: staged block required for step >= 0");
+    FeedArgs a;
+    a.params = params; a.L = make_policy_layout(obs_dim, hidden, act_dim);
+    a.O = obs_dim; a.H = hidden; a.A = act_dim; a.F = feat_dim; a.N = N; a.T = T; a.step = step;
+    a.staged = staged; a.noise = noise;
+    a.obs = obs; a.obs_feat = obs_feat; a.hxs = hxs; a.rewards = rewards; a.value_preds = value_preds;
+    a.action_log_probs = action_log_probs; a.actions = actions; a.masks = masks; a.bad_masks = bad_masks; a.action_out = action_out;
+    const size_t smem = (size_t)PolicyTile<kRows>::floats(obs_dim, hidden, act_dim) * sizeof(float);
+    SG_REQUIRE(smem <= 200 * 1024, "sg_rollout_feed: tile needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        SG_CUDA(cudaFuncSetAttribute(rollout_feed_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int tiles = (N + kRows - 1) / kRows;
+    int grid = tiles < 1184 ? tiles : 1184;
+    rollout_feed_kernel<kRows><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(a);
     count_launches(1);
     SG_CUDA(cudaGetLastError());
     return SG_OK;

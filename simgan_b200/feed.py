@@ -1,0 +1,75 @@
+"""Rollout feed boundary: host vec-env  <->  device rollout buffer, one copy each way and ONE kernel per env step.
+
+The reference's collection loop (third_party/a2c_ppo_acktr/main_gail_dyn_ppo.py:209-236) issues per step a policy
+forward (6 GEMMs + sampling), ``actions.cpu().numpy()`` (third_party/a2c_ppo_acktr/envs.py:199-205), three
+``torch.from_numpy(...).to(device)`` / ``Tensor(...)`` uploads (envs.py:207-210, main_gail_dyn_ppo.py:230-236) and nine
+``copy_`` calls (storage.py:70-84).  ``RolloutFeeder`` keeps the same data flow -- PyBullet envs stay on the host --
+but packs a step's env outputs into one pinned block (one async H2D copy), runs ``sg_rollout_feed`` (insert + act in
+one launch) and reads the next actions back with one async D2H copy.  ``Policy.act`` + ``RolloutStorage.insert`` remain
+available and produce bit-identical buffers (tests/test_gpu_parity.py::test_rollout_feeder_matches_act_insert).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class RolloutFeeder(object):
+    def __init__(self, actor_critic, rollouts):
+        self.ac, self.rs = actor_critic, rollouts
+        if not rollouts.obs.is_cuda:
+            raise _lib.SgError("RolloutFeeder needs the rollout buffer on a CUDA device; there is no CPU fallback")
+        self.dev = rollouts.obs.device
+        self.T, self.N = rollouts.rewards.shape[:2]
+        self.O, self.F, self.A = rollouts.obs.shape[-1], rollouts.obs_feat.shape[-1], rollouts.actions.shape[-1]
+        n = int(_lib.lib().sg_rollout_stage_floats(self.O, self.F, self.N))
+        self.stage_host = torch.empty(n, dtype=torch.float32).pin_memory()
+        self.stage_dev = torch.empty(n, dtype=torch.float32, device=self.dev)
+        N, O, F = self.N, self.O, self.F
+        h = self.stage_host.numpy()
+        o = 0
+        self.h_obs = h[o:o + N * O].reshape(N, O); o += N * O
+        self.h_feat = h[o:o + N * F].reshape(N, F); o += N * F
+        self.h_reward = h[o:o + N]; o += N
+        self.h_mask = h[o:o + N]; o += N
+        self.h_bad = h[o:o + N]
+        self.action_dev = torch.empty(N, self.A, dtype=torch.float32, device=self.dev)
+        self.action_host = torch.empty(N, self.A, dtype=torch.float32).pin_memory()
+        self.done_event = torch.cuda.Event()
+
+    def _launch(self, step, deterministic):
+        rs, ac = self.rs, self.ac
+        flat = ac.flat_params()
+        noise = None if deterministic else torch.randn(self.N, self.A, device=self.dev, dtype=torch.float32)
+        rc = _lib.lib().sg_rollout_feed(
+            _lib.ptr(flat), self.O, ac.hidden_size, self.A, self.F, self.N, self.T, step,
+            _lib.ptr(self.stage_dev) if step >= 0 else None, _lib.ptr(noise), _lib.ptr(rs.obs), _lib.ptr(rs.obs_feat),
+            _lib.ptr(rs.recurrent_hidden_states), _lib.ptr(rs.rewards), _lib.ptr(rs.value_preds),
+            _lib.ptr(rs.action_log_probs), _lib.ptr(rs.actions), _lib.ptr(rs.masks), _lib.ptr(rs.bad_masks),
+            _lib.ptr(self.action_dev), _lib.current_stream())
+        _lib.check(rc, "sg_rollout_feed")
+        self.action_host.copy_(self.action_dev, non_blocking=True)
+        self.done_event.record()
+        self.done_event.synchronize()           # the host envs need the actions: the one sync of the step
+        return self.action_host.numpy()
+
+    def begin(self, deterministic=False):
+        """Start of a rollout: act on ``rollouts.obs[0]`` (set by ``envs.reset()`` / ``after_update``).
+        Returns the (N, A) float32 action array for the first ``envs.step``."""
+        self.rs.step = 0
+        return self._launch(-1, deterministic)
+
+    def step(self, obs, reward, done, bad_transition, sas_feat, deterministic=False):
+        """One env step: ``obs (N,O)``, ``reward (N,)`` or ``(N,1)``, ``done (N,)`` bools, ``bad_transition (N,)`` bools
+        (``'bad_transition' in info``), ``sas_feat (N,F)`` -- NumPy arrays straight from the vec-env.  Inserts them
+        into slot ``rollouts.step`` and returns the actions for the next ``envs.step``."""
+        s = self.rs.step
+        np.copyto(self.h_obs, obs, casting="same_kind")
+        np.copyto(self.h_feat, sas_feat, casting="same_kind")
+        np.copyto(self.h_reward, np.asarray(reward).reshape(-1), casting="same_kind")
+        np.subtract(1.0, np.asarray(done, dtype=np.float32), out=self.h_mask)          # masks = 0 where done
+        np.subtract(1.0, np.asarray(bad_transition, dtype=np.float32), out=self.h_bad)
+        self.stage_dev.copy_(self.stage_host, non_blocking=True)
+        out = self._launch(s, deterministic)
+        self.rs.step = (s + 1) % self.T
+        return out

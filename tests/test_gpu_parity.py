@@ -541,3 +541,49 @@ def test_disc_epoch_bounded_by_shorter_stream_and_small_rollout():
     loader_big = DataLoader(TensorDataset(expert.to(gu.DEV)), batch_size=64, shuffle=True, drop_last=True)
     with pytest.raises(ZeroDivisionError):
         d.update_gail_dyn(loader_big, rs)
+
+
+# ----------------------------------------------------------------------------------------- rollout feed step
+def test_rollout_feeder_matches_act_insert():
+    """One fused launch per env step (RolloutFeeder) == Policy.act + RolloutStorage.insert of the reference-shaped
+    loop (main_gail_dyn_ppo.py:209-236), bit for bit, including wrap-around and the value of the last observation."""
+    from oracle.ref_shim import BoxSpace
+    T, N, O, A, F, H = 6, 5, 14, 7, 25, 64
+    torch.manual_seed(0)
+    p = orc.init_policy(O, H, A)
+    pol = gu.make_policy(p, O, H, A)
+    rs_a = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, F); rs_a.to(gu.DEV)
+    rs_b = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, F); rs_b.to(gu.DEV)
+    rng = np.random.RandomState(0)
+    obs0 = rng.randn(N, O).astype(np.float32)
+    rs_a.obs[0].copy_(torch.from_numpy(obs0)); rs_b.obs[0].copy_(torch.from_numpy(obs0))
+    env = [(rng.randn(N, O).astype(np.float32), rng.randn(N).astype(np.float32), rng.rand(N) < 0.3, rng.rand(N) < 0.1,
+            rng.randn(N, F)) for _ in range(T)]
+    # reference-shaped loop
+    torch.cuda.manual_seed(11)
+    acts_a = []
+    for step in range(T):
+        with torch.no_grad():
+            value, action, logp, hxs = pol.act(rs_a.obs[step], rs_a.recurrent_hidden_states[step], rs_a.masks[step])
+        acts_a.append(action.cpu().numpy())
+        obs, rew, done, bad, feat = env[step]
+        masks = torch.tensor([[0.0] if d else [1.0] for d in done])
+        bad_masks = torch.tensor([[0.0] if b else [1.0] for b in bad])
+        rs_a.insert(torch.from_numpy(obs).to(gu.DEV), hxs, action, logp, value, torch.from_numpy(rew).unsqueeze(1),
+                    masks, bad_masks, torch.Tensor(feat))
+    # fused feed
+    torch.cuda.manual_seed(11)
+    feeder = sg.RolloutFeeder(pol, rs_b)
+    acts_b = [feeder.begin().copy()]
+    for step in range(T):
+        obs, rew, done, bad, feat = env[step]
+        acts_b.append(feeder.step(obs, rew, done, bad, feat).copy())
+    for a, b in zip(acts_a, acts_b):
+        assert np.array_equal(a, b)
+    for k in ("obs", "obs_feat", "recurrent_hidden_states", "rewards", "actions", "action_log_probs", "masks", "bad_masks"):
+        assert torch.equal(getattr(rs_a, k), getattr(rs_b, k)), k
+    assert torch.equal(rs_a.value_preds[:-1], rs_b.value_preds[:-1])
+    with torch.no_grad():
+        nv = pol.get_value(rs_a.obs[-1], None, None)
+    assert torch.equal(rs_b.value_preds[-1], nv)             # slot T already holds next_value
+    assert rs_b.step == rs_a.step == 0
