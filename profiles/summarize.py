@@ -97,7 +97,7 @@ def full(tag, rep):
         name = r[hdr.index("Kernel Name")]
         short = "ppo_update" if "ppo" in name else "disc_update" if "disc" in name else name.split("(")[0]
         out = ["# %s: ncu --set full capture of `%s`" % (tag, name), "",
-               "Command: `ncu --set full --clock-control none --import-source on -k regex:persistent -s 4 -c 2 "
+               "Command: `ncu --set full --clock-control none --import-source on -k regex:\"disc_reg|ppo_persistent\" -s 4 -c 2 "
                "python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (cfg2 workload).", "", "| metric | value | unit |", "|---|---:|---|"]
         vals = {}
         for m in RAW_METRICS:
