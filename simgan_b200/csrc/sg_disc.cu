@@ -645,6 +645,10 @@ static int disc_grid(const sg_disc_config* c, int* sms_out) {
     if (sms_out) *sms_out = sms;
     int tiles = disc_tiles(c);
     int g = tiles < sms ? tiles : sms;
+    // never fewer than 64 CTAs: CTAs without a tile skip phase A but still own a slice of the reduce / Adam phases,
+    // which keeps those phases on the narrow one-parameter-per-thread path for small (or sharded) minibatches
+    const int gmin = sms < 64 ? sms : 64;
+    if (g < gmin) g = gmin;
     return g < 1 ? 1 : g;
 }
 constexpr size_t kDiscMaxDynSmem = 227 * 1024 - 1024;

@@ -781,6 +781,10 @@ static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
     if (sm_count_out) *sm_count_out = sms;
     int tiles = ppo_tiles(c);
     int g = tiles < sms ? tiles : sms;
+    // never fewer than 64 CTAs: CTAs without a tile skip phase A but still own a slice of the reduce / Adam phases,
+    // which keeps those phases on the narrow one-parameter-per-thread path for small (or sharded) minibatches
+    const int gmin = sms < 64 ? sms : 64;
+    if (g < gmin) g = gmin;
     return g < 1 ? 1 : g;
 }
 

@@ -91,7 +91,7 @@ def test_data_parallel_matches_single_gpu(case, transport, tmp_path):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
-    world = 2
+    world = min(n, int(os.environ.get("SG_DP_WORLD", "2")))
     out = str(tmp_path / "ok")
     mp.spawn(_worker, args=(world, _free_port(), case, out, transport), nprocs=world, join=True)
     assert os.path.exists(out)
