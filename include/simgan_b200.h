@@ -148,6 +148,25 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
                   const float* adv_stats, const int32_t* perm, const float* step_size, const float* bc2_sqrt,
                   float* trace, void* workspace, sg_allreduce_fn allreduce_cb, void* allreduce_user, void* stream);
 
+/* ---- SplitPolicy (A2C/model_split.py:39-95, 157-238; what the shipped train_*.sh scripts use) ---------------- */
+/* Flat layout: offsets[22] in nn.Module.parameters() order of SplitPolicy (base.actor_contact.{0,2}.{weight,bias},
+ * base.actor_actuator.{0,2}.*, base.critic_full.{0,2,4}.*, dist.{contact_mean, actuator_mean, contact_logstd,
+ * actuator_logstd}.{weight,bias}); inside the vector every actor's mean and log-std heads are adjacent so that
+ * they form one (2*n, H) matrix.  Returns the padded total length. */
+#define SG_SPLIT_SEGMENTS 22
+int sg_split_layout(int obs_dim, int hidden, int num_feet, int* offsets);
+/* SplitPolicy.act / get_value / evaluate_actions (A2C/model_split.py:69-95); as sg_policy_forward, except that the
+ * entropy is state dependent: entropy_rows (B) receives the per-row entropies (their mean is dist_entropy). */
+int sg_split_forward(const float* params, int obs_dim, int hidden, int num_feet, const float* obs, int B, const float* noise,
+                     const float* actions_in, float* value, float* action, float* logp, float* entropy_rows, void* stream);
+/* PPO.update (A2C/algo/ppo.py:65-157) for a SplitPolicy: arguments as sg_ppo_update (cfg->act_dim = 7*num_feet;
+ * persistent kernel only: cfg->mode and cfg->dp_ctx must be 0 / NULL); trace columns as sg_ppo_update. */
+int64_t sg_split_ppo_workspace_bytes(const sg_ppo_config* cfg);
+int sg_split_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float* adam_v, const float* obs,
+                        const float* actions, const float* value_preds, const float* returns, const float* old_logp,
+                        const float* adv_stats, const int32_t* perm, const float* step_size, const float* bc2_sqrt,
+                        float* trace, void* workspace, void* stream);
+
 /* ---- data-parallel exchange over NVLink peer memory (no reference counterpart) ---------- */
 /* One context per optimizer per rank.  sg_dp_create allocates this rank's exchange buffer (room for a flat
  * gradient of max_floats); the 64-byte CUDA IPC handle from sg_dp_local_handle is exchanged between the ranks

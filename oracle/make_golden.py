@@ -122,6 +122,53 @@ def run_case(ref, name, seed, T, N, O, A, H, F_, HD, expert, gail_epoch, gail_ba
           g["ppo_losses"], g["disc_losses"][-1])
 
 
+def run_split_case(ref, name, seed, T, N, O, H, num_feet, ppo_epoch, nmb, entropy_coef, ep_len):
+    """PPO.update of the REAL reference on its SplitPolicy (third_party/a2c_ppo_acktr/model_split.py), the policy
+    class the shipped train_*.sh scripts use (--use-split-pi): inputs, index stream, losses and parameters after."""
+    torch.set_num_threads(1)
+    torch.manual_seed(seed)
+    A = 7 * num_feet
+    pol = ref.model_split.SplitPolicy((O,), ref_shim.BoxSpace(A), base_kwargs={"hidden_size": H, "num_feet": num_feet})
+    agent = ref.ppo.PPO(pol, 0.2, ppo_epoch, nmb, 0.5, entropy_coef, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    g = {"meta_dims": np.array([T, N, O, A, H, num_feet, ppo_epoch, nmb, seed], dtype=np.int64),
+         "entropy_coef": np.array(entropy_coef, dtype=np.float64)}
+    p0 = {k: v.detach().clone() for k, v in zip(orc.SPLIT_KEYS, pol.parameters())}
+    for k, v in p0.items():
+        g["sp0_" + k] = v.numpy()
+    # rollout contents: obs ~ N(0,1), masks ~ Bernoulli, actions/values/log-probs from the policy's own act()
+    gen = torch.Generator().manual_seed(1000 + seed)
+    buf = orc.new_buffer(T, N, O, A, 3)
+    buf["obs"].copy_(torch.randn(T + 1, N, O, generator=gen))
+    buf["masks"].copy_((torch.rand(T + 1, N, 1, generator=gen) >= 1.0 / ep_len).float())
+    noise = torch.randn(T * N, A, generator=gen)
+    v, a, lp = orc.split_act(p0, buf["obs"][:-1].reshape(T * N, O), noise=noise)
+    buf["value_preds"][:-1] = v.view(T, N, 1)
+    buf["actions"].copy_(a.view(T, N, A))
+    buf["action_log_probs"].copy_(lp.view(T, N, 1))
+    buf["rewards"].copy_(torch.randn(T, N, 1, generator=gen).clamp(-3, 3))
+    rs = ref.storage.RolloutStorage(T, N, (O,), ref_shim.BoxSpace(A), 1, 3)
+    for k, val in buf.items():
+        getattr(rs, k).copy_(val)
+    with torch.no_grad():
+        next_value = pol.get_value(rs.obs[-1], rs.recurrent_hidden_states[-1], rs.masks[-1]).detach()
+        ve, lpe, ente, _ = pol.evaluate_actions(rs.obs[3], None, None, rs.actions[3])
+    g["next_value"] = next_value.numpy()
+    g["eval_value"], g["eval_logp"], g["eval_entropy"] = ve.numpy(), lpe.numpy(), np.array(float(ente))
+    rs.compute_returns(next_value, True, 0.99, 0.95, True)
+    for k in buf:
+        g["buf_" + k] = getattr(rs, k).numpy().copy()
+    S = T * N
+    g["rng_before_ppo"] = torch.get_rng_state().numpy()
+    st = torch.get_rng_state()
+    g["ppo_perm"] = torch.stack([torch.randperm(S) for _ in range(ppo_epoch)]).numpy()
+    torch.set_rng_state(st)
+    g["ppo_losses"] = np.array(agent.update(rs), dtype=np.float64)
+    for k, val in zip(orc.SPLIT_KEYS, pol.parameters()):
+        g["sp1_" + k] = val.detach().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name), **g)
+    print(name, g["ppo_losses"])
+
+
 def main():
     assert ref_shim.available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -155,7 +202,20 @@ def main():
     torch.manual_seed(2)
     run_case(ref, "laika_dims_seed2.npz", 2, 24, 4, 64, 28, 256, 86, 100, torch.randn(96, 86),
              gail_epoch=1, gail_batch=32, ppo_epoch=1, nmb=3, ep_len=20.0)
+    if "--all" in sys.argv or "--split" in sys.argv:
+        split_cases(ref)
+
+
+def split_cases(ref):
+    # SplitPolicy, shipped-script dims (Hopper: O=14, A=7, hidden 100, entropy_coef 0; train_hopper_deform.sh:5)
+    run_split_case(ref, "split_hopper_seed3.npz", 3, 40, 4, 14, 100, 1, ppo_epoch=2, nmb=4, entropy_coef=0.0, ep_len=9.0)
+    # Laikago-like: 4 feet (A=28), hidden 64, with an entropy bonus so that the state-dependent log-std heads get
+    # the entropy gradient as well
+    run_split_case(ref, "split_feet4_seed4.npz", 4, 24, 3, 64, 64, 4, ppo_epoch=1, nmb=3, entropy_coef=0.01, ep_len=9.0)
 
 
 if __name__ == "__main__":
-    main()
+    if "--split" in sys.argv and "--all" not in sys.argv:
+        split_cases(ref_shim.load())
+    else:
+        main()

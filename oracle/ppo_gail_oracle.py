@@ -105,6 +105,73 @@ def policy_act(p, x, deterministic=False, noise: Optional[torch.Tensor] = None):
 
 
 # ----------------------------------------------------------------------------------------------
+# SplitPolicy: A2C/model_split.py:39-95, 157-238 (what the shipped train_*.sh scripts use, --use-split-pi)
+# ----------------------------------------------------------------------------------------------
+SPLIT_KEYS = ("c_w1", "c_b1", "c_w2", "c_b2", "a_w1", "a_b1", "a_w2", "a_b2",
+              "v_w1", "v_b1", "v_w2", "v_b2", "v_w3", "v_b3",
+              "cm_w", "cm_b", "am_w", "am_b", "cl_w", "cl_b", "al_w", "al_b")
+
+
+def _ortho_linear_bias(n_out: int, n_in: int, gain: float, bias: float):
+    lin = torch.nn.Linear(n_in, n_out)
+    torch.nn.init.orthogonal_(lin.weight.data, gain=gain)
+    torch.nn.init.constant_(lin.bias.data, bias)
+    return lin.weight.data.clone(), lin.bias.data.clone()
+
+
+def init_split_policy(obs_dim: int, hidden: int, num_feet: int = 1) -> Dict[str, torch.Tensor]:
+    """Parameters of SplitPolicy in construction (= RNG) order: SplitPolicyBaseNew (contact trunk, actuator
+    trunk, critic trunk incl. its gain-1 final layer, model_split.py:172-185), then StateDiagGaussianNew
+    (contact_mean, actuator_mean gain 0.02; contact_logstd, actuator_logstd gain 1 / bias -0.5, :220-224)."""
+    g = math.sqrt(2.0)
+    p = {}
+    p["c_w1"], p["c_b1"] = _ortho_linear(hidden, obs_dim, g)
+    p["c_w2"], p["c_b2"] = _ortho_linear(hidden, hidden, g)
+    p["a_w1"], p["a_b1"] = _ortho_linear(hidden, obs_dim, g)
+    p["a_w2"], p["a_b2"] = _ortho_linear(hidden, hidden, g)
+    p["v_w1"], p["v_b1"] = _ortho_linear(hidden, obs_dim, g)
+    p["v_w2"], p["v_b2"] = _ortho_linear(hidden, hidden, g)
+    p["v_w3"], p["v_b3"] = _ortho_linear(1, hidden, 1.0)
+    p["cm_w"], p["cm_b"] = _ortho_linear_bias(4 * num_feet, hidden, 0.02, 0.0)
+    p["am_w"], p["am_b"] = _ortho_linear_bias(3 * num_feet, hidden, 0.02, 0.0)
+    p["cl_w"], p["cl_b"] = _ortho_linear_bias(4 * num_feet, hidden, 1.0, -0.5)
+    p["al_w"], p["al_b"] = _ortho_linear_bias(3 * num_feet, hidden, 1.0, -0.5)
+    return p
+
+
+def split_forward(p: Dict[str, torch.Tensor], x: torch.Tensor):
+    """-> value (B,1), mean (B,A), logstd (B,A) -- state-dependent log-std (model_split.py:187-198, 226-238)."""
+    def trunk(pre):
+        return torch.tanh(F.linear(torch.tanh(F.linear(x, p[pre + "_w1"], p[pre + "_b1"])), p[pre + "_w2"], p[pre + "_b2"]))
+    value = F.linear(trunk("v"), p["v_w3"], p["v_b3"])
+    y1, y2 = trunk("c"), trunk("a")
+    mean = torch.cat((F.linear(y1, p["cm_w"], p["cm_b"]), F.linear(y2, p["am_w"], p["am_b"])), 1)
+    logstd = torch.cat((F.linear(y1, p["cl_w"], p["cl_b"]), F.linear(y2, p["al_w"], p["al_b"])), 1)
+    return value, mean, logstd
+
+
+def split_evaluate(p, x, action):
+    """-> value, logp (B,1), batch-mean entropy (model_split.py:87-95)."""
+    value, mean, logstd = split_forward(p, x)
+    logp, ent = gaussian_logp_entropy(mean, logstd, action)
+    return value, logp, ent.mean()
+
+
+def split_act(p, x, deterministic=False, noise: Optional[torch.Tensor] = None):
+    """-> value, action, logp (model_split.py:69-81)."""
+    with torch.no_grad():
+        value, mean, logstd = split_forward(p, x)
+        if deterministic:
+            action = mean
+        elif noise is not None:
+            action = mean + logstd.exp() * noise
+        else:
+            action = torch.distributions.Normal(mean, logstd.exp()).sample()
+        logp, _ = gaussian_logp_entropy(mean, logstd, action)
+    return value, action, logp
+
+
+# ----------------------------------------------------------------------------------------------
 # rollout buffer: A2C/storage.py
 # ----------------------------------------------------------------------------------------------
 def new_buffer(T: int, N: int, obs_dim: int, act_dim: int, feat_len: int) -> Dict[str, torch.Tensor]:
@@ -220,9 +287,9 @@ def normalized_advantages(buf) -> torch.Tensor:
     return (adv - adv.mean()) / (adv.std() + 1e-5)
 
 
-def ppo_losses(p, hyper: PPOHyper, obs, actions, value_preds, returns, old_logp, adv):
+def ppo_losses(p, hyper: PPOHyper, obs, actions, value_preds, returns, old_logp, adv, evaluate=None):
     """value_loss, action_loss, entropy for one minibatch (A2C/algo/ppo.py:88-108)."""
-    values, logp, entropy = policy_evaluate(p, obs, actions)
+    values, logp, entropy = (evaluate or policy_evaluate)(p, obs, actions)
     ratio = torch.exp(logp - old_logp)
     s1 = ratio * adv
     s2 = torch.clamp(ratio, 1.0 - hyper.clip_param, 1.0 + hyper.clip_param) * adv
@@ -238,18 +305,20 @@ def ppo_losses(p, hyper: PPOHyper, obs, actions, value_preds, returns, old_logp,
 class PPOOracle:
     """Holds leaf parameters + torch.optim.Adam exactly as A2C/algo/ppo.py:57 does."""
 
-    def __init__(self, params: Dict[str, torch.Tensor], hyper: PPOHyper):
+    def __init__(self, params: Dict[str, torch.Tensor], hyper: PPOHyper, keys=None, evaluate=None):
         self.hyper = hyper
-        self.p = {k: params[k].clone().requires_grad_(True) for k in POLICY_KEYS}
-        self.optimizer = torch.optim.Adam([self.p[k] for k in POLICY_KEYS], lr=hyper.lr, eps=hyper.eps)
+        self.keys = tuple(keys or POLICY_KEYS)          # parameter order = nn.Module.parameters() order
+        self.evaluate = evaluate                        # policy_evaluate (Policy) or split_evaluate (SplitPolicy)
+        self.p = {k: params[k].clone().requires_grad_(True) for k in self.keys}
+        self.optimizer = torch.optim.Adam([self.p[k] for k in self.keys], lr=hyper.lr, eps=hyper.eps)
 
     def step(self, obs, actions, value_preds, returns, old_logp, adv):
         """One optimizer step; returns the three loss scalars and the pre-clip gradient norm."""
         h = self.hyper
-        vl, al, ent = ppo_losses(self.p, h, obs, actions, value_preds, returns, old_logp, adv)
+        vl, al, ent = ppo_losses(self.p, h, obs, actions, value_preds, returns, old_logp, adv, self.evaluate)
         self.optimizer.zero_grad()
         (vl * h.value_loss_coef + al - ent * h.entropy_coef).backward()
-        gn = torch.nn.utils.clip_grad_norm_([self.p[k] for k in POLICY_KEYS], h.max_grad_norm)
+        gn = torch.nn.utils.clip_grad_norm_([self.p[k] for k in self.keys], h.max_grad_norm)
         self.optimizer.step()
         return vl.item(), al.item(), ent.item(), float(gn)
 

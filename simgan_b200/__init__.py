@@ -5,6 +5,7 @@ RolloutStorage); the minibatch math runs in hand-written sm_100a kernels behind 
 in include/simgan_b200.h (loaded by simgan_b200._lib).
 """
 from .model import Policy, MLPBase  # noqa: F401
+from .model_split import SplitPolicy  # noqa: F401
 from .storage import RolloutStorage  # noqa: F401
 from .running_mean_std import RunningMeanStd  # noqa: F401
 from . import algo  # noqa: F401

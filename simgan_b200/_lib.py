@@ -60,6 +60,11 @@ SIGNATURES = {
     "sg_ppo_workspace_bytes": (C.c_int64, [C.POINTER(PpoConfig)]),
     "sg_ppo_phase_cycles_offset": (C.c_int64, [C.POINTER(PpoConfig)]),
     "sg_ppo_update": (C.c_int, [C.POINTER(PpoConfig)] + [c_void] * 14 + [ALLREDUCE_FN, c_void, c_void]),
+    "sg_split_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "sg_split_forward": (C.c_int, [c_void, C.c_int, C.c_int, C.c_int, c_void, C.c_int, c_void, c_void, c_void, c_void,
+                                   c_void, c_void, c_void]),
+    "sg_split_ppo_workspace_bytes": (C.c_int64, [C.POINTER(PpoConfig)]),
+    "sg_split_ppo_update": (C.c_int, [C.POINTER(PpoConfig)] + [c_void] * 15),
     "sg_dp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_dp_local_handle": (C.c_int, [c_void, C.c_char_p]),
     "sg_dp_open_peers": (C.c_int, [c_void, C.c_char_p]),
@@ -114,6 +119,14 @@ def policy_layout(obs_dim, hidden, act_dim):
     total = lib().sg_policy_layout(obs_dim, hidden, act_dim, offs)
     if total < 0:
         check(1, "sg_policy_layout")
+    return list(offs), total
+
+
+def split_layout(obs_dim, hidden, num_feet):
+    offs = (C.c_int * 22)()
+    total = lib().sg_split_layout(obs_dim, hidden, num_feet, offs)
+    if total < 0:
+        check(1, "sg_split_layout")
     return list(offs), total
 
 

@@ -45,8 +45,9 @@ class PPO(object):
         self._perm_dev = None
 
     # ---- helpers -------------------------------------------------------------------------------------
-    def _workspace(self, cfg, dev):
-        need = _lib.lib().sg_ppo_workspace_bytes(C.byref(cfg))
+    def _workspace(self, cfg, dev, split=False):
+        lib = _lib.lib()
+        need = (lib.sg_split_ppo_workspace_bytes if split else lib.sg_ppo_workspace_bytes)(C.byref(cfg))
         if need < 0:
             _lib.check(1, "sg_ppo_workspace_bytes")
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
@@ -92,6 +93,7 @@ class PPO(object):
         m, v = opt.ensure_state(flat)
         g = opt.param_groups[0]
 
+        is_split = type(ac).__name__ == "SplitPolicy"
         cfg = _lib.PpoConfig()
         cfg.obs_dim, cfg.hidden, cfg.act_dim = ac.obs_dim, ac.hidden_size, ac.act_dim
         cfg.T, cfg.N = T, N
@@ -102,6 +104,8 @@ class PPO(object):
         cfg.use_clipped_value_loss = int(bool(self.use_clipped_value_loss))
         cfg.first_adam_step = opt.step_count + 1
         cfg.row_begin, cfg.row_end = (0, mbs) if self.dp is None else self.dp.shard(mbs)
+        if is_split and self.dp is not None:
+            raise NotImplementedError("data-parallel updates are not wired for SplitPolicy yet")
         p2p = self.dp is not None and self.dp.p2p_ok(mbs)
         cfg.mode = self.kernel_mode if (self.dp is None or p2p) else 1
         if cfg.mode == 1 and p2p:
@@ -110,7 +114,7 @@ class PPO(object):
 
         lib = _lib.lib()
         stream = _lib.current_stream()
-        ws = self._workspace(cfg, dev)
+        ws = self._workspace(cfg, dev, is_split)
         # advantage statistics (ppo.py:66-68); the normalisation itself is fused into the tile phase
         stats = torch.empty(2, device=dev)
         stat_ws = torch.empty(int(lib.sg_adv_stats_workspace_bytes(S)), dtype=torch.uint8, device=dev)
@@ -140,17 +144,17 @@ class PPO(object):
             self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
             cfg.first_adam_step = opt.step_count + 1 + e * nmb
             tok = _lib.timer.start("ppo_update")
-            rc = lib.sg_ppo_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
-                                   _lib.ptr(rollouts.actions), _lib.ptr(rollouts.value_preds), _lib.ptr(rollouts.returns),
-                                   _lib.ptr(rollouts.action_log_probs), _lib.ptr(stats), _lib.ptr(self._perm_dev[e]),
-                                   _lib.ptr(sched[0, e * nmb:]), _lib.ptr(sched[1, e * nmb:]), _lib.ptr(trace[e * nmb:]),
-                                   _lib.ptr(ws), cb, user, stream)
+            args = (C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),
+                    _lib.ptr(rollouts.actions), _lib.ptr(rollouts.value_preds), _lib.ptr(rollouts.returns),
+                    _lib.ptr(rollouts.action_log_probs), _lib.ptr(stats), _lib.ptr(self._perm_dev[e]),
+                    _lib.ptr(sched[0, e * nmb:]), _lib.ptr(sched[1, e * nmb:]), _lib.ptr(trace[e * nmb:]), _lib.ptr(ws))
+            rc = lib.sg_split_ppo_update(*args, stream) if is_split else lib.sg_ppo_update(*args, cb, user, stream)
             _lib.timer.stop(tok)
             _lib.check(rc, "sg_ppo_update")
         cfg.ppo_epoch = self.ppo_epoch
         opt.step_count += n_steps
 
-        self._prof_view = (ws, int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
+        self._prof_view = (ws, 0 if is_split else int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
         if p2p:
             self.dp.sum_trace_(trace, 2)      # value / action loss columns are per-rank partial sums
         tr = trace.cpu()            # the one host sync of the update

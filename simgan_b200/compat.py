@@ -5,7 +5,7 @@ The reference's caller (third_party/a2c_ppo_acktr/main_gail_dyn_ppo.py:32-38) im
 classes by those module paths, and its checkpoints are whole-object pickles that record the class path
 ``third_party.a2c_ppo_acktr.model.Policy`` (main_gail_dyn_ppo.py:307-320, my_pybullet_envs/utils.py:24-56).
 ``install()`` registers alias modules in ``sys.modules`` so that both keep working unmodified; modules
-that are NOT on the hot path (``arguments``, ``envs``, ``model_split``, the rest of ``baselines``) still
+that are NOT on the hot path (``arguments``, ``envs``, the rest of ``baselines``) still
 come from the reference tree when ``reference_root`` is given.
 """
 import importlib
@@ -16,6 +16,7 @@ import types
 _A2C = "third_party.a2c_ppo_acktr"
 ALIASES = {
     _A2C + ".model": "simgan_b200.model",
+    _A2C + ".model_split": "simgan_b200.model_split",
     _A2C + ".storage": "simgan_b200.storage",
     _A2C + ".distributions": "simgan_b200.distributions",
     _A2C + ".utils": "simgan_b200.utils",

@@ -1,0 +1,86 @@
+"""SplitPolicy on the GPU (sg_split_forward / sg_split_ppo_update) vs the CPU oracle and the golden vectors of the
+real reference (third_party/a2c_ppo_acktr/model_split.py + algo/ppo.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_gail_oracle as orc
+from oracle.ref_shim import BoxSpace
+from test_split_oracle import SPLIT_CASES, SplitGolden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _make(g, which="sp0"):
+    import simgan_b200 as sg
+    sp = sg.SplitPolicy((g.O,), BoxSpace(g.A), base_kwargs={"hidden_size": g.H, "num_feet": g.feet})
+    for q, k in zip(sp.parameters(), orc.SPLIT_KEYS):
+        q.data.copy_(g.t("%s_%s" % (which, k)).reshape(q.shape))
+    sp.to(DEV)
+    return sp
+
+
+def _storage(g):
+    import gpu_util as gu
+    return gu.make_storage(g.buffer(), g.O, g.A, 3)
+
+
+def _rel(a, b, floor=1e-30):
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(floor))
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+@pytest.mark.parametrize("B", [1, 13, 64])
+def test_split_forward(case, B):
+    g = SplitGolden(case)
+    p = g.params()
+    sp = _make(g)
+    gen = torch.Generator().manual_seed(B)
+    x, act = torch.randn(B, g.O, generator=gen), torch.randn(B, g.A, generator=gen)
+    v_o, lp_o, ent_o = orc.split_evaluate(p, x, act)
+    with torch.no_grad():
+        v, lp, ent, _ = sp.evaluate_actions(x.to(DEV), None, None, act.to(DEV))
+        assert _rel(sp.get_value(x.to(DEV), None, None).cpu(), v_o, 0.5) < 3e-6
+    assert _rel(v.cpu(), v_o, 0.5) < 3e-6 and _rel(lp.cpu(), lp_o) < 3e-6
+    assert abs(float(ent) - float(ent_o)) < 3e-6 * abs(float(ent_o))
+    v_d, a_d, lp_d = orc.split_act(p, x, deterministic=True)
+    v2, a2, lp2, _ = sp.act(x.to(DEV), None, None, deterministic=True)
+    assert _rel(a2.cpu(), a_d, 0.01) < 3e-6 and _rel(lp2.cpu(), lp_d) < 3e-6
+    # sampled: action = mean + exp(logstd) * N(0,1) drawn from the CUDA generator, like Normal.sample()
+    torch.cuda.manual_seed(3)
+    _, a3, lp3, _ = sp.act(x.to(DEV), None, None)
+    torch.cuda.manual_seed(3)
+    noise = torch.randn(B, g.A, device=DEV)
+    _, a_n, lp_n = orc.split_act(p, x, noise=noise.cpu())
+    assert _rel(a3.cpu(), a_n, 0.05) < 1e-5 and _rel(lp3.cpu(), lp_n) < 1e-5
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_split_ppo_update_vs_oracle_and_golden(case):
+    import simgan_b200 as sg
+    g = SplitGolden(case)
+    sp = _make(g)
+    agent = sg.PPO(sp, 0.2, g.ppo_epoch, g.nmb, 0.5, g.entropy_coef, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    rs = _storage(g)
+    ora = orc.PPOOracle(g.params(), g.hyper(), keys=orc.SPLIT_KEYS, evaluate=orc.split_evaluate)
+    trace = []
+    out_o = ora.update(g.buffer(), index_chunks=g.chunks(), trace=trace)
+    out = agent.update(rs, permutations=g.t("ppo_perm"))
+    tr, tr_o = agent.last_trace.double().numpy(), np.array(trace)
+    scale = np.abs(tr_o).max(axis=0)
+    scale[1] = max(scale[1], 0.5)
+    assert np.all(np.abs(tr[0] - tr_o[0]) <= 1e-5 * scale + 1e-7), (tr[0], tr_o[0])
+    assert np.all(np.abs(tr - tr_o) <= 1e-4 * scale + 1e-6), np.abs(tr - tr_o).max(axis=0) / scale
+    ref = g.z["ppo_losses"]                                         # the REAL reference's outputs
+    assert abs(out[0] - ref[0]) <= 1e-4 * abs(ref[0]) and abs(out[2] - ref[2]) <= 1e-4 * abs(ref[2])
+    assert abs(out[1] - ref[1]) <= 1e-4 * max(abs(ref[1]), 0.05)
+    for q, k in zip(sp.parameters(), orc.SPLIT_KEYS):
+        assert torch.allclose(q.detach().cpu().reshape(-1), g.t("sp1_" + k).reshape(-1), rtol=1e-3, atol=2e-5), k
+    # drop-in call: draws its own permutations from the CPU generator, like feed_forward_generator
+    sp2 = _make(g)
+    agent2 = sg.PPO(sp2, 0.2, g.ppo_epoch, g.nmb, 0.5, g.entropy_coef, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    torch.set_rng_state(g.t("rng_before_ppo"))
+    out2 = agent2.update(_storage(g))
+    assert abs(out2[0] - ref[0]) <= 1e-4 * abs(ref[0])
