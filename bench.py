@@ -49,6 +49,10 @@ CONFIGS = {
                  label="LaikagoCombinedEnv-v1 sizes num_processes=128 num_steps=2048 hidden=256"),
     "cfg5": dict(T=1024, N=4096, O=111, A=12, H=64, F=86, HD=100, expert=16384, ep_len=78.0,
                  label="synthetic rollout 1024x4096 obs_dim=111"),
+    # what train_hopper_deform.sh:5 actually runs: SplitPolicy, hidden 100, 8 envs x 1000 steps, 16 minibatches
+    "shipped": dict(T=1000, N=8, O=14, A=7, H=100, F=25, HD=100, expert="hopper", ep_len=88.0, split=True,
+                    hyper=dict(num_mini_batch=16, entropy_coef=0.0),
+                    label="train_hopper_deform.sh sizes: SplitPolicy hidden=100 num_processes=8 num_steps=1000 num_mini_batch=16"),
 }
 HYPER = dict(gamma=0.99, gae_lambda=0.95, clip_param=0.2, ppo_epoch=10, num_mini_batch=32, value_loss_coef=0.5,
              entropy_coef=0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5, gail_epoch=5, gail_batch=128,
@@ -95,7 +99,10 @@ def algorithmic_work(c, n_disc_batches):
     w = {}
     w["gae_bytes"] = 20 * S
     w["ppo_bytes"] = h["ppo_epoch"] * s_used * 4 * (O + A + 4)
-    w["ppo_flops"] = h["ppo_epoch"] * s_used * 2 * (3 * (2 * H * H + H * A + H) + 2 * (2 * O * H))
+    if c.get("split"):     # three trunks, heads (8f + 6f + 1) x H; first-layer dX skipped
+        w["ppo_flops"] = h["ppo_epoch"] * s_used * 2 * (3 * (3 * H * H + H * (2 * A + 1)) + 2 * (3 * O * H))
+    else:
+        w["ppo_flops"] = h["ppo_epoch"] * s_used * 2 * (3 * (2 * H * H + H * A + H) + 2 * (2 * O * H))
     w["disc_bytes"] = h["gail_epoch"] * n_disc_batches * h["gail_batch"] * 4 * F * 2
     w["disc_flops"] = h["gail_epoch"] * n_disc_batches * h["gail_batch"] * 12 * 2 * (F * HD + HD * HD + HD)
     w["relabel_bytes"] = S * (4 * F + 8)
@@ -116,7 +123,10 @@ class Workload(object):
         torch.manual_seed(seed)
         T, N, O, A, H, F, HD = c["T"], c["N"], c["O"], c["A"], c["H"], c["F"], c["HD"]
         # construction order of main_gail_dyn_ppo.py:71-162: policy -> PPO -> expert -> D
-        self.policy = sg.Policy((O,), Box(A), base_kwargs={"recurrent": False, "hidden_size": H})
+        if c.get("split"):
+            self.policy = sg.SplitPolicy((O,), Box(A), base_kwargs={"hidden_size": H, "num_feet": A // 7})
+        else:
+            self.policy = sg.Policy((O,), Box(A), base_kwargs={"recurrent": False, "hidden_size": H})
         self.policy.to(device)
         self.agent = sg.PPO(self.policy, h["clip_param"], h["ppo_epoch"], h["num_mini_batch"], h["value_loss_coef"],
                             h["entropy_coef"], lr=h["lr"], eps=h["eps"], max_grad_norm=h["max_grad_norm"])
@@ -341,7 +351,7 @@ def run_cuda(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    env_steps = fake_env_collection(w) if world == 1 else None
+    env_steps = fake_env_collection(w) if (world == 1 and not c.get("split")) else None      # feed kernel: Policy layout only
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -435,19 +445,21 @@ def reference_sample(c, seed, threads):
     torch.set_num_threads(threads)
     torch.manual_seed(seed)
     T, N, O, A, H, F, HD = c["T"], c["N"], c["O"], c["A"], c["H"], c["F"], c["HD"]
-    pol = orc.init_policy(O, H, A)
+    split = bool(c.get("split"))
+    pol = orc.init_split_policy(O, H, A // 7) if split else orc.init_policy(O, H, A)
     expert = expert_rows(c, seed)
     dparams = orc.init_disc(F, HD)
     host, noise = host_rollout(c, seed, expert)
     buf = orc.new_buffer(T, N, O, A, F)
     for k, v in host.items():
         buf[k].copy_(v)
-    v, a, lp = orc.policy_act(pol, buf["obs"][:-1].reshape(T * N, O), noise=noise)
+    v, a, lp = (orc.split_act if split else orc.policy_act)(pol, buf["obs"][:-1].reshape(T * N, O), noise=noise)
     buf["value_preds"][:-1] = v.view(T, N, 1)
     buf["actions"].copy_(a.view(T, N, A))
     buf["action_log_probs"].copy_(lp.view(T, N, 1))
-    hyper = orc.PPOHyper(ppo_epoch=2)
-    ppo = orc.PPOOracle(pol, hyper)
+    hyper = orc.PPOHyper(ppo_epoch=2, num_mini_batch=h["num_mini_batch"], entropy_coef=h["entropy_coef"])
+    ppo = (orc.PPOOracle(pol, hyper, keys=orc.SPLIT_KEYS, evaluate=orc.split_evaluate) if split else orc.PPOOracle(pol, hyper))
+    fwd = orc.split_forward if split else orc.policy_forward
     disc = orc.DiscOracle(dparams)
     rms = orc.RunningMeanStd(shape=())
     n_db = min(len(expert) // h["gail_batch"], T * N // h["gail_batch"])
@@ -455,7 +467,7 @@ def reference_sample(c, seed, threads):
 
     def one():
         t0 = time.perf_counter()
-        nv = orc.policy_forward(ppo.params(), buf["obs"][-1])[0]
+        nv = fwd(ppo.params(), buf["obs"][-1])[0]
         disc.update_epoch(expert, buf, batch_size=h["gail_batch"], drop_last=len(expert) > h["gail_batch"])
         t1 = time.perf_counter()
         r_sa = orc.alive_bonus_offset(buf["masks"], T, N, h["gail_tar_length"])
@@ -524,6 +536,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    HYPER.update(CONFIGS[args.config].get("hyper", {}))
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) == 0:
             run_reference(args)
