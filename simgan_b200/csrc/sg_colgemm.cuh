@@ -69,9 +69,65 @@ __device__ __forceinline__ void col_dot_nq_bwd(const float* __restrict__ Wq, int
 }
 
 // G[n*K + k] (+)= sum_r Yt[n*R + r] * X[r*ldx + k]   for an (N,K) weight gradient, K % 4 == 0.
-// Work item = (row n, interleaved k-quad lane s of NSEG); float4 results go straight to L2 (st.cg).
+// Register tile: a work item is 4 rows n x QG k-quads (QG <= 4 chosen so that one sweep covers the matrix);
+// the 4xR block of Yt is loaded once and every X quad is used for 4 outputs rows, i.e. ~3 FMAs per float that
+// crosses the shared-memory port instead of 1.  float4 results go straight to L2 (st.cg).
 template <int R>
 __device__ __forceinline__ void outer_cols(float* __restrict__ G, const float* __restrict__ Yt, const float* __restrict__ X,
+                                           int ldx, int N, int K, int t, int nth, bool acc) {
+    static_assert(R % 4 == 0, "rows come in float4 groups");
+    const int KQ = K >> 2;
+    const int NB = (N + 3) >> 2;
+    int qg = 1;
+    while (qg < 4 && NB * ((KQ + qg - 1) / qg) > nth) ++qg;
+    const int ngrp = (KQ + qg - 1) / qg;
+    for (int idx = t; idx < NB * ngrp; idx += nth) {
+        const int nb = idx / ngrp, g = idx - nb * ngrp;
+        const int n0 = nb * 4, q0 = g * qg;
+        float y[4][R];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (n0 + i < N) {
+                load_rows_t<R>(Yt, n0 + i, y[i]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) y[i][r] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = q0 + j;
+            if (j >= qg || q >= KQ) break;
+            float4 o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + 4 * q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    o[i].x = fmaf(y[i][r], x.x, o[i].x); o[i].y = fmaf(y[i][r], x.y, o[i].y);
+                    o[i].z = fmaf(y[i][r], x.z, o[i].z); o[i].w = fmaf(y[i][r], x.w, o[i].w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (n0 + i < N) {
+                    float4* gp = reinterpret_cast<float4*>(G + (size_t)(n0 + i) * K + 4 * q);
+                    float4 v = o[i];
+                    if (acc) { const float4 old = __ldcg(gp); v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w; }
+                    __stcg(gp, v);
+                }
+            }
+        }
+    }
+}
+
+// Same product, one row n x an interleaved set of k-quads per work item (lighter on registers; what the PPO
+// column tile uses).  G[n*K + k] (+)= sum_r Yt[n*R + r] * X[r*ldx + k], K % 4 == 0.
+// Work item = (row n, interleaved k-quad lane s of NSEG); float4 results go straight to L2 (st.cg).
+template <int R>
+__device__ __forceinline__ void outer_cols_seg(float* __restrict__ G, const float* __restrict__ Yt, const float* __restrict__ X,
                                            int ldx, int N, int K, int t, int nth, bool acc) {
     const int KQ = K >> 2;
     int nseg = 1, lg = 0;

@@ -507,16 +507,16 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
     {
         const float* Dh = half ? sm.DVt : sm.DMUt;
         const int NH = half ? 1 : A;
-        outer_cols<R>(gout + (half ? a.L.vw : a.L.mw), Dh, h2, ldh, NH, H, t, kHalf, acc);
+        outer_cols_seg<R>(gout + (half ? a.L.vw : a.L.mw), Dh, h2, ldh, NH, H, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.vb : a.L.mb), Dh, NH, t, kHalf, acc);
         if (!half) rowsum_store<R>(gout + a.L.ls, sm.DLSt, A, t, kHalf, acc);
-        outer_cols<R>(gout + (half ? a.L.cw2 : a.L.aw2), dz2t, h1, ldh, H, H, t, kHalf, acc);
+        outer_cols_seg<R>(gout + (half ? a.L.cw2 : a.L.aw2), dz2t, h1, ldh, H, H, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.cb2 : a.L.ab2), dz2t, H, t, kHalf, acc);
     }
     __syncthreads();
     {
         float* gW1 = gout + (half ? a.L.cw1 : a.L.aw1);
-        if ((O & 3) == 0) outer_cols<R>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
+        if ((O & 3) == 0) outer_cols_seg<R>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
         else outer_store<R, 1>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.cb1 : a.L.ab1), dz1t, H, t, kHalf, acc);
     }
