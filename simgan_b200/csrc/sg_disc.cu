@@ -415,6 +415,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     const DiscRegImage I = make_disc_reg_image(a.F, a.H);
     float* img = smem;
     float* tile = smem + I.total;
+    float* stage = tile + DiscRegSmem::floats(a.F, a.H);      // H*H floats: coalesced landing zone of W2
     DiscRegSmem sm;
     sm.carve(tile, a.F, a.H);
     DiscRegW2<HQ> w;
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     for (int step = 0; step < a.nsteps; ++step) {
-        disc_reg_fill<HQ>(w, img, a.params, a.L, I, threadIdx.x);
+        disc_reg_fill<HQ>(w, img, stage, a.params, a.L, I, threadIdx.x);
         pc.lap(0);
         bool acc = false;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
@@ -662,8 +663,10 @@ static bool disc_reg_ok(const sg_disc_config* c) {
 }
 static size_t disc_reg_smem_bytes(const sg_disc_config* c) {
     size_t tile = (size_t)DiscRegSmem::floats(c->feat_dim, c->hidden);
-    if (tile < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);     // phase B scratch: NT + 128 float4
-    return ((size_t)make_disc_reg_image(c->feat_dim, c->hidden).total + tile) * sizeof(float);
+    // phase B scratch (NT + 128 float4) aliases the tile arrays + the W2 staging area behind them
+    const size_t stage = (size_t)c->hidden * c->hidden;
+    if (tile + stage < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);
+    return ((size_t)make_disc_reg_image(c->feat_dim, c->hidden).total + tile + stage) * sizeof(float);
 }
 static size_t disc_resident_smem_bytes(const sg_disc_config* c) {
     if (disc_reg_ok(c)) return disc_reg_smem_bytes(c);

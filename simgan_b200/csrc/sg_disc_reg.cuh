@@ -67,25 +67,31 @@ struct DiscRegW2 {
     float wcol[Q0 * 4];
 };
 
-// (re)load this thread's register slices of W2 and the small shared image, straight from global through L2
+// (re)load this thread's register slices of W2 and the small shared image.  W2 travels global -> shared with
+// fully coalesced 16-byte loads into `stage` (H*H floats, natural layout) and is then picked into registers from
+// shared memory: the row form needs 16-byte pieces of 128 different rows and the column form scalar columns, which
+// as direct global loads cost ~20 memory transactions per warp-load.
 template <int HQ>
-__device__ __forceinline__ void disc_reg_fill(DiscRegW2<HQ>& w, float* __restrict__ img, const float* __restrict__ params,
-                                              const DiscLayout& L, const DiscRegImage& I, int tid) {
+__device__ __forceinline__ void disc_reg_fill(DiscRegW2<HQ>& w, float* __restrict__ img, float* __restrict__ stage,
+                                              const float* __restrict__ params, const DiscLayout& L, const DiscRegImage& I,
+                                              int tid) {
     constexpr int H = 4 * HQ, Q0 = DiscRegW2<HQ>::Q0;
     const int u = tid >> 1, kh = tid & 1;
     const float* W2 = params + L.w2;
     const bool live = u < H;
+    constexpr int U = 6;
+    for (int p = 4 * tid; p < H * H; p += 4 * kStepThreads * U) {
+        float4 q[U];
 #pragma unroll
-    for (int i = 0; i < Q0; ++i) {
-        const int q = kh * Q0 + i;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live && q < HQ) v = ld_cg4(W2 + (size_t)u * H + 4 * q);
-        w.wrow[4 * i] = v.x; w.wrow[4 * i + 1] = v.y; w.wrow[4 * i + 2] = v.z; w.wrow[4 * i + 3] = v.w;
-    }
+        for (int i = 0; i < U; ++i) {
+            const int e = p + 4 * kStepThreads * i;
+            q[i] = e < H * H ? ld_cg4(W2 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-    for (int i = 0; i < Q0 * 4; ++i) {
-        const int m = kh * Q0 * 4 + i;
-        w.wcol[i] = (live && m < H) ? ld_cg(W2 + (size_t)m * H + u) : 0.f;
+        for (int i = 0; i < U; ++i) {
+            const int e = p + 4 * kStepThreads * i;
+            if (e < H * H) *reinterpret_cast<float4*>(stage + e) = q[i];
+        }
     }
     // small image: segments before W2 (W1, b1) and after it (b2, w3, b3)
     const int n1 = L.w2;                       // floats before the W2 block (multiple of 4)
@@ -95,6 +101,19 @@ __device__ __forceinline__ void disc_reg_fill(DiscRegW2<HQ>& w, float* __restric
         *reinterpret_cast<float4*>(img + p) = ld_cg4(params + src);
     }
     __syncthreads();
+#pragma unroll
+    for (int i = 0; i < Q0; ++i) {
+        const int q = kh * Q0 + i;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live && q < HQ) v = *reinterpret_cast<const float4*>(stage + (size_t)u * H + 4 * q);
+        w.wrow[4 * i] = v.x; w.wrow[4 * i + 1] = v.y; w.wrow[4 * i + 2] = v.z; w.wrow[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < Q0 * 4; ++i) {
+        const int m = kh * Q0 * 4 + i;
+        w.wcol[i] = (live && m < H) ? stage[(size_t)m * H + u] : 0.f;
+    }
+    __syncthreads();                           // `stage` may alias buffers the tile phase writes
 }
 
 // out[r] = sum over my quads of A[r][k] * wreg[k]; both lanes of a unit get the full sum
