@@ -419,11 +419,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     DiscRegSmem sm;
     sm.carve(tile, a.F, a.H);
     DiscRegW2<HQ> w;
+    __shared__ __align__(8) unsigned long long fill_bar;
+    if (threadIdx.x == 0) mbar_init(&fill_bar, 1);
+    __syncthreads();
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     for (int step = 0; step < a.nsteps; ++step) {
-        disc_reg_fill<HQ>(w, img, stage, a.params, a.L, I, threadIdx.x);
+        disc_reg_fill<HQ>(w, img, stage, a.params, a.L, I, threadIdx.x, &fill_bar, (unsigned int)(step & 1));
         pc.lap(0);
         bool acc = false;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {

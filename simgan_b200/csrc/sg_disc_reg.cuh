@@ -67,40 +67,30 @@ struct DiscRegW2 {
     float wcol[Q0 * 4];
 };
 
-// (re)load this thread's register slices of W2 and the small shared image.  W2 travels global -> shared with
-// fully coalesced 16-byte loads into `stage` (H*H floats, natural layout) and is then picked into registers from
+// (re)load this thread's register slices of W2 and the small shared image.  W2 travels global -> shared as ONE TMA
+// bulk copy (cp.async.bulk) into `stage` (H*H floats, natural layout) and is then picked into registers from
 // shared memory: the row form needs 16-byte pieces of 128 different rows and the column form scalar columns, which
 // as direct global loads cost ~20 memory transactions per warp-load.
 template <int HQ>
 __device__ __forceinline__ void disc_reg_fill(DiscRegW2<HQ>& w, float* __restrict__ img, float* __restrict__ stage,
                                               const float* __restrict__ params, const DiscLayout& L, const DiscRegImage& I,
-                                              int tid) {
+                                              int tid, unsigned long long* bar, unsigned int parity) {
     constexpr int H = 4 * HQ, Q0 = DiscRegW2<HQ>::Q0;
     const int u = tid >> 1, kh = tid & 1;
     const float* W2 = params + L.w2;
     const bool live = u < H;
-    constexpr int U = 6;
-    for (int p = 4 * tid; p < H * H; p += 4 * kStepThreads * U) {
-        float4 q[U];
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const int e = p + 4 * kStepThreads * i;
-            q[i] = e < H * H ? ld_cg4(W2 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < U; ++i) {
-            const int e = p + 4 * kStepThreads * i;
-            if (e < H * H) *reinterpret_cast<float4*>(stage + e) = q[i];
-        }
-    }
-    // small image: segments before W2 (W1, b1) and after it (b2, w3, b3)
+    // three TMA bulk copies (W2 -> stage; [W1|b1] and [b2|w3|b3] -> img) on one mbarrier; nothing else ever writes
+    // these shared-memory regions, so there is no generic/async proxy hazard on them
     const int n1 = L.w2;                       // floats before the W2 block (multiple of 4)
     const int n2 = L.total - L.b2;             // floats after it
-    for (int p = 4 * tid; p < n1 + n2; p += 4 * kStepThreads) {
-        const int src = p < n1 ? p : L.b2 + (p - n1);
-        *reinterpret_cast<float4*>(img + p) = ld_cg4(params + src);
+    if (tid == 0) {
+        fence_proxy_async();                   // the parameters were written by other CTAs' generic stores (grid barrier acquired)
+        mbar_expect_tx(bar, (unsigned int)((H * H + n1 + n2) * sizeof(float)));
+        tma_bulk_g2s(stage, W2, (unsigned int)(H * H * sizeof(float)), bar);
+        tma_bulk_g2s(img, params, (unsigned int)(n1 * sizeof(float)), bar);
+        tma_bulk_g2s(img + n1, params + L.b2, (unsigned int)(n2 * sizeof(float)), bar);
     }
-    __syncthreads();
+    mbar_wait(bar, parity);
 #pragma unroll
     for (int i = 0; i < Q0; ++i) {
         const int q = kh * Q0 + i;
