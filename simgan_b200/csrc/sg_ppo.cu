@@ -258,35 +258,31 @@ __host__ __device__ inline PolicyLayout make_policy_image_layout(int O, int H, i
     return L;
 }
 
-// global natural parameter vector -> shared-memory image (natural segments copied, W2 blocks scattered to NQ)
-__device__ __forceinline__ void load_policy_image(float* __restrict__ Wi, const float* __restrict__ params, const PolicyLayout& L,
-                                                  const PolicyLayout& LI, int H, int tid) {
+// global natural parameter vector -> shared-memory image.  Five TMA bulk copies (cp.async.bulk) on one mbarrier:
+// the natural segments land directly at their image offsets, the two W2 blocks land in `stage` (2*H*H floats) and
+// are then re-laid out into the NQ form shared -> shared by all threads.
+__device__ __forceinline__ void load_policy_image(float* __restrict__ Wi, float* __restrict__ stage, const float* __restrict__ params,
+                                                  const PolicyLayout& L, const PolicyLayout& LI, int H, int tid,
+                                                  unsigned long long* bar, unsigned int parity) {
     const int HH = H * H;
-    const int d1 = LI.ab2 - L.ab2, d2 = LI.cb2 - L.cb2;
-    constexpr int U = 8;
-    for (int p = 4 * tid; p < L.total; p += 4 * kStepThreads * U) {
-        float4 q[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = p + 4 * kStepThreads * u;
-            q[u] = i < L.total ? ld_cg4(params + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = p + 4 * kStepThreads * u;
-            if (i >= L.total) break;
-            int rel = -1, base = 0;
-            if (i >= L.aw2 && i < L.aw2 + HH) { rel = i - L.aw2; base = LI.aw2; }
-            else if (i >= L.cw2 && i < L.cw2 + HH) { rel = i - L.cw2; base = LI.cw2; }
-            if (rel >= 0) {
-                const int n = rel / H, k = rel - n * H;
-                float* d = Wi + base + nq_index(n, k, H);
-                d[0] = q[u].x; d[4] = q[u].y; d[8] = q[u].z; d[12] = q[u].w;
-            } else {
-                const int dst = i < L.aw2 ? i : (i < L.cw2 ? i + d1 : i + d2);
-                *reinterpret_cast<float4*>(Wi + dst) = q[u];
-            }
-        }
+    if (tid == 0) {
+        fence_proxy_async();        // parameters were written by other CTAs' generic stores (grid barrier acquired)
+        mbar_expect_tx(bar, (unsigned int)(L.total * sizeof(float)));
+        tma_bulk_g2s(Wi, params, (unsigned int)(L.aw2 * sizeof(float)), bar);                                      // aw1 ab1
+        tma_bulk_g2s(stage, params + L.aw2, (unsigned int)(HH * sizeof(float)), bar);                              // aw2
+        tma_bulk_g2s(Wi + LI.ab2, params + L.ab2, (unsigned int)((L.cw2 - L.ab2) * sizeof(float)), bar);           // ab2 cw1 cb1
+        tma_bulk_g2s(stage + HH, params + L.cw2, (unsigned int)(HH * sizeof(float)), bar);                         // cw2
+        tma_bulk_g2s(Wi + LI.cb2, params + L.cb2, (unsigned int)((L.total - L.cb2) * sizeof(float)), bar);         // cb2 .. logstd
+    }
+    mbar_wait(bar, parity);
+    // natural (n,k) -> NQ: lanes walk k-quads of one row; the 4 scalar stores of a quad go to 4 consecutive k slots
+    for (int q = tid; q < 2 * (HH >> 2); q += kStepThreads) {
+        const int net = q >= (HH >> 2);
+        const int rel = 4 * (q - net * (HH >> 2));
+        const float4 v = *reinterpret_cast<const float4*>(stage + net * HH + rel);
+        const int n = rel / H, k = rel - n * H;
+        float* d = Wi + (net ? LI.cw2 : LI.aw2) + nq_index(n, k, H);
+        d[0] = v.x; d[4] = v.y; d[8] = v.z; d[12] = v.w;
     }
     __syncthreads();
 }
@@ -700,6 +696,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
     __shared__ double red[kStepThreads / 32];
     float* Ws = smem;
     float* tile = RESIDENT == 2 ? smem + a.LI.total : (RESIDENT == 1 ? smem + a.P : smem);
+    float* stage = tile + PpoSmemCol<R>::floats(a.O, a.H, a.A);      // RESIDENT 2: TMA landing zone of the two W2 blocks
+    __shared__ __align__(8) unsigned long long img_bar;
+    if (RESIDENT == 2) {
+        if (threadIdx.x == 0) mbar_init(&img_bar, 1);
+        __syncthreads();
+    }
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
         float4 mine;
         bool have;
         if (RESIDENT == 2) {
-            load_policy_image(Ws, a.params, a.L, a.LI, a.H, threadIdx.x);
+            load_policy_image(Ws, stage, a.params, a.L, a.LI, a.H, threadIdx.x, &img_bar, (unsigned int)(step & 1));
             pc.lap(0);
             ppo_phaseA_col<R>(a, Ws, step, blockIdx.x, gridDim.x, tile);
             pc.lap(1);
@@ -797,8 +799,9 @@ static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
     if (ppo_col_ok(c)) {
         PolicyLayout LI = make_policy_image_layout(c->obs_dim, c->hidden, c->act_dim);
         size_t tile = (size_t)PpoSmemCol<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
-        if (tile < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);
-        return ((size_t)LI.total + tile) * sizeof(float);
+        const size_t stage = 2 * (size_t)c->hidden * c->hidden;            // TMA landing zone of the two W2 blocks
+        if (tile + stage < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);
+        return ((size_t)LI.total + tile + stage) * sizeof(float);
     }
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
     return ((size_t)L.total + ppo_tile_smem_floats(c)) * sizeof(float);
