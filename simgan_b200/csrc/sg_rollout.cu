@@ -6,72 +6,15 @@
 namespace sg {
 
 // ------------------------------------------------------------------------------------------------
-// compute_returns (A2C/storage.py:103-142).  One thread per env column walks t = T-1..0; loads are
-// issued a block of UNR steps ahead of the dependent chain.  Every arithmetic step uses explicit
-// round-to-nearest mul/add in the reference's order so the result is bit-identical to the eager
-// fp32 tensor ops (no FMA contraction).
+// compute_returns (A2C/storage.py:103-142): a first-order linear recurrence over t = T-1..0 per env column.
+// Every arithmetic step uses explicit round-to-nearest mul/add in the reference's order so the result is
+// bit-identical to the eager fp32 tensor ops (no FMA contraction).
 //   mode 0: GAE + proper time limits   mode 1: GAE   mode 2: plain + proper limits   mode 3: plain
-// ------------------------------------------------------------------------------------------------
-constexpr int kUnr = 8;
-
-template <int MODE>
-__global__ void __launch_bounds__(128) returns_scan_kernel(const float* __restrict__ rewards, float* __restrict__ vpred,
-                                                           const float* __restrict__ masks,
-                                                           const float* __restrict__ bad, float* __restrict__ ret,
-                                                           const float* __restrict__ next_value, int T, int N,
-                                                           float g, float gl) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const float nv = next_value[n];
-    constexpr bool GAE = (MODE <= 1), PROPER = (MODE == 0 || MODE == 2);
-    float carry;       // gae (GAE modes) or returns[t+1] (plain modes)
-    float v_next = nv;
-    if (GAE) { vpred[(size_t)T * N + n] = nv; carry = 0.f; }
-    else { ret[(size_t)T * N + n] = nv; carry = nv; }
-    for (int t0 = T; t0 > 0; t0 -= kUnr) {
-        float r[kUnr], v[kUnr], m[kUnr], b[kUnr];
-#pragma unroll
-        for (int u = 0; u < kUnr; ++u) {
-            const int t = t0 - 1 - u;
-            if (t >= 0) {
-                r[u] = rewards[(size_t)t * N + n];
-                v[u] = vpred[(size_t)t * N + n];
-                m[u] = masks[(size_t)(t + 1) * N + n];
-                b[u] = PROPER ? bad[(size_t)(t + 1) * N + n] : 1.f;
-            } else { r[u] = v[u] = m[u] = 0.f; b[u] = 1.f; }
-        }
-#pragma unroll
-        for (int u = 0; u < kUnr; ++u) {
-            const int t = t0 - 1 - u;
-            if (t < 0) break;
-            float out;
-            if (GAE) {
-                // delta = r + gamma*V[t+1]*m - V[t];  gae = delta + (gamma*lambda)*m*gae;  gae *= bad
-                const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(g, v_next), m[u])), v[u]);
-                carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, m[u]), carry));
-                if (PROPER) carry = __fmul_rn(carry, b[u]);
-                out = __fadd_rn(carry, v[u]);
-                v_next = v[u];
-            } else if (PROPER) {
-                // (ret[t+1]*gamma*m + r)*bad + (1-bad)*V[t]
-                const float a = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(carry, g), m[u]), r[u]), b[u]);
-                out = __fadd_rn(a, __fmul_rn(__fsub_rn(1.f, b[u]), v[u]));
-                carry = out;
-            } else {
-                out = __fadd_rn(__fmul_rn(__fmul_rn(carry, g), m[u]), r[u]);
-                carry = out;
-            }
-            ret[(size_t)t * N + n] = out;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Staged variant for narrow buffers (N small: too few env columns to hide the load latency of a serial
-// chain with thread-level prefetch).  One CTA per 32 columns; ALL 256 threads stream chunks of kTC steps of the
+// A thread walking the chain cannot hide the latency of its own loads (16 columns x 2048 dependent steps took
+// 0.46 ms with thread-level prefetch), so the inputs are staged:
+// one CTA per 32 columns; ALL 256 threads stream chunks of kTC steps of the
 // four input arrays into double-buffered shared memory with cp.async (coalesced 128-byte row segments) while
 // the first `cols` threads walk the recurrence out of shared memory; results are written back coalesced.
-// Same arithmetic, same order: bit-identical to returns_scan_kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTC = 32;
 
@@ -369,27 +312,13 @@ int sg_compute_returns(const float* rewards, float* value_preds, const float* ma
     SG_REQUIRE(rewards && value_preds && masks && bad_masks && returns && next_value, "sg_compute_returns: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
-    const int threads = 128, blocks = (N + threads - 1) / threads;
     const int mode = use_gae ? (use_proper_time_limits ? 0 : 1) : (use_proper_time_limits ? 2 : 3);
-    if (N > 0) {
-        // the serial chain cannot hide its own loads -> staged shared-memory pipeline (any N; the per-thread
-        // prefetch kernel below is kept as the simple reference implementation)
-        const int sb = (N + 31) / 32;
-        switch (mode) {
-            case 0: returns_scan_staged_kernel<0><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-            case 1: returns_scan_staged_kernel<1><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-            case 2: returns_scan_staged_kernel<2><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-            default: returns_scan_staged_kernel<3><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        }
-        count_launches(1);
-        SG_CUDA(cudaGetLastError());
-        return SG_OK;
-    }
+    const int sb = (N + 31) / 32;
     switch (mode) {
-        case 0: returns_scan_kernel<0><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        case 1: returns_scan_kernel<1><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        case 2: returns_scan_kernel<2><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        default: returns_scan_kernel<3><<<blocks, threads, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 0: returns_scan_staged_kernel<0><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 1: returns_scan_staged_kernel<1><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 2: returns_scan_staged_kernel<2><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        default: returns_scan_staged_kernel<3><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
     }
     count_launches(1);
     SG_CUDA(cudaGetLastError());
