@@ -17,6 +17,9 @@ from . import _lib
 class RolloutFeeder(object):
     def __init__(self, actor_critic, rollouts):
         self.ac, self.rs = actor_critic, rollouts
+        if type(actor_critic).__name__ != "Policy":
+            raise NotImplementedError("RolloutFeeder drives sg_rollout_feed, which reads the Policy (MLPBase + DiagGaussian) "
+                                      "parameter layout; use act() + insert() with %s" % type(actor_critic).__name__)
         if not rollouts.obs.is_cuda:
             raise _lib.SgError("RolloutFeeder needs the rollout buffer on a CUDA device; there is no CPU fallback")
         self.dev = rollouts.obs.device
