@@ -416,29 +416,18 @@ __device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ 
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < NQ) {
             const float* src = part + p0 + 4 * j;
-            int c = q;
-            for (; c + 15 * NQ < nslots; c += 16 * NQ) {    // sixteen independent L2 loads in flight
+            // one fully predicated batch of 16 independent L2 loads per sweep (slots beyond nslots read as zero):
+            // a sequential tail would cost one L2 round trip per leftover slot
+            for (int c = q; c < nslots; c += 16 * NQ) {
                 float4 v[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = ld_cg4(src + (size_t)(c + u * NQ) * stride);
+                for (int u = 0; u < 16; ++u) {
+                    const int cc = c + u * NQ;
+                    v[u] = cc < nslots ? ld_cg4(src + (size_t)cc * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int u = 0; u < 16; ++u) s = f4_add(s, v[u]);
             }
-            for (; c + 7 * NQ < nslots; c += 8 * NQ) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = ld_cg4(src + (size_t)(c + u * NQ) * stride);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
-            }
-            for (; c + 3 * NQ < nslots; c += 4 * NQ) {
-                const float4 v0 = ld_cg4(src + (size_t)c * stride);
-                const float4 v1 = ld_cg4(src + (size_t)(c + NQ) * stride);
-                const float4 v2 = ld_cg4(src + (size_t)(c + 2 * NQ) * stride);
-                const float4 v3 = ld_cg4(src + (size_t)(c + 3 * NQ) * stride);
-                s = f4_add(f4_add(f4_add(f4_add(s, v0), v1), v2), v3);
-            }
-            for (; c < nslots; c += NQ) s = f4_add(s, ld_cg4(src + (size_t)c * stride));
             scr4[q * n4 + j] = s;
         }
         __syncthreads();
@@ -456,15 +445,14 @@ __device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ 
         for (int j = tid; j < n4; j += NT) {
             const float* src = part + p0 + 4 * j;
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            int c = 0;
-            for (; c + 3 < nslots; c += 4) {
-                const float4 v0 = ld_cg4(src + (size_t)c * stride);
-                const float4 v1 = ld_cg4(src + (size_t)(c + 1) * stride);
-                const float4 v2 = ld_cg4(src + (size_t)(c + 2) * stride);
-                const float4 v3 = ld_cg4(src + (size_t)(c + 3) * stride);
-                s = f4_add(f4_add(f4_add(f4_add(s, v0), v1), v2), v3);
+            for (int c = 0; c < nslots; c += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = c + u < nslots ? ld_cg4(src + (size_t)(c + u) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s = f4_add(s, v[u]);
             }
-            for (; c < nslots; ++c) s = f4_add(s, ld_cg4(src + (size_t)c * stride));
             __stcg(reinterpret_cast<float4*>(out + p0 + 4 * j), s);
         }
         __syncthreads();
