@@ -425,12 +425,17 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
+    DiscPrefetch pf;
+    pf.on = a.ntiles <= (int)gridDim.x && 8 * round_up(a.F, 4) <= kStepThreads;
+    pf.valid = false;
+    pf.ei = pf.pi = -1;
+    pf.xe = pf.xp = pf.al = 0.f;
     for (int step = 0; step < a.nsteps; ++step) {
         disc_reg_fill<HQ>(w, img, stage, a.params, a.L, I, threadIdx.x, &fill_bar, (unsigned int)(step & 1));
         pc.lap(0);
         bool acc = false;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-            disc_tile_reg<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc);
+            disc_tile_reg<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
             acc = true;
         }
         pc.lap(1);

@@ -128,11 +128,43 @@ __device__ __forceinline__ void reg_pass(const float (&wreg)[DiscRegW2<HQ>::Q0 *
     for (int j = 0; j < NR; ++j) out[j] += __shfl_xor_sync(0xffffffffu, out[j], 1);
 }
 
+// Tile inputs of the NEXT optimizer step (see PpoPrefetch in sg_ppo.cu): expert / policy feature elements and the mixup
+// alpha of the row my gather element belongs to, fetched while this step's reduce / Adam phase waits on its barriers.
+struct DiscPrefetch {
+    bool on, valid;
+    int ei, pi;           // expert / policy row indices (stage 1), -1 = padding element
+    float xe, xp, al;
+};
+template <class Args>
+__device__ __forceinline__ void disc_prefetch_idx(const Args& a, DiscPrefetch& pf, int step, int tile, int ldf) {
+    const int tid = threadIdx.x;
+    pf.ei = pf.pi = -1;
+    pf.al = 0.f;
+    if (tid < 8 * ldf) {
+        const int r = tid / ldf;
+        const int kind = r / 2, j = r - kind * 2;
+        const int row = a.row_begin + tile * 2 + j;
+        if (kind < 3 && row < a.row_end) {
+            pf.ei = a.eidx[(size_t)step * a.B + row];
+            pf.pi = a.pidx[(size_t)step * a.B + row];
+            pf.al = a.alpha[(size_t)step * a.B + row];
+        }
+    }
+}
+template <class Args>
+__device__ __forceinline__ void disc_prefetch_rows(const Args& a, DiscPrefetch& pf, int ldf) {
+    const int k = threadIdx.x % ldf;
+    const bool ok = pf.ei >= 0 && k < a.F;
+    pf.xe = ok ? a.expert[(size_t)pf.ei * a.F + k] : 0.f;
+    pf.xp = ok ? a.policy[(size_t)pf.pi * a.F + k] : 0.f;
+    pf.valid = true;
+}
+
 // One tile = 2 (expert, policy, mixup) row triples.  `img` = small natural image (DiscRegImage), `w` = W2 slices.
 template <int HQ, class Args>
 __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float* __restrict__ img, const DiscRegImage& I,
                               int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                              DiscRegSmem& sm, bool acc) {
+                              DiscRegSmem& sm, bool acc, DiscPrefetch& pf) {
     constexpr int H = 4 * HQ, TB = 2, R = 8;
     const int tid = threadIdx.x, nth = kStepThreads;
     const int F = a.F, ldf = sm.ldf, ldh = sm.ldh;
@@ -147,20 +179,32 @@ __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float
     const float* W3 = img + I.w3; const float* B3 = img + I.b3;
 
     // ---- S0: rows [e0 e1 | p0 p1 | m0 m1 | 0 0], mixup = alpha*e + (1-alpha)*p (gail.py:72-75) -----------------
-    for (int e = tid; e < R * ldf; e += nth) {
-        const int r = e / ldf, k = e - r * ldf;
-        const int kind = r / TB, j = r - kind * TB;
-        const int row = row0 + j;
-        float x = 0.f;
-        if (kind < 3 && row < a.row_end && k < F) {
-            const float xe = a.expert[(size_t)eidx[row] * F + k];
-            const float xp = a.policy[(size_t)pidx[row] * F + k];
-            const float al = alpha[row];
-            x = kind == 0 ? xe : (kind == 1 ? xp : __fadd_rn(__fmul_rn(al, xe), __fmul_rn(__fsub_rn(1.f, al), xp)));
+    if (pf.valid) {
+        if (tid < R * ldf) {                       // fetched during the previous step's barriers
+            const int kind = (tid / ldf) / TB;
+            const bool ok = pf.ei >= 0 && (tid % ldf) < F;
+            const float mixed = __fadd_rn(__fmul_rn(pf.al, pf.xe), __fmul_rn(__fsub_rn(1.f, pf.al), pf.xp));
+            sm.X[tid] = !ok ? 0.f : (kind == 0 ? pf.xe : (kind == 1 ? pf.xp : mixed));
         }
-        sm.X[e] = x;
+    } else {
+        for (int e = tid; e < R * ldf; e += nth) {
+            const int r = e / ldf, k = e - r * ldf;
+            const int kind = r / TB, j = r - kind * TB;
+            const int row = row0 + j;
+            float x = 0.f;
+            if (kind < 3 && row < a.row_end && k < F) {
+                const float xe = a.expert[(size_t)eidx[row] * F + k];
+                const float xp = a.policy[(size_t)pidx[row] * F + k];
+                const float al = alpha[row];
+                x = kind == 0 ? xe : (kind == 1 ? xp : __fadd_rn(__fmul_rn(al, xe), __fmul_rn(__fsub_rn(1.f, al), xp)));
+            }
+            sm.X[e] = x;
+        }
     }
     __syncthreads();
+    pf.valid = false;
+    const bool pf_next = pf.on && step + 1 < a.nsteps;
+    if (pf_next) disc_prefetch_idx(a, pf, step + 1, tile, ldf);          // stage 1: next step's row indices and alpha
     // rows owned by this lane in 6-row stages: kh, kh+2, kh+4  (e_kh, p_kh, m_kh)
     const int myrows[3] = {kh, kh + 2, kh + 4};
     // ---- S1: layer 1 forward, W1 natural in shared memory -------------------------------------------------------
@@ -346,6 +390,7 @@ __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float
         __stcg(gout + a.L.b3, db3);
         lossout[0] = le; lossout[1] = lp; lossout[2] = gp;
     }
+    if (pf_next) disc_prefetch_rows(a, pf, ldf);                        // stage 2: the feature rows themselves
     __syncthreads();
 }
 

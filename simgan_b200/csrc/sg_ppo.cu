@@ -313,9 +313,42 @@ struct PpoSmemCol {
     }
 };
 
+// Tile inputs of the NEXT optimizer step, fetched into registers while this step's reduce / clip / Adam phases sit in
+// their grid barriers (the sampler permutation of the whole epoch is on the device, and the rollout rows never change
+// during an update): the two dependent L2 round trips of the gather leave the critical path.
+struct PpoPrefetch {
+    bool on;              // usable: one tile per CTA and the gather is a single sweep of the CTA
+    bool valid;           // registers hold the inputs of the step about to run
+    int ix, ia, is;       // sampler indices of the rows my X element / ACT element / row scalars belong to
+    float x, act, ret, vp, olp;
+};
+
+template <int R>
+__device__ __forceinline__ void ppo_prefetch_idx(const PpoArgs& a, PpoPrefetch& pf, int step, int tile, int ldo, int lda) {
+    const int tid = threadIdx.x;
+    const int epoch = step / a.nmb, mb = step - epoch * a.nmb;
+    const int32_t* idx = a.perm + (size_t)epoch * a.S + (size_t)mb * a.mbs;
+    const int row0 = a.row_begin + tile * R;
+    pf.ix = pf.ia = pf.is = -1;
+    if (tid < R * ldo) { const int row = row0 + tid / ldo; if (row < a.row_end) pf.ix = idx[row]; }
+    if (tid < R * lda) { const int row = row0 + tid / lda; if (row < a.row_end) pf.ia = idx[row]; }
+    if (tid >= kStepThreads - R) { const int row = row0 + tid - (kStepThreads - R); if (row < a.row_end) pf.is = idx[row]; }
+}
+template <int R>
+__device__ __forceinline__ void ppo_prefetch_rows(const PpoArgs& a, PpoPrefetch& pf, int ldo, int lda) {
+    const int tid = threadIdx.x;
+    const int kx = tid % ldo, ka = tid % lda;
+    pf.x = (pf.ix >= 0 && kx < a.O) ? a.obs[(size_t)pf.ix * a.O + kx] : 0.f;
+    pf.act = (pf.ia >= 0 && ka < a.A) ? a.actions[(size_t)pf.ia * a.A + ka] : 0.f;
+    pf.ret = pf.is >= 0 ? a.ret[pf.is] : 0.f;
+    pf.vp = pf.is >= 0 ? a.vpred[pf.is] : 0.f;
+    pf.olp = pf.is >= 0 ? a.oldlp[pf.is] : 0.f;
+    pf.valid = true;
+}
+
 template <int R, int RG>
 __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int step, int tile, float* __restrict__ gout,
-                             float* __restrict__ lossout, PpoSmemCol<R>& sm, bool acc) {
+                             float* __restrict__ lossout, PpoSmemCol<R>& sm, bool acc, PpoPrefetch& pf) {
     constexpr int RT = R / RG;            // rows per thread
     constexpr int NC = kHalf / RG;        // column lanes per net
     constexpr int LPR = 32 / R;           // lanes per row in the loss warp
@@ -332,28 +365,45 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
     float* rAdv = sm.ROW + 3 * R;    float* rValid = sm.ROW + 4 * R;
 
     // ---- gather this tile's rows (flat sample id = t*N+n, A2C/storage.py:169-181) ----------------------
-    for (int e = tid; e < R * ldo; e += kStepThreads) {
-        const int r = e / ldo, k = e - r * ldo;
-        const int row = row0 + r;
-        sm.X[e] = (row < a.row_end && k < O) ? a.obs[(size_t)idx[row] * O + k] : 0.f;
-    }
-    for (int e = tid; e < R * lda; e += kStepThreads) {
-        const int r = e / lda, k = e - r * lda;
-        const int row = row0 + r;
-        sm.ACT[e] = (row < a.row_end && k < A) ? a.actions[(size_t)idx[row] * A + k] : 0.f;
-    }
-    if (tid >= kStepThreads - R) {
-        const int r = tid - (kStepThreads - R);
-        const int row = row0 + r;
-        const bool ok = row < a.row_end;
-        const int i = ok ? idx[row] : 0;
-        const float ret = ok ? a.ret[i] : 0.f, vp = ok ? a.vpred[i] : 0.f;
-        rRet[r] = ret; rVp[r] = vp; rOlp[r] = ok ? a.oldlp[i] : 0.f;
-        const float mean = a.advstats[0], sd = a.advstats[1];
-        rAdv[r] = ok ? __fdiv_rn(__fsub_rn(__fsub_rn(ret, vp), mean), __fadd_rn(sd, 1e-5f)) : 0.f;   // ppo.py:66-68
-        rValid[r] = ok ? 1.f : 0.f;
+    if (pf.valid) {
+        // fetched during the previous step's barriers
+        if (tid < R * ldo) sm.X[tid] = pf.x;
+        if (tid < R * lda) sm.ACT[tid] = pf.act;
+        if (tid >= kStepThreads - R) {
+            const int r = tid - (kStepThreads - R);
+            const bool ok = pf.is >= 0;
+            rRet[r] = pf.ret; rVp[r] = pf.vp; rOlp[r] = pf.olp;
+            const float mean = a.advstats[0], sd = a.advstats[1];
+            rAdv[r] = ok ? __fdiv_rn(__fsub_rn(__fsub_rn(pf.ret, pf.vp), mean), __fadd_rn(sd, 1e-5f)) : 0.f;   // ppo.py:66-68
+            rValid[r] = ok ? 1.f : 0.f;
+        }
+    } else {
+        for (int e = tid; e < R * ldo; e += kStepThreads) {
+            const int r = e / ldo, k = e - r * ldo;
+            const int row = row0 + r;
+            sm.X[e] = (row < a.row_end && k < O) ? a.obs[(size_t)idx[row] * O + k] : 0.f;
+        }
+        for (int e = tid; e < R * lda; e += kStepThreads) {
+            const int r = e / lda, k = e - r * lda;
+            const int row = row0 + r;
+            sm.ACT[e] = (row < a.row_end && k < A) ? a.actions[(size_t)idx[row] * A + k] : 0.f;
+        }
+        if (tid >= kStepThreads - R) {
+            const int r = tid - (kStepThreads - R);
+            const int row = row0 + r;
+            const bool ok = row < a.row_end;
+            const int i = ok ? idx[row] : 0;
+            const float ret = ok ? a.ret[i] : 0.f, vp = ok ? a.vpred[i] : 0.f;
+            rRet[r] = ret; rVp[r] = vp; rOlp[r] = ok ? a.oldlp[i] : 0.f;
+            const float mean = a.advstats[0], sd = a.advstats[1];
+            rAdv[r] = ok ? __fdiv_rn(__fsub_rn(__fsub_rn(ret, vp), mean), __fadd_rn(sd, 1e-5f)) : 0.f;   // ppo.py:66-68
+            rValid[r] = ok ? 1.f : 0.f;
+        }
     }
     __syncthreads();
+    pf.valid = false;
+    const bool pf_next = pf.on && step + 1 < a.nsteps;
+    if (pf_next) ppo_prefetch_idx<R>(a, pf, step + 1, tile, ldo, lda);       // stage 1: next step's sampler indices
 
     const int half = tid >> 7, t = tid & (kHalf - 1);
     const int cn = t % NC, r0 = (t / NC) * RT;
@@ -516,19 +566,21 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
         else outer_store<R, 1>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.cb1 : a.L.ab1), dz1t, H, t, kHalf, acc);
     }
+    if (pf_next) ppo_prefetch_rows<R>(a, pf, ldo, lda);                        // stage 2: the rows themselves
     __syncthreads();   // smem is reused by the next tile
 }
 
 template <int R>
-__device__ __forceinline__ void ppo_phaseA_col(const PpoArgs& a, const float* Wi, int step, int cta, int ncta, float* smem) {
+__device__ __forceinline__ void ppo_phaseA_col(const PpoArgs& a, const float* Wi, int step, int cta, int ncta, float* smem,
+                                               PpoPrefetch& pf) {
     PpoSmemCol<R> sm;
     sm.carve(smem, a.O, a.H, a.A);
     bool acc = false;
     for (int tile = cta; tile < a.ntiles; tile += ncta) {
         float* g = a.gpart + (size_t)cta * a.P;
         float* l = a.losspart + cta * 4;
-        if (a.H > 64) ppo_tile_col<R, 1>(a, Wi, step, tile, g, l, sm, acc);
-        else ppo_tile_col<R, 2>(a, Wi, step, tile, g, l, sm, acc);
+        if (a.H > 64) ppo_tile_col<R, 1>(a, Wi, step, tile, g, l, sm, acc, pf);
+        else ppo_tile_col<R, 2>(a, Wi, step, tile, g, l, sm, acc, pf);
         acc = true;
     }
 }
@@ -706,13 +758,18 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     const bool own1 = a.SL <= kStepThreads && a.SL <= 512;      // narrow slice, one parameter per thread
+    PpoPrefetch pf;
+    pf.on = RESIDENT == 2 && a.ntiles <= (int)gridDim.x && R * round_up(a.O, 4) <= kStepThreads && R * round_up(a.A, 4) <= kStepThreads - R;
+    pf.valid = false;
+    pf.ix = pf.ia = pf.is = -1;
+    pf.x = pf.act = pf.ret = pf.vp = pf.olp = 0.f;
     for (int step = 0; step < a.nsteps; ++step) {
         float4 mine;
         bool have;
         if (RESIDENT == 2) {
             load_policy_image(Ws, stage, a.params, a.L, a.LI, a.H, threadIdx.x, &img_bar, (unsigned int)(step & 1));
             pc.lap(0);
-            ppo_phaseA_col<R>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+            ppo_phaseA_col<R>(a, Ws, step, blockIdx.x, gridDim.x, tile, pf);
             pc.lap(1);
             gb.sync();
             pc.lap(2);
