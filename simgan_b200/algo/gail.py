@@ -156,19 +156,23 @@ class Discriminator(nn.Module):
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
             self.__dict__["_ws"] = ws
-        # cached pinned staging block: [expert_idx | policy_idx] int32 and alpha fp32
+        # ONE cached pinned staging block and ONE async H2D copy per call:
+        # int32 words [expert_idx (n,B) | policy_idx (n,B) | alpha bits (n,B) | Adam step sizes (n) | sqrt(1-beta2^t) (n)]
+        nb = n * B
+        words = 3 * nb + 2 * n
         st = self.__dict__.get("_stage")
-        if st is None or st[0].shape != (2, n, B) or st[2].device != dev:
-            st = (torch.empty(2, n, B, dtype=torch.int32).pin_memory(), torch.empty(n, B, dtype=torch.float32).pin_memory(),
-                  torch.empty(2, n, B, dtype=torch.int32, device=dev), torch.empty(n, B, dtype=torch.float32, device=dev))
+        if st is None or st[0].numel() != words or st[1].device != dev:
+            st = (torch.empty(words, dtype=torch.int32).pin_memory(), torch.empty(words, dtype=torch.int32, device=dev))
             self.__dict__["_stage"] = st
-        stage_i, stage_a, idx_dev, alpha_dev = st
-        stage_i[0].copy_(e_idx)
-        stage_i[1].copy_(p_idx)
-        stage_a.copy_(alpha)
-        idx_dev.copy_(stage_i, non_blocking=True)
-        alpha_dev.copy_(stage_a, non_blocking=True)
-        sched = torch.from_numpy(opt.schedule(n)).to(dev)
+        stage, stage_dev = st
+        stage[:nb].view(n, B).copy_(e_idx)
+        stage[nb:2 * nb].view(n, B).copy_(p_idx)
+        stage[2 * nb:3 * nb].view(torch.float32).view(n, B).copy_(alpha)
+        stage[3 * nb:].view(torch.float32).copy_(torch.from_numpy(opt.schedule(n)).reshape(-1))
+        stage_dev.copy_(stage, non_blocking=True)
+        idx_dev = stage_dev[:2 * nb].view(2, n, B)
+        alpha_dev = stage_dev[2 * nb:3 * nb].view(torch.float32)
+        sched = stage_dev[3 * nb:].view(torch.float32).view(2, n)
         trace = torch.empty(n, 3, device=dev)
         cb, user = _lib.NULL_ALLREDUCE, None
         if self.dp is not None and not p2p:
