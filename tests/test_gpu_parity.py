@@ -587,3 +587,39 @@ def test_rollout_feeder_matches_act_insert():
         nv = pol.get_value(rs_a.obs[-1], None, None)
     assert torch.equal(rs_b.value_preds[-1], nv)             # slot T already holds next_value
     assert rs_b.step == rs_a.step == 0
+
+
+# ------------------------------------------------------------------------------------ remaining API surface
+def test_legacy_discriminator_update_and_mod_reward():
+    """Discriminator.update (the (state, action)-split form, gail.py:91-152) maps onto the same kernel over
+    concatenated rows; RolloutStorage.mod_reward (storage.py:86-94) adds an offset to the last slots."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from oracle.ref_shim import BoxSpace
+    torch.manual_seed(0)
+    T, N, O, A = 20, 4, 6, 3
+    p = orc.init_policy(O, 16, A)
+    buf = orc.synth_rollout(T, N, O, A, 2, p, seed=5)
+    rs = gu.make_storage(buf, O, A, 2)
+    dpar = orc.init_disc(O + A, 48)
+    d = gu.make_disc(dpar, O + A, 48)
+    es, ea = torch.randn(64, O), torch.randn(64, A)
+    loader = DataLoader(TensorDataset(es.to(gu.DEV), ea.to(gu.DEV)), batch_size=16, shuffle=True, drop_last=True)
+    # oracle: the same update on the concatenated matrices with the same streams
+    expert = torch.cat([es, ea], 1)
+    fl = orc.flat_views(buf)
+    pol_rows = torch.cat([fl["obs"], fl["actions"]], 1)
+    torch.manual_seed(3)
+    e_idx, p_idx, alpha = sg.Discriminator.draw_epoch_indices(64, 16, True, T * N)
+    ora = orc.DiscOracle(dpar)
+    tot = [0.0, 0.0, 0.0]
+    for i in range(e_idx.shape[0]):
+        out = ora.step(expert[e_idx[i]], pol_rows[p_idx[i]], alpha[i].view(-1, 1))
+        tot = [a + b for a, b in zip(tot, out)]
+    torch.manual_seed(3)
+    got = d.update(loader, rs)
+    assert all(abs(a - b / e_idx.shape[0]) <= 1e-4 * abs(b / e_idx.shape[0]) for a, b in zip(got, tot))
+    before = rs.rewards.clone()
+    rs.step = 3
+    rs.mod_reward(torch.full((N,), 0.5, device=gu.DEV), 2)
+    assert torch.equal(rs.rewards[2], before[2] + 0.5) and torch.equal(rs.rewards[1], before[1] + 0.5)
+    assert torch.equal(rs.rewards[0], before[0]) and torch.equal(rs.rewards[3], before[3])
