@@ -7,9 +7,11 @@
 //                           phase A (tile: forward / double backward -> per-CTA partial gradient), grid
 //                           barrier, phase B (CTA c sums slice c of the partials in a fixed order and
 //                           applies Adam to that slice -- the discriminator has no gradient clipping, so
-//                           no global norm is needed), grid barrier.  In the "resident" variant (mode 0
-//                           when it fits in shared memory) every CTA then refreshes a private shared-memory
-//                           image of the parameters and reads its weights from there in the tile phase.
+//                           no global norm is needed), grid barrier.  Variants: register-resident
+//                           (disc_reg_kernel, sg_disc_reg.cuh: hidden widths 48/64/100/128; W2 lives in
+//                           registers, refreshed through a TMA-staged shared copy after every Adam step),
+//                           resident (natural shared-memory image), persistent (weights through L2) and
+//                           phased (one launch per phase; NCCL data-parallel path).
 //   sg_disc_predict_reward  predict_reward_combined (gail.py:201-210) for one (N,F) block
 //   sg_disc_relabel         the whole T-step relabel loop of main_gail_dyn_ppo.py:275-297, including the
 //                           float64 RunningMeanStd merge (baselines/common/running_mean_std.py:33-56),

@@ -6,17 +6,20 @@
 //                     loss -> hand-derived backward -> per-CTA partial gradient (P floats) in L2
 //   B  reduce-scatter CTA c sums slice c of all partial gradients in a fixed order -> flat gradient,
 //                     plus the slice's sum of squares (fp64) for the global norm
-//                     [data-parallel mode: the sum-allreduce of the flat gradient happens after B]
+//                     [data parallel, nccl: the sum-allreduce of the flat gradient happens after B]
 //   C  clip + Adam    global-norm clip (A2C/algo/ppo.py:143-144) + Adam (ppo.py:145)
 //
-// Kernel variants (sg_ppo_config.mode):
-//   resident   (mode 0 when it fits, mode 3 forced) ONE persistent cooperative kernel for all steps of
-//              the call, three grid barriers per step; every CTA refreshes a private shared-memory image
-//              of the flat parameter vector after each Adam step and the tile phase reads its weights
-//              from shared memory.
-//   persistent (mode 0 otherwise, mode 2 forced) same single launch, weights read from global through L2.
-//   phased     (mode 1) one launch per phase; the data-parallel path (host allreduce callback).
-// All three run the same arithmetic in the same order and are bit-identical.
+//                     [data parallel, p2p: the slice is exchanged with the peers inside B (sg_dp.cuh)]
+//
+// Kernel variants (sg_ppo_config.mode), all one persistent cooperative launch per call except `phased`:
+//   resident   (mode 0 when it fits, mode 3 forced) every CTA refreshes a private shared-memory image of the
+//              parameters after each Adam step (TMA bulk copies) and the tile phase reads its weights from shared
+//              memory.  H % 4 == 0: the column-owner tile (ppo_tile_col, W2 in the NQ layout); otherwise the
+//              generic tile on a natural image.
+//   persistent (mode 0 otherwise, mode 2 forced) weights read from global memory through L2, generic tile.
+//   phased     (mode 1) one launch per phase; the NCCL data-parallel path (host allreduce callback).
+// persistent and phased run the same arithmetic in the same order (bit-identical); the column-owner tile sums in
+// another order and agrees to fp32 reassociation.
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
 #include "sg_colgemm.cuh"
