@@ -623,3 +623,28 @@ def test_legacy_discriminator_update_and_mod_reward():
     rs.mod_reward(torch.full((N,), 0.5, device=gu.DEV), 2)
     assert torch.equal(rs.rewards[2], before[2] + 0.5) and torch.equal(rs.rewards[1], before[1] + 0.5)
     assert torch.equal(rs.rewards[0], before[0]) and torch.equal(rs.rewards[3], before[3])
+
+
+def test_disc_hidden_width_without_register_kernel():
+    """Hidden widths other than 48/64/100/128 take the shared-memory-resident generic tile (disc_persistent_kernel<true>);
+    odd feature / hidden sizes exercise the scalar (non-float4) micro-kernel paths."""
+    from torch.utils.data import DataLoader, TensorDataset
+    for F_, HD in ((9, 40), (7, 30)):
+        torch.manual_seed(F_)
+        dpar = orc.init_disc(F_, HD)
+        expert = torch.randn(80, F_)
+        buf = orc.synth_rollout(30, 2, 4, 2, F_, orc.init_policy(4, 16, 2), seed=F_)
+        loader = DataLoader(TensorDataset(expert.to(gu.DEV)), batch_size=16, shuffle=True, drop_last=True)
+        outs = []
+        for mode in (0, 1):
+            d = gu.make_disc(dpar, F_, HD)
+            d.kernel_mode = mode
+            rs = gu.make_storage(buf, 4, 2, F_)
+            torch.manual_seed(21)
+            outs.append((d.update_gail_dyn(loader, rs), d.last_trace.clone(), d.flat_params().cpu().clone()))
+        ora = orc.DiscOracle(dpar)
+        torch.manual_seed(21)
+        out_o = ora.update_epoch(expert, buf, batch_size=16)
+        for got in outs:
+            assert all(abs(a - b) <= LOSS_RTOL * abs(b) for a, b in zip(got[0], out_o)), (got[0], out_o)
+        assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])     # same tile code: bit-identical
