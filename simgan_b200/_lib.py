@@ -114,6 +114,24 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+_readback = {}
+
+
+def read_back(t):
+    """Device tensor -> fresh host tensor through a cached pinned buffer: one async copy and one stream sync."""
+    import torch
+    key = (tuple(t.shape), t.dtype)
+    buf = _readback.get(key)
+    if buf is None:
+        if len(_readback) > 64:
+            _readback.clear()
+        buf = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        _readback[key] = buf
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.clone()
+
+
 def policy_layout(obs_dim, hidden, act_dim):
     offs = (C.c_int * 13)()
     total = lib().sg_policy_layout(obs_dim, hidden, act_dim, offs)

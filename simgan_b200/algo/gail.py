@@ -11,12 +11,13 @@ generator in exactly the order ``zip(DataLoader, feed_forward_generator)`` consu
 (main_gail_dyn_ppo.py:275-297): one device pass instead of T launches with three host syncs each.
 """
 import ctypes as C
+import math
 
 import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _lib
+from .. import _lib, _spec
 from ..running_mean_std import RunningMeanStd
 from .adam import FusedAdam
 
@@ -77,7 +78,8 @@ class Discriminator(nn.Module):
         state.pop("_prof_view", None)
         state.pop("_rms_dev", None)
         state.pop("_predraw", None)
-        state.pop("_stage", None)
+        for k in ("_stage", "_stage_cur", "_side_upload", "_copy_stream", "_last_key", "_relabel_ws"):
+            state.pop(k, None)
         return state
 
     # ---- update --------------------------------------------------------------------------------------------
@@ -110,27 +112,70 @@ class Discriminator(nn.Module):
         return (e_perm[:n * batch_size].view(n, batch_size), p_perm[:n * batch_size].view(n, batch_size),
                 alpha.view(n, batch_size))
 
-    # ---- speculative index draws ---------------------------------------------------------------------------------
-    # The caller runs gail_epoch back-to-back epochs (main_gail_dyn_ppo.py:255-256).  While the kernel of one epoch
-    # runs, the host draws the streams the NEXT call would draw -- then rewinds the CPU generator, so nothing has
-    # been consumed as far as any other code can tell.  The next call takes the pre-drawn streams only if the
-    # generator is still exactly where the speculation started (and the sizes match) and then fast-forwards it to
-    # where the reference's own draws would have left it; otherwise the speculation is discarded.
-    def _speculate_next_draw(self, *key):
-        before = torch.get_rng_state()
-        draw = self.draw_epoch_indices(*key)
-        after = torch.get_rng_state()
-        torch.set_rng_state(before)
-        self.__dict__["_predraw"] = (key, before, after, draw)
+    # ---- early index draws (simgan_b200/_spec.py) -----------------------------------------------------------------
+    # The caller runs gail_epoch back-to-back epochs (main_gail_dyn_ppo.py:255-256).  While a kernel runs, the host
+    # draws the streams the NEXT call would draw, stages them in the idle one of two pinned blocks and uploads that
+    # block on a side stream -- then rewinds the CPU generator.  The next call uses the staged block only if the
+    # generator is still exactly where the early draw started and the Adam schedule it baked in is still the right
+    # one; otherwise it is discarded and the call draws / stages as usual.
+    def _speculate(self):
+        key = self.__dict__.get("_last_key")
+        flat = self.__dict__.get("_flat")
+        if key is None or flat is None or _spec.still_valid(self.__dict__.get("_predraw"), key):
+            return
+        slot = _spec.predraw(key, lambda: self.draw_epoch_indices(*key))
+        if slot is None:
+            return
+        e_idx, p_idx, alpha = slot[3]
+        staged = self._fill_stage(flat.device, e_idx, p_idx, alpha, side_stream=True)
+        self.__dict__["_predraw"] = slot[:3] + ((e_idx, p_idx, alpha, staged),)
 
     def _take_or_draw(self, key):
-        pre = self.__dict__.pop("_predraw", None)
-        if pre is not None and pre[0] == key and torch.equal(torch.get_rng_state(), pre[1]):
-            torch.set_rng_state(pre[2])
-            return pre[3]
-        return self.draw_epoch_indices(*key)
+        _spec.consumed(self)
+        self.__dict__["_last_key"] = key
+        got = _spec.take(self.__dict__.pop("_predraw", None), key)
+        return got if got is not None else self.draw_epoch_indices(*key) + (None,)
 
-    def _run_update(self, expert, policy_feat, e_idx, p_idx, alpha, speculate=None):
+    def _sched_sig(self, n):
+        g = self.optimizer.param_groups[0]
+        return (self.optimizer.step_count + 1, n, g["lr"], tuple(g["betas"]))
+
+    def _fill_stage(self, dev, e_idx, p_idx, alpha, side_stream=False):
+        """Fill the idle staging pair and start its upload:
+        int32 words [expert_idx (n,B) | policy_idx (n,B) | alpha bits (n,B) | Adam step sizes (n) | sqrt(1-beta2^t) (n)].
+        Returns (pair index, schedule signature, upload-done event or None)."""
+        n, B = e_idx.shape
+        nb = n * B
+        words = 3 * nb + 2 * n
+        pairs = self.__dict__.setdefault("_stage", [None, None])
+        which = 1 - self.__dict__.get("_stage_cur", 1)
+        pending = self.__dict__.pop("_side_upload", None)
+        if pending is not None:
+            pending.synchronize()       # an abandoned early upload may still be reading / writing this pair
+        st = pairs[which]
+        if st is None or st[0].numel() != words or st[1].device != dev:
+            st = (torch.empty(words, dtype=torch.int32).pin_memory(), torch.empty(words, dtype=torch.int32, device=dev))
+            pairs[which] = st
+        stage, stage_dev = st
+        stage[:nb].view(n, B).copy_(e_idx)
+        stage[nb:2 * nb].view(n, B).copy_(p_idx)
+        stage[2 * nb:3 * nb].view(torch.float32).view(n, B).copy_(alpha)
+        stage[3 * nb:].view(torch.float32).copy_(torch.from_numpy(self.optimizer.schedule(n)).reshape(-1))
+        event = None
+        if side_stream:
+            cs = self.__dict__.get("_copy_stream")
+            if cs is None or cs.device != dev:
+                cs = torch.cuda.Stream(dev)
+                self.__dict__["_copy_stream"] = cs
+            with torch.cuda.stream(cs):
+                stage_dev.copy_(stage, non_blocking=True)
+                event = cs.record_event()
+            self.__dict__["_side_upload"] = event
+        else:
+            stage_dev.copy_(stage, non_blocking=True)
+        return which, self._sched_sig(n), event
+
+    def _run_update(self, expert, policy_feat, e_idx, p_idx, alpha, staged=None):
         flat = self.flat_params()
         dev = flat.device
         n, B = e_idx.shape
@@ -156,20 +201,17 @@ class Discriminator(nn.Module):
         if ws is None or ws.numel() < need or ws.device != dev:
             ws = torch.empty(int(need), dtype=torch.uint8, device=dev)
             self.__dict__["_ws"] = ws
-        # ONE cached pinned staging block and ONE async H2D copy per call:
-        # int32 words [expert_idx (n,B) | policy_idx (n,B) | alpha bits (n,B) | Adam step sizes (n) | sqrt(1-beta2^t) (n)]
+        # ONE pinned staging block and ONE async H2D copy per call -- already done when the draw was made early
+        pairs = self.__dict__.get("_stage")
+        if (staged is not None and staged[1] == self._sched_sig(n) and pairs is not None
+                and pairs[staged[0]] is not None and pairs[staged[0]][1].device == dev):
+            torch.cuda.current_stream().wait_event(staged[2])
+            which = staged[0]
+        else:
+            which = self._fill_stage(dev, e_idx, p_idx, alpha)[0]
+        self.__dict__["_stage_cur"] = which
+        stage_dev = self.__dict__["_stage"][which][1]
         nb = n * B
-        words = 3 * nb + 2 * n
-        st = self.__dict__.get("_stage")
-        if st is None or st[0].numel() != words or st[1].device != dev:
-            st = (torch.empty(words, dtype=torch.int32).pin_memory(), torch.empty(words, dtype=torch.int32, device=dev))
-            self.__dict__["_stage"] = st
-        stage, stage_dev = st
-        stage[:nb].view(n, B).copy_(e_idx)
-        stage[nb:2 * nb].view(n, B).copy_(p_idx)
-        stage[2 * nb:3 * nb].view(torch.float32).view(n, B).copy_(alpha)
-        stage[3 * nb:].view(torch.float32).copy_(torch.from_numpy(opt.schedule(n)).reshape(-1))
-        stage_dev.copy_(stage, non_blocking=True)
         idx_dev = stage_dev[:2 * nb].view(2, n, B)
         alpha_dev = stage_dev[2 * nb:3 * nb].view(torch.float32)
         sched = stage_dev[3 * nb:].view(torch.float32).view(2, n)
@@ -186,19 +228,18 @@ class Discriminator(nn.Module):
         _lib.check(rc, "sg_disc_update")
         opt.step_count += n
         self.__dict__["_prof_view"] = (ws, int(lib.sg_disc_phase_cycles_offset(C.byref(cfg))))
-        if speculate is not None:
-            self._speculate_next_draw(*speculate)     # host draws the next epoch's streams while the GPU runs this one
         if p2p:
             self.dp.sum_trace_(trace, 3)      # all three loss columns are per-rank partial sums
-        tr = trace.cpu()
-        if not bool(torch.isfinite(tr).all()):
-            raise _lib.SgError("sg_disc_update produced non-finite losses (grid barrier timeout or diverged update)")
+        _spec.host_idle()                     # the next consumer of the CPU generator draws while the GPU runs this epoch
+        tr = _lib.read_back(trace)
         self.last_trace = tr
         lt = le = lp = 0.0
         for row in tr.tolist():
             lt += row[0]
             le += row[1]
             lp += row[2]
+        if not (math.isfinite(lt) and math.isfinite(le) and math.isfinite(lp)):
+            raise _lib.SgError("sg_disc_update produced non-finite losses (grid barrier timeout or diverged update)")
         return lt / n, le / n, lp / n
 
     def phase_cycles(self):
@@ -216,7 +257,8 @@ class Discriminator(nn.Module):
         (main_gail_dyn_ppo.py:165-175); its dataset tensor is used in place on the device and its
         batch_size / drop_last drive the index emulation.  ``replay`` = (expert_idx, policy_idx, alpha)
         bypasses the generator (parity tests)."""
-        self.train()
+        if not self.training:
+            self.train()
         expert = expert_loader.dataset.tensors[0]
         if not expert.is_cuda or not rollouts.obs_feat.is_cuda:
             raise _lib.SgError("update_gail_dyn needs the expert set and the rollout buffer on the CUDA device")
@@ -226,14 +268,14 @@ class Discriminator(nn.Module):
         F = rollouts.obs_feat.shape[-1]
         assert expert.shape[1] == F == self.feat_dim
         policy_feat = rollouts.obs_feat[1:].reshape(S, F)       # next_obs_feat rows (storage.py:172, gail.py:166)
-        key = None
+        staged = None
         if replay is None:
             key = (expert.shape[0], expert_loader.batch_size, bool(expert_loader.drop_last), S)
-            e_idx, p_idx, alpha = self._take_or_draw(key)
+            e_idx, p_idx, alpha, staged = self._take_or_draw(key)
         else:
             e_idx, p_idx, alpha = [x if torch.is_tensor(x) else torch.stack([torch.as_tensor(r).reshape(-1) for r in x])
                                    for x in replay]
-        return self._run_update(expert, policy_feat, e_idx, p_idx, alpha, speculate=key)
+        return self._run_update(expert, policy_feat, e_idx, p_idx, alpha, staged)
 
     def update(self, expert_loader, rollouts, obsfilt=None, is_gail_dyn=False, a_dim=None):
         """Legacy (state, action)-split variant (gail.py:91-152): the D input is cat([state, action]) on
@@ -314,7 +356,11 @@ class Discriminator(nn.Module):
         if not has:
             self.returns = torch.zeros(N, 1, device=dev)
         lib = _lib.lib()
-        ws = torch.empty(int(lib.sg_relabel_workspace_bytes(T, N)), dtype=torch.uint8, device=dev)
+        need = int(lib.sg_relabel_workspace_bytes(T, N))
+        ws = self.__dict__.get("_relabel_ws")
+        if ws is None or ws.numel() < need or ws.device != dev:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            self.__dict__["_relabel_ws"] = ws
         rms_dev = torch.tensor([float(ret_rms.mean), float(ret_rms.var), float(ret_rms.count)], dtype=torch.float64,
                                device=dev)
         mean_returns = torch.empty(T, device=dev)
@@ -327,6 +373,7 @@ class Discriminator(nn.Module):
         _lib.check(rc, "sg_disc_relabel")
         self.__dict__["_rms_dev"] = rms_dev
         if sync:
+            _spec.host_idle()
             self.sync_rms(ret_rms)
         return mean_returns
 

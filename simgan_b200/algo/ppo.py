@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, _spec
 from .adam import FusedAdam
 
 
@@ -43,6 +43,9 @@ class PPO(object):
         self._ws = None
         self._stage = None
         self._perm_dev = None
+        self._predraw = None            # early draw of the next update's first sampler permutation (_spec.py)
+        self._last_S = None
+        self._sched_cache = None
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _workspace(self, cfg, dev, split=False):
@@ -62,6 +65,22 @@ class PPO(object):
         for e in range(n):
             out[e].copy_(torch.randperm(S))
         return out
+
+    def _speculate(self):
+        """Draw the next update's first sampler permutation early and rewind the generator (_spec.py)."""
+        S = self._last_S
+        if S is None or _spec.still_valid(self._predraw, S):
+            return
+        self._predraw = _spec.predraw(S, lambda: torch.randperm(S))
+        self._schedule(self.ppo_epoch * self.num_mini_batch)      # pure host arithmetic; cached by its inputs
+
+    def _schedule(self, n_steps):
+        """Adam step-size scalars of the next n_steps (FusedAdam.schedule), cached by everything they depend on."""
+        g = self.optimizer.param_groups[0]
+        sig = (self.optimizer.step_count, n_steps, g["lr"], tuple(g["betas"]))
+        if self._sched_cache is None or self._sched_cache[0] != sig:
+            self._sched_cache = (sig, torch.from_numpy(self.optimizer.schedule(n_steps)))
+        return self._sched_cache[1]
 
     def phase_cycles(self):
         """Diagnostics: per-phase SM-clock totals of CTA 0 of the last persistent launch
@@ -123,7 +142,7 @@ class PPO(object):
         # Adam scalars -> device; sampler index stream: one torch.randperm(S) per epoch on the CPU default generator
         # (storage.py:158-162).  Epochs are launched one by one so that the host draws epoch e+1 while the GPU
         # runs epoch e (the launches are asynchronous; nothing below synchronises until the trace is read).
-        sched = torch.from_numpy(opt.schedule(n_steps)).to(dev)
+        sched = self._schedule(n_steps).to(dev)
         trace = torch.empty(n_steps, 4, device=dev)
         nmb = self.num_mini_batch
         if self._stage is None or self._stage.shape != (self.ppo_epoch, S):
@@ -138,9 +157,17 @@ class PPO(object):
         cb, user = _lib.NULL_ALLREDUCE, None
         if self.dp is not None and not p2p:
             cb = self.dp.make_callback(ws)
+        first = None
+        if permutations is None:
+            _spec.consumed(self)
+            self._last_S = S
+            first, self._predraw = _spec.take(self._predraw, S), None
         cfg.ppo_epoch = 1
         for e in range(self.ppo_epoch):
-            self._stage[e].copy_(torch.randperm(S) if permutations is None else permutations[e])
+            if permutations is not None:
+                self._stage[e].copy_(permutations[e])
+            else:
+                self._stage[e].copy_(first if (e == 0 and first is not None) else torch.randperm(S))
             self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
             cfg.first_adam_step = opt.step_count + 1 + e * nmb
             tok = _lib.timer.start("ppo_update")
@@ -157,7 +184,8 @@ class PPO(object):
         self._prof_view = (ws, 0 if is_split else int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
         if p2p:
             self.dp.sum_trace_(trace, 2)      # value / action loss columns are per-rank partial sums
-        tr = trace.cpu()            # the one host sync of the update
+        _spec.host_idle()           # the next consumer of the CPU generator draws while the last epoch runs
+        tr = _lib.read_back(trace)  # the one host sync of the update
         if not bool(torch.isfinite(tr).all()):
             raise _lib.SgError("sg_ppo_update produced non-finite losses (grid barrier timeout or diverged update)")
         self.last_trace = tr

@@ -648,3 +648,54 @@ def test_disc_hidden_width_without_register_kernel():
         for got in outs:
             assert all(abs(a - b) <= LOSS_RTOL * abs(b) for a, b in zip(got[0], out_o)), (got[0], out_o)
         assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])     # same tile code: bit-identical
+
+
+@pytest.mark.parametrize("perturb", [False, True])
+def test_early_draws_do_not_change_results(perturb):
+    """Three outer iterations (D x 3 -> relabel -> GAE -> PPO) with the early index draws of simgan_b200/_spec.py on
+    and off: identical parameters, per-step traces and CPU generator state; the early path must actually have been
+    taken (staged block used) in the steady state, and a caller that consumes the generator between calls voids it."""
+    from torch.utils.data import DataLoader, TensorDataset
+    from simgan_b200 import _spec
+    g = Golden(CASES[0])
+
+    def run(enabled):
+        _spec.reset()
+        _spec.enabled = enabled
+        pol = gu.make_policy(g.policy(), g.O, g.H, g.A)
+        agent = sg.PPO(pol, 0.2, g.ppo_epoch, g.nmb, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+        d = gu.make_disc(g.disc(), g.F, g.HD)
+        rs = gu.make_storage(g.buffer(), g.O, g.A, g.F)
+        expert = g.t("expert").to(gu.DEV)
+        loader = DataLoader(TensorDataset(expert), batch_size=g.gail_batch, shuffle=True,
+                            drop_last=len(expert) > g.gail_batch)
+        rms = sg.RunningMeanStd(shape=())
+        torch.set_rng_state(g.t("rng_before_disc"))
+        traces, taken = [], 0
+        for it in range(3):
+            with torch.no_grad():
+                nv = pol.get_value(rs.obs[-1], rs.recurrent_hidden_states[-1], rs.masks[-1]).detach()
+            for e in range(3):
+                pre = d.__dict__.get("_predraw")
+                taken += int(_spec.still_valid(pre, d.__dict__.get("_last_key")))
+                d.update_gail_dyn(loader, rs)
+                traces.append(d.last_trace.clone())
+                if perturb and it == 1 and e == 1:
+                    torch.rand(2)
+            d.relabel_rollout(rs, 0.99, 0.1, rms)
+            rs.compute_returns(nv, True, 0.99, 0.95, True)
+            taken += int(_spec.still_valid(agent._predraw, agent._last_S))
+            agent.update(rs)
+            traces.append(agent.last_trace.clone())
+            rs.after_update()
+        return traces, pol.flat_params().cpu().clone(), d.flat_params().cpu().clone(), torch.get_rng_state(), taken
+
+    try:
+        t0, p0, d0, s0, k0 = run(False)
+        t1, p1, d1, s1, k1 = run(True)
+    finally:
+        _spec.enabled = True
+        _spec.reset()
+    assert k0 == 0 and k1 >= (5 if perturb else 6), (k0, k1)
+    assert torch.equal(s0, s1) and torch.equal(p0, p1) and torch.equal(d0, d1)
+    assert len(t0) == len(t1) and all(torch.equal(a, b) for a, b in zip(t0, t1))

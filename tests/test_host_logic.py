@@ -253,3 +253,72 @@ def test_expert_tensor_reproduces_the_committed_fixture():
     torch.manual_seed(0)
     x = sg.expert_tensor(os.path.join(ref_shim.REF_ROOT, "hopper_new11_deform_n200_3.pkl"), "cpu")
     assert np.array_equal(x.numpy(), np.load(os.path.join(GOLDEN_DIR, "hopper_expert_sas_f32.npy")))
+
+
+class _FakeConsumer(object):
+    def __init__(self, n):
+        self.n, self.slot, self.early = n, None, 0
+
+    def _speculate(self):
+        from simgan_b200 import _spec
+        if not _spec.still_valid(self.slot, self.n):
+            self.slot = _spec.predraw(self.n, lambda: torch.randperm(self.n))
+            self.early += 1
+
+    def call(self):
+        from simgan_b200 import _spec
+        _spec.consumed(self)
+        got, self.slot = _spec.take(self.slot, self.n), None
+        out = got if got is not None else torch.randperm(self.n)
+        _spec.host_idle()
+        return out, got is not None
+
+
+def test_early_draws_leave_the_generator_stream_unchanged():
+    """_spec: draws made early + rewind are indistinguishable from late draws, the predictor learns the
+    D x k -> PPO -> D ... order, and a caller that touches the generator in between just voids the early draw."""
+    from simgan_b200 import _spec
+
+    def run(enabled, perturb):
+        _spec.reset()
+        _spec.enabled = enabled
+        torch.manual_seed(5)
+        d, p = _FakeConsumer(37), _FakeConsumer(101)
+        outs, hits = [], 0
+        for it in range(4):
+            for _ in range(3):
+                o, h = d.call(); outs.append(o); hits += h
+            if perturb and it == 2:
+                outs.append(torch.rand(3))
+            o, h = p.call(); outs.append(o); hits += h
+        return outs, hits, torch.get_rng_state()
+
+    try:
+        base, hits0, st0 = run(False, False)
+        spec, hits1, st1 = run(True, False)
+        assert hits0 == 0 and hits1 >= 10                  # steady state: every draw after the first iteration is early
+        assert torch.equal(st0, st1) and all(torch.equal(a, b) for a, b in zip(base, spec))
+        base, _, st0 = run(False, True)
+        spec, _, st1 = run(True, True)
+        assert torch.equal(st0, st1) and all(torch.equal(a, b) for a, b in zip(base, spec))
+    finally:
+        _spec.enabled = True
+        _spec.reset()
+
+
+def test_predraw_swallows_errors_and_rewinds():
+    from simgan_b200 import _spec
+    torch.manual_seed(1)
+    before = torch.get_rng_state()
+
+    def boom():
+        torch.rand(4)
+        raise ZeroDivisionError("as gail.py:193 would")
+    assert _spec.predraw("k", boom) is None
+    assert torch.equal(torch.get_rng_state(), before)
+    slot = _spec.predraw("k", lambda: torch.rand(2))
+    assert torch.equal(torch.get_rng_state(), before)
+    assert _spec.take(slot, "other") is None and torch.equal(torch.get_rng_state(), before)
+    got = _spec.take(slot, "k")
+    torch.set_rng_state(before)
+    assert torch.equal(got, torch.rand(2))
