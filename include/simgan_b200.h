@@ -232,6 +232,13 @@ int sg_relabel_normalize(const float* raw_reward, const float* masks, float* rew
                          float* disc_returns, int has_returns, double* rms_state, float* mean_returns, void* workspace,
                          void* stream);
 
+/* Diagnostics (no reference counterpart): the relabel's RunningMeanStd chain divides through a precomputed
+ * correctly-rounded reciprocal plus two fused residual corrections instead of three plain IEEE divisions per step.
+ * This compares that division with the plain one on blocks*256*per_thread pseudo-random operand pairs, divisors
+ * log-uniform in [b_lo, b_hi]; *mismatches (DEVICE pointer, one uint64, caller-zeroed) receives the count. */
+int sg_selftest_division(uint64_t seed, int blocks, int per_thread, double b_lo, double b_hi, uint64_t* mismatches,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

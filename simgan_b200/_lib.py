@@ -78,6 +78,7 @@ SIGNATURES = {
     "sg_relabel_workspace_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "sg_disc_relabel": (C.c_int, [c_void, C.c_int, C.c_int, c_void, c_void, c_void, C.c_int, C.c_int, C.c_double,
                                   C.c_double, c_void, C.c_int, c_void, c_void, c_void, c_void]),
+    "sg_selftest_division": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double, c_void, c_void]),
     "sg_relabel_normalize": (C.c_int, [c_void, c_void, c_void, C.c_int, C.c_int, C.c_double, c_void, C.c_int, c_void,
                                        c_void, c_void, c_void]),
 }

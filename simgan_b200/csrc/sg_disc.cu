@@ -598,43 +598,126 @@ __global__ void __launch_bounds__(128) relabel_moments_kernel(const float* __res
 }
 
 // the sequential float64 Chan merge (running_mean_std.py:45-56); scale[t] = sqrt(var_t + 1e-7).
-// The chain itself is inherently serial (one thread); the other threads of the CTA stage the per-step batch
-// moments in shared memory, a chunk ahead, so that no global-memory latency sits inside the chain.
-constexpr int kRmsChunk = 1024;
+//
+// The merge is an inherently serial chain over the T steps (one thread), and in its plain form every step carries
+// three IEEE divisions by tot_t = count_t + N and one square root: ~500 cycles per step, all dependent.  Everything
+// that does not depend on the running mean / variance is therefore taken OFF the chain, per chunk of steps:
+//   1. thread 0 walks the count chain alone (tot_t depends on nothing else);
+//   2. all threads form r_t = RN(1/tot_t) (__drcp_rn) and the batch second moments in parallel;
+//   3. thread 0 walks the mean / variance chain, dividing with div_rcp(): q = a*r followed by two fused residual
+//      corrections q += (a - q*tot)*r.  With r the correctly rounded reciprocal and the first correction making q
+//      faithful, the second one yields exactly RN(a/tot) (Markstein's theorem; needs tot's significand not all ones
+//      and no under/overflow in the residuals);
+//   4. all threads check that every quotient of the chunk stayed inside that domain (an ineligible tot was given a
+//      NaN reciprocal in 2.); if one did not, thread 0 redoes the chunk with plain divisions;
+//   5. all threads take the square roots.
+// Measured: the chain is bound by the number of DEPENDENT fp64 operations per step (8 on both the mean and the
+// variance recurrence now, ~12 with plain divisions), ~45-50 cycles each.
+// tests/test_gpu_parity.py::test_relabel_normalize_bitexact pins the result bit for bit against NumPy.
+constexpr int kRmsChunk = 512;
+
+__device__ __forceinline__ double div_rcp(double a, double b, double r) {
+    double q = __dmul_rn(a, r);
+    q = __fma_rn(__fma_rn(-q, b, a), r, q);
+    return __fma_rn(__fma_rn(-q, b, a), r, q);
+}
+// quotient magnitudes for which no residual of div_rcp can have under- or overflowed (NaN fails the test too)
+__device__ __forceinline__ bool div_rcp_in_domain(double q) {
+    const double m = fabs(q);
+    return q == 0.0 || (m > 1e-270 && m < 1e270);
+}
+
+// one Chan merge step with plain IEEE divisions, NumPy's op order (no FMA contraction)
+__device__ __forceinline__ void rms_step_plain(double bmean, double m_b, double bc, double& mean, double& var, double& count) {
+    const double delta = __dsub_rn(bmean, mean);
+    const double tot = __dadd_rn(count, bc);
+    const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, bc), tot));
+    const double m_a = __dmul_rn(var, count);
+    const double corr = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), bc), tot);
+    const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), corr);
+    mean = new_mean; var = __ddiv_rn(m2, tot); count = tot;
+}
+
 __global__ void __launch_bounds__(256) relabel_rms_kernel(const float* __restrict__ bmean, const float* __restrict__ bvar, int T, int N,
                                                           double* __restrict__ rms, double* __restrict__ scale) {
-    __shared__ float sMean[2][kRmsChunk], sVar[2][kRmsChunk];
-    __shared__ double sScale[kRmsChunk];
+    __shared__ float sMean[kRmsChunk];
+    __shared__ double sMb[kRmsChunk], sTot[kRmsChunk], sRcp[kRmsChunk], sVarOut[kRmsChunk];
+    __shared__ double sQ1[kRmsChunk], sQ2[kRmsChunk];      // the other two quotients of a step, for the domain check
+    __shared__ int sBad;
     const int tid = threadIdx.x;
     double mean = rms[0], var = rms[1], count = rms[2];
     const double bc = (double)N;
-    const int nchunks = (T + kRmsChunk - 1) / kRmsChunk;
-    for (int e = tid; e < kRmsChunk && e < T; e += 256) { sMean[0][e] = bmean[e]; sVar[0][e] = bvar[e]; }
-    __syncthreads();
-    for (int k = 0; k < nchunks; ++k) {
-        const int b = k & 1, t0 = k * kRmsChunk, len = min(kRmsChunk, T - t0);
+    for (int t0 = 0; t0 < T; t0 += kRmsChunk) {
+        const int len = min(kRmsChunk, T - t0);
+        for (int e = tid; e < len; e += 256) {
+            sMean[e] = bmean[t0 + e];
+            sMb[e] = (double)__fmul_rn(bvar[t0 + e], (float)N);      // float32 * int stays float32 in numpy
+        }
         if (tid == 0) {
-            for (int i = 0; i < len; ++i) {
-                // explicit round-to-nearest ops: no FMA contraction, numpy evaluates these one by one
-                const double delta = __dsub_rn((double)sMean[b][i], mean);
-                const double tot = __dadd_rn(count, bc);
-                const double new_mean = __dadd_rn(mean, __ddiv_rn(__dmul_rn(delta, bc), tot));
-                const double m_a = __dmul_rn(var, count);
-                const double m_b = (double)__fmul_rn(sVar[b][i], (float)N);     // float32 * int stays float32 in numpy
-                const double corr = __ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), bc), tot);
-                const double m2 = __dadd_rn(__dadd_rn(m_a, m_b), corr);
-                mean = new_mean; var = __ddiv_rn(m2, tot); count = tot;
-                sScale[i] = sqrt(__dadd_rn(var, 1e-7));
-            }
-        } else if (k + 1 < nchunks) {
-            const int t1 = t0 + kRmsChunk;
-            for (int e = tid - 1; e < kRmsChunk && t1 + e < T; e += 255) { sMean[b ^ 1][e] = bmean[t1 + e]; sVar[b ^ 1][e] = bvar[t1 + e]; }
+            sBad = 0;
+            double c = count;
+            for (int i = 0; i < len; ++i) { c = __dadd_rn(c, bc); sTot[i] = c; }
         }
         __syncthreads();
-        for (int e = tid; e < len; e += 256) scale[t0 + e] = sScale[e];
+        for (int e = tid; e < len; e += 256) {
+            const double tot = sTot[e];
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(tot);
+            const bool eligible = tot > 1e-270 && tot < 1e270 && (bits & 0xFFFFFFFFFFFFFull) != 0xFFFFFFFFFFFFFull;
+            sRcp[e] = eligible ? __drcp_rn(tot) : __longlong_as_double(0x7ff8000000000000ll);     // NaN poisons the step
+        }
+        __syncthreads();
+        const double mean0 = mean, var0 = var, count0 = count;
+        if (tid == 0) {
+            for (int i = 0; i < len; ++i) {
+                // explicit round-to-nearest ops in NumPy's order; only the divisions are restructured (see above)
+                const double tot = sTot[i], r = sRcp[i];
+                const double delta = __dsub_rn((double)sMean[i], mean);
+                const double q1 = div_rcp(__dmul_rn(delta, bc), tot, r);
+                const double m_a = __dmul_rn(var, count);
+                const double q2 = div_rcp(__dmul_rn(__dmul_rn(__dmul_rn(delta, delta), count), bc), tot, r);
+                const double m2 = __dadd_rn(__dadd_rn(m_a, sMb[i]), q2);
+                mean = __dadd_rn(mean, q1); var = div_rcp(m2, tot, r); count = tot;
+                sQ1[i] = q1; sQ2[i] = q2; sVarOut[i] = var;
+            }
+        }
+        __syncthreads();
+        // domain check of every quotient of the chunk, off the chain; a failure anywhere redoes the chunk plainly
+        bool bad = false;
+        for (int e = tid; e < len; e += 256)
+            bad = bad || !div_rcp_in_domain(sQ1[e]) || !div_rcp_in_domain(sQ2[e]) || !div_rcp_in_domain(sVarOut[e]);
+        if (bad) sBad = 1;
+        __syncthreads();
+        if (sBad && tid == 0) {
+            mean = mean0; var = var0; count = count0;
+            for (int i = 0; i < len; ++i) {
+                rms_step_plain((double)sMean[i], sMb[i], bc, mean, var, count);
+                sVarOut[i] = var;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < len; e += 256) scale[t0 + e] = sqrt(__dadd_rn(sVarOut[e], 1e-7));
         __syncthreads();
     }
     if (tid == 0) { rms[0] = mean; rms[1] = var; rms[2] = count; }
+}
+
+// Self-check of div_rcp against __ddiv_rn on pseudo-random operands (tests only): returns the number of mismatches.
+__global__ void div_rcp_selfcheck_kernel(unsigned long long seed, int per_thread, double b_lo, double b_hi, unsigned long long* mismatches) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    unsigned long long bad_count = 0;
+    for (int i = 0; i < per_thread; ++i) {
+        // b: log-uniform in [b_lo, b_hi] with random significand; a: random significand, exponent in [-60, 60]
+        const double ub = (double)(next() >> 11) * (1.0 / 9007199254740992.0);
+        const double b = b_lo * exp(ub * log(b_hi / b_lo));
+        const unsigned long long ma = next() & 0xFFFFFFFFFFFFFull;
+        const long long ea = 1023 + (long long)(next() % 121) - 60;
+        double a = __longlong_as_double((long long)(((unsigned long long)ea << 52) | ma));
+        if (next() & 1) a = -a;
+        const double q = div_rcp(a, b, __drcp_rn(b));
+        if (div_rcp_in_domain(q) && q != __ddiv_rn(a, b)) ++bad_count;
+    }
+    if (bad_count) atomicAdd(mismatches, bad_count);
 }
 
 // rewards[t] = float32(clip(float64(raw)/sqrt(var_t+1e-7), -10, 10))   (main_gail_dyn_ppo.py:288-292)
@@ -888,6 +971,16 @@ int sg_relabel_normalize(const float* raw_reward, const float* masks, float* rew
     const RelabelWs w = relabel_ws(T, N);
     return relabel_from_raw(raw_reward, masks, rewards, T, N, gamma, disc_returns, has_returns, rms_state, mean_returns,
                             (char*)workspace, w, (cudaStream_t)stream);
+}
+
+int sg_selftest_division(uint64_t seed, int blocks, int per_thread, double b_lo, double b_hi, uint64_t* mismatches,
+                         void* stream) {
+    SG_REQUIRE(mismatches && blocks > 0 && per_thread > 0 && b_lo > 0 && b_hi > b_lo, "sg_selftest_division: bad arguments");
+    div_rcp_selfcheck_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((unsigned long long)seed, per_thread, b_lo, b_hi,
+                                                                      (unsigned long long*)mismatches);
+    count_launches(1);
+    SG_CUDA(cudaGetLastError());
+    return SG_OK;
 }
 
 int sg_disc_relabel(const float* params, int feat_dim, int hidden, const float* obs_feat, const float* masks,
