@@ -503,45 +503,82 @@ __global__ void __launch_bounds__(kStepThreads) disc_reward_kernel(const float* 
 // running statistics (gail.py:206-209 called with masks[step], main_gail_dyn_ppo.py:276-280).
 // One CTA per 32 columns; all threads stream chunks of steps through double-buffered shared memory with
 // cp.async while the first `cols` threads walk the recurrence (see returns_scan_staged_kernel).
-constexpr int kRTC = 32;
+constexpr int kRTC = 64;
+constexpr int kRlStages = 4;
+constexpr size_t kRlScanSmemBytes = (size_t)(2 * kRlStages + 1) * kRTC * 32 * sizeof(float);
 __device__ __forceinline__ void rl_cp_async4(float* dst_smem, const float* src) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
 }
+__device__ __forceinline__ void rl_cp_async16(float* dst_smem, const float* src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
 __global__ void __launch_bounds__(256) relabel_scan_kernel(const float* __restrict__ raw, const float* __restrict__ masks,
                                                            float* __restrict__ ret_all, float* __restrict__ disc_returns,
                                                            int T, int N, float gamma, int has_returns) {
-    __shared__ float sR[2][kRTC][32], sM[2][kRTC][32], sO[kRTC][32];
+    extern __shared__ __align__(16) float rl_scan_smem[];
+    typedef float (*Stage)[kRTC][32];
+    Stage sR = reinterpret_cast<Stage>(rl_scan_smem);
+    Stage sM = sR + kRlStages;
+    float (*sO)[32] = reinterpret_cast<float (*)[32]>(sM + kRlStages);
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * 32;
     const int cols = min(32, N - n0);
     const int nchunks = (T + kRTC - 1) / kRTC;
-    auto issue = [&](int k) {
-        const int b = k & 1;
-        for (int e = tid; e < kRTC * 32; e += 256) {
-            const int tt = e >> 5, c = e & 31;
-            const int t = k * kRTC + tt;
-            if (c < cols && t < T) {
-                rl_cp_async4(&sR[b][tt][c], raw + (size_t)t * N + n0 + c);
-                rl_cp_async4(&sM[b][tt][c], masks + (size_t)t * N + n0 + c);
+    // 16-byte copies when every row segment is float4-aligned (see returns_scan_staged_kernel)
+    const bool vec = (N & 3) == 0 && (reinterpret_cast<unsigned long long>(raw) & 15ull) == 0 &&
+                     (reinterpret_cast<unsigned long long>(masks) & 15ull) == 0;
+    auto issue = [&](int k) {       // always commits a (possibly empty) group, so that group k <-> chunk k
+        const int b = k % kRlStages;
+        if (k < nchunks && vec) {
+            const int c4 = 4 * (tid & 7);
+            if (c4 < cols) {
+                for (int tt = tid >> 3; tt < kRTC; tt += 32) {
+                    const int t = k * kRTC + tt;
+                    if (t < T) {
+                        const size_t i0 = (size_t)t * N + n0 + c4;
+                        rl_cp_async16(&sR[b][tt][c4], raw + i0);
+                        rl_cp_async16(&sM[b][tt][c4], masks + i0);
+                    }
+                }
+            }
+        } else if (k < nchunks) {
+            for (int e = tid; e < kRTC * 32; e += 256) {
+                const int tt = e >> 5, c = e & 31;
+                const int t = k * kRTC + tt;
+                if (c < cols && t < T) {
+                    rl_cp_async4(&sR[b][tt][c], raw + (size_t)t * N + n0 + c);
+                    rl_cp_async4(&sM[b][tt][c], masks + (size_t)t * N + n0 + c);
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     float ret = 0.f;
     if (tid < cols && has_returns) ret = disc_returns[n0 + tid];
-    issue(0);
+    for (int k = 0; k < kRlStages - 1; ++k) issue(k);
     for (int k = 0; k < nchunks; ++k) {
-        if (k + 1 < nchunks) { issue(k + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        issue(k + kRlStages - 1);         // refills the buffer chunk k-1 was read from (all threads passed its barrier)
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRlStages - 1) : "memory");
         __syncthreads();
-        const int b = k & 1;
+        const int b = k % kRlStages;
         if (tid < cols) {
-#pragma unroll 4
-            for (int tt = 0; tt < kRTC; ++tt) {
-                const int t = k * kRTC + tt;
-                if (t >= T) break;
-                ret = (has_returns || t > 0) ? __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), sM[b][tt][tid]), sR[b][tt][tid]) : sR[b][tt][tid];
+            const int len = min(kRTC, T - k * kRTC);
+            int tt = 0;
+            if (k == 0 && !has_returns) { ret = sR[b][0][tid]; sO[0][tid] = ret; tt = 1; }     // the first ever call clones (gail.py:205-206)
+            // groups of 8 steps: all shared-memory loads of a group are issued before its dependent chain starts
+            for (; tt + 8 <= len; tt += 8) {
+                float m[8], r[8], o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { m[j] = sM[b][tt + j][tid]; r[j] = sR[b][tt + j][tid]; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { ret = __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), m[j]), r[j]); o[j] = ret; }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sO[tt + j][tid] = o[j];
+            }
+            for (; tt < len; ++tt) {
+                ret = __fadd_rn(__fmul_rn(__fmul_rn(ret, gamma), sM[b][tt][tid]), sR[b][tt][tid]);
                 sO[tt][tid] = ret;
             }
         }
@@ -950,7 +987,12 @@ static int relabel_from_raw(const float* raw, const float* masks, float* rewards
     float* bmean = (float*)(ws + w.bmean);
     float* bvar = (float*)(ws + w.bvar);
     double* scale = (double*)(ws + w.scale);
-    relabel_scan_kernel<<<(N + 31) / 32, 256, 0, s>>>(raw, masks, ret_all, disc_returns, T, N, (float)gamma, has_returns);
+    static bool scan_smem_set = false;
+    if (!scan_smem_set) {
+        SG_CUDA(cudaFuncSetAttribute(relabel_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRlScanSmemBytes));
+        scan_smem_set = true;
+    }
+    relabel_scan_kernel<<<(N + 31) / 32, 256, kRlScanSmemBytes, s>>>(raw, masks, ret_all, disc_returns, T, N, (float)gamma, has_returns);
     relabel_moments_kernel<<<(T + 127) / 128, 128, 0, s>>>(ret_all, T, N, bmean, bvar, mean_returns);
     relabel_rms_kernel<<<1, 256, 0, s>>>(bmean, bvar, T, N, rms_state, scale);
     long long total = (long long)T * N;

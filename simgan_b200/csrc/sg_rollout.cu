@@ -13,15 +13,24 @@ namespace sg {
 // A thread walking the chain cannot hide the latency of its own loads (16 columns x 2048 dependent steps took
 // 0.46 ms with thread-level prefetch), so the inputs are staged:
 // one CTA per 32 columns; ALL 256 threads stream chunks of kTC steps of the
-// four input arrays into double-buffered shared memory with cp.async (coalesced 128-byte row segments) while
-// the first `cols` threads walk the recurrence out of shared memory; results are written back coalesced.
+// four input arrays into a kScanStages-deep ring of shared-memory buffers with cp.async (coalesced 128-byte row
+// segments) while the first `cols` threads walk the recurrence out of shared memory; results are written back
+// coalesced.  Three chunks in flight (~1.5 us of chain work) cover the global-memory latency of a chunk; with two
+// buffers of 32 steps every chunk still waited ~1 us for its loads.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTC = 32;
+constexpr int kTC = 64;
+constexpr int kScanStages = 4;
+constexpr size_t kScanSmemBytes = (size_t)(4 * kScanStages + 1) * kTC * 32 * sizeof(float);
 
 __device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
     const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+    const unsigned int d = (unsigned int)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<unsigned long long>(p) & 15ull) == 0; }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NKEEP) : "memory"); }
@@ -33,24 +42,48 @@ __global__ void __launch_bounds__(256) returns_scan_staged_kernel(const float* _
                                                                   const float* __restrict__ next_value, int T, int N,
                                                                   float g, float gl) {
     constexpr bool GAE = (MODE <= 1), PROPER = (MODE == 0 || MODE == 2);
-    __shared__ float sR[2][kTC][32], sV[2][kTC][32], sM[2][kTC][32], sB[2][kTC][32], sO[kTC][32];
+    extern __shared__ __align__(16) float scan_smem[];
+    typedef float (*Stage)[kTC][32];
+    Stage sR = reinterpret_cast<Stage>(scan_smem);
+    Stage sV = sR + kScanStages, sM = sV + kScanStages, sB = sM + kScanStages;
+    float (*sO)[32] = reinterpret_cast<float (*)[32]>(sB + kScanStages);
     const int tid = threadIdx.x;
     const int n0 = blockIdx.x * 32;
     const int cols = min(32, N - n0);
     const int nchunks = (T + kTC - 1) / kTC;
     // chunk k covers steps t in [T - (k+1)*kTC, T - k*kTC) (clipped at 0); slot tt <-> t = tbase + tt
-    auto issue = [&](int k) {
-        const int b = k & 1;
+    // 16-byte copies when every row segment is float4-aligned (N % 4 == 0 and aligned bases): 8 float4 per row,
+    // 32 rows per sweep of the CTA, one 64-bit index per copy -- the scalar form spent more time computing
+    // addresses for 4-byte copies than the chain spends on the recurrence
+    const bool vec = (N & 3) == 0 && aligned16(rewards) && aligned16(vpred) && aligned16(masks) && (!PROPER || aligned16(bad));
+    auto issue = [&](int k) {       // always commits a (possibly empty) group, so that group k <-> chunk k
+        const int b = k % kScanStages;
         const int tbase = T - (k + 1) * kTC;
-        for (int e = tid; e < kTC * 32; e += 256) {
-            const int tt = e >> 5, c = e & 31;
-            const int t = tbase + tt;
-            if (c < cols && t >= 0) {
-                const size_t i0 = (size_t)t * N + n0 + c, i1 = (size_t)(t + 1) * N + n0 + c;
-                cp_async4(&sR[b][tt][c], rewards + i0);
-                cp_async4(&sV[b][tt][c], vpred + i0);
-                cp_async4(&sM[b][tt][c], masks + i1);
-                if (PROPER) cp_async4(&sB[b][tt][c], bad + i1);
+        if (k < nchunks && vec) {
+            const int c4 = 4 * (tid & 7);
+            if (c4 < cols) {
+                for (int tt = tid >> 3; tt < kTC; tt += 32) {
+                    const int t = tbase + tt;
+                    if (t >= 0) {
+                        const size_t i0 = (size_t)t * N + n0 + c4, i1 = i0 + N;
+                        cp_async16(&sR[b][tt][c4], rewards + i0);
+                        cp_async16(&sV[b][tt][c4], vpred + i0);
+                        cp_async16(&sM[b][tt][c4], masks + i1);
+                        if (PROPER) cp_async16(&sB[b][tt][c4], bad + i1);
+                    }
+                }
+            }
+        } else if (k < nchunks) {
+            for (int e = tid; e < kTC * 32; e += 256) {
+                const int tt = e >> 5, c = e & 31;
+                const int t = tbase + tt;
+                if (c < cols && t >= 0) {
+                    const size_t i0 = (size_t)t * N + n0 + c, i1 = (size_t)(t + 1) * N + n0 + c;
+                    cp_async4(&sR[b][tt][c], rewards + i0);
+                    cp_async4(&sV[b][tt][c], vpred + i0);
+                    cp_async4(&sM[b][tt][c], masks + i1);
+                    if (PROPER) cp_async4(&sB[b][tt][c], bad + i1);
+                }
             }
         }
         cp_async_commit();
@@ -62,20 +95,18 @@ __global__ void __launch_bounds__(256) returns_scan_staged_kernel(const float* _
         if (GAE) { vpred[(size_t)T * N + n0 + tid] = nv; carry = 0.f; }
         else { ret[(size_t)T * N + n0 + tid] = nv; carry = nv; }
     }
-    issue(0);
+    for (int k = 0; k < kScanStages - 1; ++k) issue(k);
     for (int k = 0; k < nchunks; ++k) {
-        if (k + 1 < nchunks) { issue(k + 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
+        issue(k + kScanStages - 1);       // refills the buffer chunk k-1 was read from (all threads passed its barrier)
+        cp_async_wait<kScanStages - 1>();
         __syncthreads();
-        const int b = k & 1;
+        const int b = k % kScanStages;
         const int tbase = T - (k + 1) * kTC;
         if (tid < cols) {
             const int c = tid;
-#pragma unroll 4
-            for (int tt = kTC - 1; tt >= 0; --tt) {
-                if (tbase + tt < 0) break;
-                const float r = sR[b][tt][c], v = sV[b][tt][c], m = sM[b][tt][c];
-                const float bb = PROPER ? sB[b][tt][c] : 1.f;
+            // one step of the recurrence in the reference's op order (storage.py:109-142); everything that does not
+            // depend on `carry` (delta, gl*m) is off the dependent chain
+            auto step = [&](float r, float v, float m, float bb) {
                 float out;
                 if (GAE) {
                     const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, v_next), m)), v);
@@ -91,8 +122,24 @@ __global__ void __launch_bounds__(256) returns_scan_staged_kernel(const float* _
                     out = __fadd_rn(__fmul_rn(__fmul_rn(carry, g), m), r);
                     carry = out;
                 }
-                sO[tt][c] = out;
+                return out;
+            };
+            const int lo = tbase < 0 ? -tbase : 0;      // first valid slot of this chunk
+            int tt = kTC - 1;
+            // groups of 8 steps: all shared-memory loads of a group are issued before its dependent chain starts
+            for (; tt - 7 >= lo; tt -= 8) {
+                float r[8], v[8], m[8], bb[8], o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    r[j] = sR[b][tt - j][c]; v[j] = sV[b][tt - j][c]; m[j] = sM[b][tt - j][c];
+                    bb[j] = PROPER ? sB[b][tt - j][c] : 1.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = step(r[j], v[j], m[j], bb[j]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sO[tt - j][c] = o[j];
             }
+            for (; tt >= lo; --tt) sO[tt][c] = step(sR[b][tt][c], sV[b][tt][c], sM[b][tt][c], PROPER ? sB[b][tt][c] : 1.f);
         }
         __syncthreads();
         for (int e = tid; e < kTC * 32; e += 256) {
@@ -314,11 +361,19 @@ int sg_compute_returns(const float* rewards, float* value_preds, const float* ma
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     const int mode = use_gae ? (use_proper_time_limits ? 0 : 1) : (use_proper_time_limits ? 2 : 3);
     const int sb = (N + 31) / 32;
+    static bool smem_set = false;
+    if (!smem_set) {
+        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
+        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
+        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
+        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
+        smem_set = true;
+    }
     switch (mode) {
-        case 0: returns_scan_staged_kernel<0><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        case 1: returns_scan_staged_kernel<1><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        case 2: returns_scan_staged_kernel<2><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
-        default: returns_scan_staged_kernel<3><<<sb, 256, 0, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 0: returns_scan_staged_kernel<0><<<sb, 256, kScanSmemBytes, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 1: returns_scan_staged_kernel<1><<<sb, 256, kScanSmemBytes, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        case 2: returns_scan_staged_kernel<2><<<sb, 256, kScanSmemBytes, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
+        default: returns_scan_staged_kernel<3><<<sb, 256, kScanSmemBytes, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
     }
     count_launches(1);
     SG_CUDA(cudaGetLastError());
