@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscAr
 }
 // Register-resident variant (H = 4*HQ known at compile time, H <= 128): W2 lives in registers, the rest of the
 // parameters in a small shared image; both are refreshed from global memory after every Adam step.
-template <int HQ>
+// TB = row triples per tile: 2 (disc_tile_reg), or 1 (disc_tile_reg1) when that still leaves at most one tile per SM.
+template <int HQ, int TB>
 __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     extern __shared__ __align__(16) float smem[];
     const DiscRegImage I = make_disc_reg_image(a.F, a.H);
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     DiscPrefetch pf;
-    pf.on = a.ntiles <= (int)gridDim.x && 8 * round_up(a.F, 4) <= kStepThreads;
+    pf.on = a.ntiles <= (int)gridDim.x && 4 * TB * round_up(a.F, 4) <= kStepThreads;
     pf.valid = false;
     pf.ei = pf.pi = -1;
     pf.xe = pf.xp = pf.al = 0.f;
@@ -437,7 +438,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
         pc.lap(0);
         bool acc = false;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
-            disc_tile_reg<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
+            if (TB == 1) disc_tile_reg1<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
+            else disc_tile_reg<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
             acc = true;
         }
         pc.lap(1);
@@ -769,19 +771,6 @@ __global__ void __launch_bounds__(256) relabel_apply_kernel(const float* __restr
     }
 }
 
-static int disc_tiles(const sg_disc_config* c) { return (c->row_end - c->row_begin + kTB - 1) / kTB; }
-static int disc_grid(const sg_disc_config* c, int* sms_out) {
-    int sms = sg_device_sm_count();
-    if (sms <= 0) sms = 148;
-    if (sms_out) *sms_out = sms;
-    int tiles = disc_tiles(c);
-    int g = tiles < sms ? tiles : sms;
-    // never fewer than 64 CTAs: CTAs without a tile skip phase A but still own a slice of the reduce / Adam phases,
-    // which keeps those phases on the narrow one-parameter-per-thread path for small (or sharded) minibatches
-    const int gmin = sms < 64 ? sms : 64;
-    if (g < gmin) g = gmin;
-    return g < 1 ? 1 : g;
-}
 constexpr size_t kDiscMaxDynSmem = 227 * 1024 - 1024;
 static size_t disc_tile_smem_floats(const sg_disc_config* c) {
     size_t f = (size_t)DiscSmem::floats(c->feat_dim, c->hidden);
@@ -802,6 +791,27 @@ static size_t disc_resident_smem_bytes(const sg_disc_config* c) {
     if (disc_reg_ok(c)) return disc_reg_smem_bytes(c);
     DiscLayout L = make_disc_layout(c->feat_dim, c->hidden);
     return ((size_t)L.total + disc_tile_smem_floats(c)) * sizeof(float);
+}
+// row triples per tile: the register-resident kernel runs single-triple tiles while that leaves at most one per SM
+static int disc_tb(const sg_disc_config* c) {
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    int mode = c->mode;
+    if (mode == 0) mode = disc_resident_smem_bytes(c) <= kDiscMaxDynSmem ? 3 : 2;
+    return (mode == 3 && disc_reg_ok(c) && c->row_end - c->row_begin <= sms) ? 1 : kTB;
+}
+static int disc_tiles(const sg_disc_config* c) { const int tb = disc_tb(c); return (c->row_end - c->row_begin + tb - 1) / tb; }
+static int disc_grid(const sg_disc_config* c, int* sms_out) {
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    if (sms_out) *sms_out = sms;
+    int tiles = disc_tiles(c);
+    int g = tiles < sms ? tiles : sms;
+    // never fewer than 64 CTAs: CTAs without a tile skip phase A but still own a slice of the reduce / Adam phases,
+    // which keeps those phases on the narrow one-parameter-per-thread path for small (or sharded) minibatches
+    const int gmin = sms < 64 ? sms : 64;
+    if (g < gmin) g = gmin;
+    return g < 1 ? 1 : g;
 }
 static int disc_validate(const sg_disc_config* c) {
     SG_REQUIRE(c, "sg_disc: null config");
@@ -933,11 +943,12 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
         if (mode == 3) {
             fn = (const void*)disc_persistent_kernel<true>;
             if (disc_reg_ok(cfg)) {
+                const bool one = disc_tb(cfg) == 1;
                 switch (cfg->hidden) {
-                    case 48: fn = (const void*)disc_reg_kernel<12>; break;
-                    case 64: fn = (const void*)disc_reg_kernel<16>; break;
-                    case 100: fn = (const void*)disc_reg_kernel<25>; break;
-                    default: fn = (const void*)disc_reg_kernel<32>; break;
+                    case 48: fn = one ? (const void*)disc_reg_kernel<12, 1> : (const void*)disc_reg_kernel<12, 2>; break;
+                    case 64: fn = one ? (const void*)disc_reg_kernel<16, 1> : (const void*)disc_reg_kernel<16, 2>; break;
+                    case 100: fn = one ? (const void*)disc_reg_kernel<25, 1> : (const void*)disc_reg_kernel<25, 2>; break;
+                    default: fn = one ? (const void*)disc_reg_kernel<32, 1> : (const void*)disc_reg_kernel<32, 2>; break;
                 }
             }
         }

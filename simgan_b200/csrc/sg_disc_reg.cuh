@@ -135,15 +135,15 @@ struct DiscPrefetch {
     int ei, pi;           // expert / policy row indices (stage 1), -1 = padding element
     float xe, xp, al;
 };
-template <class Args>
+template <int TB, class Args>
 __device__ __forceinline__ void disc_prefetch_idx(const Args& a, DiscPrefetch& pf, int step, int tile, int ldf) {
     const int tid = threadIdx.x;
     pf.ei = pf.pi = -1;
     pf.al = 0.f;
-    if (tid < 8 * ldf) {
+    if (tid < 4 * TB * ldf) {
         const int r = tid / ldf;
-        const int kind = r / 2, j = r - kind * 2;
-        const int row = a.row_begin + tile * 2 + j;
+        const int kind = r / TB, j = r - kind * TB;
+        const int row = a.row_begin + tile * TB + j;
         if (kind < 3 && row < a.row_end) {
             pf.ei = a.eidx[(size_t)step * a.B + row];
             pf.pi = a.pidx[(size_t)step * a.B + row];
@@ -204,7 +204,7 @@ __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float
     __syncthreads();
     pf.valid = false;
     const bool pf_next = pf.on && step + 1 < a.nsteps;
-    if (pf_next) disc_prefetch_idx(a, pf, step + 1, tile, ldf);          // stage 1: next step's row indices and alpha
+    if (pf_next) disc_prefetch_idx<TB>(a, pf, step + 1, tile, ldf);      // stage 1: next step's row indices and alpha
     // rows owned by this lane in 6-row stages: kh, kh+2, kh+4  (e_kh, p_kh, m_kh)
     const int myrows[3] = {kh, kh + 2, kh + 4};
     // ---- S1: layer 1 forward, W1 natural in shared memory -------------------------------------------------------
@@ -386,6 +386,229 @@ __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float
         float db3 = 0.f, le = 0.f, lp = 0.f, gp = 0.f;
         for (int r = 0; r < 2 * TB; ++r) db3 += sm.DD[r];
         for (int r = 0; r < TB; ++r) { le += sm.LOSS[r]; lp += sm.LOSS[8 + TB + r]; gp += sm.LOSS[16 + r]; }
+        if (acc) { db3 += __ldcg(gout + a.L.b3); le += lossout[0]; lp += lossout[1]; gp += lossout[2]; }
+        __stcg(gout + a.L.b3, db3);
+        lossout[0] = le; lossout[1] = lp; lossout[2] = gp;
+    }
+    if (pf_next) disc_prefetch_rows(a, pf, ldf);                        // stage 2: the feature rows themselves
+    __syncthreads();
+}
+
+// One tile = ONE (expert, policy, mixup) row triple: used when the minibatch (or this rank's shard of it) has at most
+// one triple per SM, so that twice as many CTAs each do half the work of disc_tile_reg.  Row slots (R = 4):
+//   X  [e | p | m | gbar]     H1 [h1_e | h1_p | h1_m | vb1]     H2 [h2_e | h2_p | h2_m]     Y2 [dz2_e | dz2_p | u2]
+//   L2t[u][4] = {dz2_e, dz2_p, zb2, u2}  pairs with the H1 rows     L1t[u][4] = {dz1_e, dz1_p, zb1, u1}  pairs with the X rows
+// Both lanes of a unit hold every pass result (the xor-shuffle in reg_pass); lane 0 finishes the expert and the mixup
+// row, lane 1 the policy row.
+template <int HQ, class Args>
+__device__ void disc_tile_reg1(const Args& a, const DiscRegW2<HQ>& w, const float* __restrict__ img, const DiscRegImage& I,
+                               int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
+                               DiscRegSmem& sm, bool acc, DiscPrefetch& pf) {
+    constexpr int H = 4 * HQ, R = 4;
+    const int tid = threadIdx.x, nth = kStepThreads;
+    const int F = a.F, ldf = sm.ldf, ldh = sm.ldh;
+    const int u = tid >> 1, kh = tid & 1;
+    const bool live = u < H;
+    const int row = a.row_begin + tile;
+    const bool rowok = row < a.row_end;
+    const float invB = 1.f / (float)a.B;
+    const float* W1 = img + I.w1; const float* B1 = img + I.b1; const float* B2 = img + I.b2;
+    const float* W3 = img + I.w3; const float* B3 = img + I.b3;
+
+    // ---- S0: rows [e | p | m | 0], mixup = alpha*e + (1-alpha)*p (gail.py:72-75) ---------------------------------------
+    if (pf.valid) {
+        if (tid < R * ldf) {                       // fetched during the previous step's barriers
+            const int kind = tid / ldf;
+            const bool ok = pf.ei >= 0 && (tid % ldf) < F;
+            const float mixed = __fadd_rn(__fmul_rn(pf.al, pf.xe), __fmul_rn(__fsub_rn(1.f, pf.al), pf.xp));
+            sm.X[tid] = !ok ? 0.f : (kind == 0 ? pf.xe : (kind == 1 ? pf.xp : mixed));
+        }
+    } else {
+        const int ei = rowok ? a.eidx[(size_t)step * a.B + row] : 0, pi = rowok ? a.pidx[(size_t)step * a.B + row] : 0;
+        const float al = rowok ? a.alpha[(size_t)step * a.B + row] : 0.f;
+        for (int e = tid; e < R * ldf; e += nth) {
+            const int kind = e / ldf, k = e - kind * ldf;
+            float x = 0.f;
+            if (kind < 3 && rowok && k < F) {
+                const float xe = a.expert[(size_t)ei * F + k];
+                const float xp = a.policy[(size_t)pi * F + k];
+                x = kind == 0 ? xe : (kind == 1 ? xp : __fadd_rn(__fmul_rn(al, xe), __fmul_rn(__fsub_rn(1.f, al), xp)));
+            }
+            sm.X[e] = x;
+        }
+    }
+    __syncthreads();
+    pf.valid = false;
+    const bool pf_next = pf.on && step + 1 < a.nsteps;
+    if (pf_next) disc_prefetch_idx<1>(a, pf, step + 1, tile, ldf);       // stage 1: next step's row indices and alpha
+    const int rows3[3] = {0, 1, 2};
+    // ---- S1: layer 1 forward, W1 natural in shared memory: lane 0 -> rows e, m; lane 1 -> row p ---------------------------
+    if (live) {
+        const int ra = kh;                        // 0: expert, 1: policy
+        float s0 = 0.f, s1 = 0.f;
+        const float* wr = W1 + (size_t)u * F;
+        for (int k0 = 0; k0 < F; k0 += 4) {
+            float wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv[j] = (k0 + j < F) ? wr[k0 + j] : 0.f;
+            const float4 x = *reinterpret_cast<const float4*>(sm.X + ra * ldf + k0);
+            s0 = fmaf(x.x, wv[0], s0); s0 = fmaf(x.y, wv[1], s0); s0 = fmaf(x.z, wv[2], s0); s0 = fmaf(x.w, wv[3], s0);
+            if (!kh) {
+                const float4 y = *reinterpret_cast<const float4*>(sm.X + 2 * ldf + k0);
+                s1 = fmaf(y.x, wv[0], s1); s1 = fmaf(y.y, wv[1], s1); s1 = fmaf(y.z, wv[2], s1); s1 = fmaf(y.w, wv[3], s1);
+            }
+        }
+        const float b = B1[u];
+        sm.H1[ra * ldh + u] = tanhf(s0 + b);
+        if (!kh) sm.H1[2 * ldh + u] = tanhf(s1 + b);
+    }
+    __syncthreads();
+    // ---- S2: layer 2 forward ("F" pass on 3 rows) ---------------------------------------------------------------------------
+    {
+        float o[3];
+        reg_pass<HQ, 3>(w.wrow, sm.H1, ldh, rows3, kh, o);
+        if (live) {
+            const float b = B2[u];
+            sm.H2[kh * ldh + u] = tanhf((kh ? o[1] : o[0]) + b);
+            if (!kh) sm.H2[2 * ldh + u] = tanhf(o[2] + b);
+        }
+    }
+    __syncthreads();
+    // ---- S3: logits + BCE-with-logits seeds (gail.py:171-176): warp r handles row r ----------------------------------------
+    {
+        const int wid = tid >> 5, lane = tid & 31;
+        if (wid < 2) {
+            float d = 0.f;
+            for (int n = lane; n < H; n += 32) d = fmaf(W3[n], sm.H2[wid * ldh + n], d);
+            d = warp_sum(d) + B3[0];
+            if (lane == 0) {
+                float dd = 0.f, l = 0.f;
+                if (rowok && wid == 0) { dd = (dsigmoidf(d) - 1.f) * invB; l = dsoftplusf(-d); }
+                if (rowok && wid == 1) { dd = dsigmoidf(d) * invB; l = dsoftplusf(d); }
+                sm.DD[wid] = dd; sm.LOSS[wid] = l;           // LOSS[0] expert term, LOSS[1] policy term
+            }
+        }
+    }
+    __syncthreads();
+    // ---- S4: dz2 (e,p) and u2 (mixup) -------------------------------------------------------------------------------------------
+    if (live) {
+        const float w3 = W3[u];
+        {
+            const float h2 = sm.H2[kh * ldh + u];
+            const float y = sm.DD[kh] * (w3 * (1.f - h2 * h2));
+            sm.Y2[kh * ldh + u] = y; sm.L2t[u * R + kh] = y;
+        }
+        if (!kh) {
+            const float h2 = sm.H2[2 * ldh + u];
+            const float base = w3 * (1.f - h2 * h2);
+            sm.Y2[2 * ldh + u] = base; sm.L2t[u * R + 3] = base;          // u2 pairs with vb1 in slot 3
+        }
+    }
+    __syncthreads();
+    // ---- S5: pass A ("B" pass on 3 rows): dz1 for the e,p rows; v1, u1 for the mixup row -------------------------------------
+    float v1 = 0.f, h1m = 0.f;
+    {
+        float o[3];
+        reg_pass<HQ, 3>(w.wcol, sm.Y2, ldh, rows3, kh, o);
+        if (live) {
+            const float h1 = sm.H1[kh * ldh + u];
+            sm.L1t[u * R + kh] = (kh ? o[1] : o[0]) * (1.f - h1 * h1);
+            v1 = o[2];
+            h1m = sm.H1[2 * ldh + u];
+            if (!kh) {
+                const float u1 = v1 * (1.f - h1m * h1m);
+                sm.U1[u] = u1;
+                sm.L1t[u * R + 3] = u1;                                    // u1 pairs with gbar in slot 3
+            }
+        }
+    }
+    __syncthreads();
+    // ---- S6: pass B: g[f] = sum_n u1[n] W1[n][f]  (input gradient of the mixup row) -------------------------------------------
+    {
+        const int nout = ldf;
+        int nch = nth / nout; nch = nch < 1 ? 1 : (nch > 8 ? 8 : nch);
+        const int clen = (H + nch - 1) / nch;
+        for (int e = tid; e < nout * nch; e += nth) {
+            const int c = e / nout, f = e - c * nout;
+            float s = 0.f;
+            if (f < F) {
+                const int n1 = min(H, (c + 1) * clen);
+                for (int n = c * clen; n < n1; ++n) s = fmaf(sm.U1[n], W1[(size_t)n * F + f], s);
+            }
+            sm.PB[c * nout + f] = s;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const int lane = tid;
+            float ssq = 0.f;
+            for (int f = lane; f < ldf; f += 32) {
+                float g = 0.f;
+                for (int c = 0; c < nch; ++c) g += sm.PB[c * nout + f];
+                sm.X[3 * ldf + f] = g;                     // raw g for now (zero in the padding lanes)
+                ssq += g * g;
+            }
+            ssq = warp_sum(ssq);
+            const float nrm = sqrtf(ssq);
+            // penalty lambda*mean((|g|-1)^2) -> gbar = (2 lambda / B)(n-1) g / n
+            const float coef = (rowok && nrm > 0.f) ? (2.f * a.gp_lambda * invB) * (nrm - 1.f) / nrm : 0.f;
+            for (int f = lane; f < ldf; f += 32) sm.X[3 * ldf + f] *= coef;
+            if (lane == 0) sm.LOSS[2] = rowok ? (nrm - 1.f) * (nrm - 1.f) : 0.f;
+        }
+    }
+    __syncthreads();
+    // ---- S7: pass C: ub1 = gbar . W1^T -> vb1, hb1 (lane 0 of the unit) ---------------------------------------------------------
+    float hb1 = 0.f;
+    if (live && !kh) {
+        float s = 0.f;
+        const float* wr = W1 + (size_t)u * F;
+        const float* gb = sm.X + 3 * ldf;
+        for (int k0 = 0; k0 < F; k0 += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(gb + k0);
+            s = fmaf(x.x, wr[k0], s);
+            if (k0 + 1 < F) s = fmaf(x.y, wr[k0 + 1], s);
+            if (k0 + 2 < F) s = fmaf(x.z, wr[k0 + 2], s);
+            if (k0 + 3 < F) s = fmaf(x.w, wr[k0 + 3], s);
+        }
+        sm.H1[3 * ldh + u] = s * (1.f - h1m * h1m);                                 // vb1
+        hb1 = -2.f * s * v1 * h1m;
+    }
+    __syncthreads();
+    // ---- S8: pass D ("F" pass on the vb1 row): ub2 -> dw3 term, zb2 ------------------------------------------------------------------
+    {
+        const int rows1[1] = {3};
+        float o[1];
+        reg_pass<HQ, 1>(w.wrow, sm.H1, ldh, rows1, kh, o);
+        if (live && !kh) {
+            const float ub2 = o[0];
+            const float h2 = sm.H2[2 * ldh + u];
+            const float om = 1.f - h2 * h2;
+            sm.C3[u] = ub2 * om;
+            const float zb2 = -2.f * ub2 * W3[u] * h2 * om;
+            sm.Z2[u] = zb2;
+            sm.L2t[u * R + 2] = zb2;
+        }
+    }
+    __syncthreads();
+    // ---- S9: pass E ("B" pass on the zb2 row): hb1 += zb2 . W2 ; zb1 = hb1*(1-h1^2) -----------------------------------------------------
+    {
+        const int rows1[1] = {0};
+        float o[1];
+        reg_pass<HQ, 1>(w.wcol, sm.Z2, ldh, rows1, kh, o);
+        if (live && !kh) sm.L1t[u * R + 2] = (hb1 + o[0]) * (1.f - h1m * h1m);
+    }
+    __syncthreads();
+    // ---- S10: parameter gradients of this tile -------------------------------------------------------------------------------------------
+    outer_cols<R>(gout + a.L.w2, sm.L2t, sm.H1, ldh, H, H, tid, nth, acc);
+    rowsum_store<R>(gout + a.L.b2, sm.L2t, H, tid, nth, acc, 3);
+    if ((F & 3) == 0) outer_cols<R>(gout + a.L.w1, sm.L1t, sm.X, ldf, H, F, tid, nth, acc);
+    else outer_store<R, 1>(gout + a.L.w1, sm.L1t, sm.X, ldf, H, F, tid, nth, acc);
+    rowsum_store<R>(gout + a.L.b1, sm.L1t, H, tid, nth, acc, 3);
+    for (int n = tid; n < H; n += nth) {
+        const float s = sm.DD[0] * sm.H2[n] + sm.DD[1] * sm.H2[ldh + n] + sm.C3[n];
+        __stcg(gout + a.L.w3 + n, acc ? s + __ldcg(gout + a.L.w3 + n) : s);
+    }
+    if (tid == nth - 1) {
+        float db3 = sm.DD[0] + sm.DD[1], le = sm.LOSS[0], lp = sm.LOSS[1], gp = sm.LOSS[2];
         if (acc) { db3 += __ldcg(gout + a.L.b3); le += lossout[0]; lp += lossout[1]; gp += lossout[2]; }
         __stcg(gout + a.L.b3, db3);
         lossout[0] = le; lossout[1] = lp; lossout[2] = gp;

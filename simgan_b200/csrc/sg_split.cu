@@ -72,9 +72,11 @@ struct SplitSmem {
 };
 
 // X must be loaded (zero padded).  Ends with a CTA barrier; OUT holds the three nets' head outputs.
-template <int R>
+// W2: base of the three trunks' second-layer matrices, stride hh4 floats per net, read with WL2 -- the flat global
+// vector (through L2) or the CTA's shared-memory copy (split_ppo_kernel<R, true>).
+template <int R, class WL2 = LdGlobal>
 __device__ __forceinline__ void split_tile_forward(const float* __restrict__ W, const SplitLayout& L, int O, int H,
-                                                   const SplitSmem<R>& sm, int tid) {
+                                                   const SplitSmem<R>& sm, int tid, const float* __restrict__ W2, int hh4) {
     const int net = tid >> 7, t = tid & 127;
     const int ldh = sm.ldh;
     float* h1 = sm.H1 + net * R * ldh;
@@ -86,8 +88,8 @@ __device__ __forceinline__ void split_tile_forward(const float* __restrict__ W, 
     else gemm_xwT<R, 1>(W + L.w1[net], sm.X, sm.ldo, H, O, t, 128, e1);
     __syncthreads();
     auto e2 = [&](int r, int n, float s) { h2[r * ldh + n] = tanhf(s + ld_cg(B2 + n)); };
-    if ((H & 3) == 0) gemm_xwT<R, 4>(W + L.w2[net], h1, ldh, H, H, t, 128, e2);
-    else gemm_xwT<R, 1>(W + L.w2[net], h1, ldh, H, H, t, 128, e2);
+    if ((H & 3) == 0) gemm_xwT<R, 4, WL2>(W2 + net * hh4, h1, ldh, H, H, t, 128, e2);
+    else gemm_xwT<R, 1, WL2>(W2 + net * hh4, h1, ldh, H, H, t, 128, e2);
     __syncthreads();
     const int ldq = sm.ldq;
     auto eh = [&](int r, int n, float s) { out[r * ldq + n] = s + ld_cg(BH + n); };
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(kSplitThreads) split_forward_kernel(const floa
             sm.X[e] = (row0 + r < B && k < O) ? obs[(size_t)(row0 + r) * O + k] : 0.f;
         }
         __syncthreads();
-        split_tile_forward<R>(params, L, O, H, sm, tid);
+        split_tile_forward<R>(params, L, O, H, sm, tid, params + L.w2[0], L.w2[1] - L.w2[0]);
         for (int e = tid; e < R * A; e += kSplitThreads) {
             const int r = e / A, k = e - r * A;
             const int row = row0 + r;
@@ -181,10 +183,11 @@ struct SplitArgs {
     unsigned int* bar;
 };
 
-template <int R>
+template <int R, class WL2>
 __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                           SplitSmem<R>& sm, bool acc) {
-    static_assert(R == 8, "loss warp maps 8 rows x 4 lanes");
+                           SplitSmem<R>& sm, bool acc, const float* __restrict__ W2, int hh4) {
+    static_assert(R == 8 || R == 4, "loss warp maps R rows x 32/R lanes");
+    constexpr int LPR = 32 / R;           // lanes per row in the loss warp
     const int tid = threadIdx.x;
     const int O = a.O, H = a.H, A = a.A;
     const SplitLayout& L = a.L;
@@ -216,15 +219,15 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
         rValid[r] = ok ? 1.f : 0.f;
     }
     __syncthreads();
-    split_tile_forward<R>(W, L, O, H, sm, tid);
+    split_tile_forward<R, WL2>(W, L, O, H, sm, tid, W2, hh4);
 
-    // per-row losses and head seeds: one warp, 4 lanes per row
+    // per-row losses and head seeds: one warp, LPR lanes per row
     if (tid < 32) {
-        const int r = tid >> 2, sub = tid & 3;
+        const int r = tid / LPR, sub = tid % LPR;
         const bool ok = rValid[r] != 0.f;
         const float invB = 1.f / (float)a.mbs;
         float lp = 0.f, ent = 0.f;
-        for (int k = sub; k < A; k += 4) {
+        for (int k = sub; k < A; k += LPR) {
             float mu, ls;
             split_mu_ls<R>(sm, L, r, k, mu, ls);
             const float sigma = expf(ls);
@@ -232,8 +235,11 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
             lp += -(d * d) / (2.f * (sigma * sigma)) - logf(sigma) - SG_LOG_SQRT_2PI;
             ent += 0.5f + 0.5f * SG_LOG_2PI + logf(sigma);
         }
-        lp += __shfl_xor_sync(0xffffffffu, lp, 1); lp += __shfl_xor_sync(0xffffffffu, lp, 2);
-        ent += __shfl_xor_sync(0xffffffffu, ent, 1); ent += __shfl_xor_sync(0xffffffffu, ent, 2);
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) {
+            lp += __shfl_xor_sync(0xffffffffu, lp, o);
+            ent += __shfl_xor_sync(0xffffffffu, ent, o);
+        }
         float vl = 0.f, al = 0.f, dv = 0.f, coef = 0.f;
         if (ok) {
             const float ratio = expf(lp - rOlp[r]);
@@ -263,7 +269,7 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
             ent = 0.f;
         }
         // seeds: d loss / d mean, d loss / d logstd (log-prob term + the entropy bonus -c_e * mean_r H_r)
-        for (int k = sub; k < A; k += 4) {
+        for (int k = sub; k < A; k += LPR) {
             float mu, ls;
             split_mu_ls<R>(sm, L, r, k, mu, ls);
             const float sigma = expf(ls);
@@ -280,7 +286,7 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
         if (sub == 0) sm.DHt[2 * sm.ldq * R + r] = dv;
         float svl = sub == 0 ? vl : 0.f, sal = sub == 0 ? al : 0.f, sen = sub == 0 ? ent : 0.f;
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
+        for (int o = LPR; o < 32; o <<= 1) {
             svl += __shfl_xor_sync(0xffffffffu, svl, o);
             sal += __shfl_xor_sync(0xffffffffu, sal, o);
             sen += __shfl_xor_sync(0xffffffffu, sen, o);
@@ -310,8 +316,8 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
     else outer_store<R, 1>(gout + L.wh[net], Dh, h2, ldh, NH, H, t, 128, acc);
     rowsum_store<R>(gout + L.bh[net], Dh, NH, t, 128, acc);
     auto epi_2 = [&](int r, int k, float s) { const float h = h1[r * ldh + k]; dz1[k * R + r] = s * (1.f - h * h); };
-    if (vecH) gemm_yW<R, 4>(W + L.w2[net], dz2, H, H, scr, t, 128, epi_2);
-    else gemm_yW<R, 1>(W + L.w2[net], dz2, H, H, scr, t, 128, epi_2);
+    if (vecH) gemm_yW<R, 4, WL2>(W2 + net * hh4, dz2, H, H, scr, t, 128, epi_2);
+    else gemm_yW<R, 1, WL2>(W2 + net * hh4, dz2, H, H, scr, t, 128, epi_2);
     if (vecH) outer_store<R, 4>(gout + L.w2[net], dz2, h1, ldh, H, H, t, 128, acc);
     else outer_store<R, 1>(gout + L.w2[net], dz2, h1, ldh, H, H, t, 128, acc);
     rowsum_store<R>(gout + L.b2[net], dz2, H, t, 128, acc);
@@ -321,21 +327,43 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
     __syncthreads();
 }
 
-template <int R>
+// W2RES: the three H x H second-layer matrices (the bulk of the weights, walked twice per tile) live in a
+// shared-memory copy that every CTA refreshes with three TMA bulk copies after each Adam step; everything else is
+// read through L2.  (The whole parameter vector + tile does not fit 227 KB at the shipped hidden size of 100.)
+template <int R, bool W2RES>
 __global__ void __launch_bounds__(kSplitThreads, 1) split_ppo_kernel(SplitArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[kSplitThreads / 32];
+    __shared__ __align__(8) unsigned long long img_bar;
     constexpr int NT = kSplitThreads;
     const int tid = threadIdx.x, cta = blockIdx.x;
     SplitSmem<R> sm;
     sm.carve(smem, a.O, a.H, a.f);
+    const int hh4 = a.L.w2[1] - a.L.w2[0];                              // global stride between the nets' W2 blocks
+    const int hhs = round_up(a.H * a.H, 4);                             // stride in the shared-memory copy
+    float* W2s = smem + SplitSmem<R>::floats(a.O, a.H, a.f);
+    if (W2RES) {
+        if (tid == 0) mbar_init(&img_bar, 1);
+        __syncthreads();
+    }
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
     for (int step = 0; step < a.nsteps; ++step) {
         // A: tile phase
         bool acc = false;
+        const bool work = cta < a.ntiles;
+        if (W2RES && work) {
+            if (tid == 0) {
+                fence_proxy_async();        // parameters were written by other CTAs' generic stores (grid barrier acquired)
+                mbar_expect_tx(&img_bar, (unsigned int)(kNets * hhs * sizeof(float)));
+                for (int j = 0; j < kNets; ++j)
+                    tma_bulk_g2s(W2s + j * hhs, a.params + a.L.w2[j], (unsigned int)(hhs * sizeof(float)), &img_bar);
+            }
+            mbar_wait(&img_bar, (unsigned int)(step & 1));
+        }
         for (int tile = cta; tile < a.ntiles; tile += gridDim.x) {
-            split_tile<R>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
+            if (W2RES) split_tile<R, LdShared>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc, W2s, hhs);
+            else split_tile<R, LdGlobal>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc, a.params + a.L.w2[0], hh4);
             acc = true;
         }
         gb.sync();
@@ -388,14 +416,23 @@ __global__ void __launch_bounds__(kSplitThreads, 1) split_ppo_kernel(SplitArgs a
 }
 
 static int split_feet(const sg_ppo_config* c) { return c->act_dim / 7; }
-static int split_tiles(const sg_ppo_config* c) { return (c->row_end - c->row_begin + kRows - 1) / kRows; }
+// rows per tile: 8, or 4 when that still leaves at most one tile per SM (twice the CTAs on half the rows each)
+static int split_rows(const sg_ppo_config* c) {
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int rows = c->row_end - c->row_begin;
+    return (rows + 3) / 4 <= sms ? 4 : kRows;
+}
+static int split_tiles(const sg_ppo_config* c) { const int r = split_rows(c); return (c->row_end - c->row_begin + r - 1) / r; }
 static int split_grid(const sg_ppo_config* c, int* sms_out) {
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
     if (sms_out) *sms_out = sms;
     int tiles = split_tiles(c);
     int g = tiles < sms ? tiles : sms;
-    const int gmin = sms < 64 ? sms : 64;
+    // CTAs without a tile still own a slice of the reduce / clip / Adam phases; this parameter vector is 3-4x the
+    // plain policy's, so more (narrower) slices pay for the slightly slower grid barrier
+    const int gmin = sms < 128 ? sms : 128;
     if (g < gmin) g = gmin;
     return g;
 }
@@ -518,9 +555,15 @@ int sg_split_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, 
     a.perm = perm; a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
     a.ssq = (double*)(ws + w.ssq); a.bar = (unsigned int*)(ws + w.bar);
-    const size_t smem = split_smem_bytes(a.O, a.H, a.f);
+    const size_t smem_tile = split_smem_bytes(a.O, a.H, a.f);
+    const bool r4 = split_rows(cfg) == 4;
+    const size_t tile_floats = r4 ? (size_t)SplitSmem<4>::floats(a.O, a.H, a.f) : (size_t)SplitSmem<kRows>::floats(a.O, a.H, a.f);
+    const size_t smem_res = (tile_floats + (size_t)kNets * round_up(a.H * a.H, 4)) * sizeof(float);
+    const bool w2res = smem_res <= 226 * 1024 && (cfg->mode == 0 || cfg->mode == 3);      // mode 2: weights through L2 only
+    const size_t smem = w2res ? (smem_res > smem_tile ? smem_res : smem_tile) : smem_tile;
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
-    const void* fn = (const void*)split_ppo_kernel<kRows>;
+    const void* fn = r4 ? (w2res ? (const void*)split_ppo_kernel<4, true> : (const void*)split_ppo_kernel<4, false>)
+                        : (w2res ? (const void*)split_ppo_kernel<kRows, true> : (const void*)split_ppo_kernel<kRows, false>);
     SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSplitThreads, smem));

@@ -84,3 +84,19 @@ def test_split_ppo_update_vs_oracle_and_golden(case):
     torch.set_rng_state(g.t("rng_before_ppo"))
     out2 = agent2.update(_storage(g))
     assert abs(out2[0] - ref[0]) <= 1e-4 * abs(ref[0])
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_split_ppo_shared_memory_w2_copy_is_bit_identical(case):
+    """kernel_mode 0 keeps the three H x H matrices in a shared-memory copy refreshed by TMA after every Adam step,
+    kernel_mode 2 reads them through L2: same micro-kernels, same summation order -> identical parameters and traces."""
+    import simgan_b200 as sg
+    g = SplitGolden(case)
+    outs = []
+    for mode in (0, 2):
+        sp = _make(g)
+        agent = sg.PPO(sp, 0.2, g.ppo_epoch, g.nmb, 0.5, g.entropy_coef, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+        agent.kernel_mode = mode
+        agent.update(_storage(g), permutations=g.t("ppo_perm"))
+        outs.append((agent.last_trace.clone(), sp.flat_params().cpu().clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
