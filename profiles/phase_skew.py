@@ -11,7 +11,7 @@ for _ in range(3):
     w.update_phase(False)
 torch.cuda.synchronize()
 for name, obj, n, steps, labels in (("ppo", w.agent, 128, 32, ["image", "tile", "bar1", "reduce", "bar2", "adam", "bar3"]),
-                                    ("disc", w.disc, 64, w.n_disc_batches, ["image", "tile", "bar1", "reduce_adam", "bar2"])):
+                                    ("disc", w.disc, 128, w.n_disc_batches, ["image", "tile", "bar1", "reduce_adam", "bar2"])):
     pc = obj.phase_cycles_all(n).double() / steps
     print(name, "cycles per optimizer step: min / median / max over CTAs, and CTA 0")
     for i, lab in enumerate(labels):
