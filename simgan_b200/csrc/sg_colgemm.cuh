@@ -126,7 +126,7 @@ __device__ __forceinline__ void outer_cols(float* __restrict__ G, const float* _
 // Same product, one row n x an interleaved set of k-quads per work item (lighter on registers; what the PPO
 // column tile uses).  G[n*K + k] (+)= sum_r Yt[n*R + r] * X[r*ldx + k], K % 4 == 0.
 // Work item = (row n, interleaved k-quad lane s of NSEG); float4 results go straight to L2 (st.cg).
-template <int R>
+template <int R, int PF = 0>
 __device__ __forceinline__ void outer_cols_seg(float* __restrict__ G, const float* __restrict__ Yt, const float* __restrict__ X,
                                            int ldx, int N, int K, int t, int nth, bool acc) {
     const int KQ = K >> 2;
@@ -136,6 +136,33 @@ __device__ __forceinline__ void outer_cols_seg(float* __restrict__ G, const floa
         const int n = idx >> lg, s = idx & (nseg - 1);
         float y[R];
         load_rows_t<R>(Yt, n, y);
+        if (PF) {       // groups of PF quads: old values requested before the group's FMAs when accumulating (see outer_store)
+            constexpr int NB = PF > 0 ? PF : 1;
+            for (int kq0 = s; kq0 < KQ; kq0 += NB * nseg) {
+                float4 old[NB];
+                if (acc) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int kq = kq0 + j * nseg;
+                        if (kq < KQ) old[j] = __ldcg(reinterpret_cast<const float4*>(G + (size_t)n * K + 4 * kq));
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int kq = kq0 + j * nseg;
+                    if (kq >= KQ) break;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const float4 x = *reinterpret_cast<const float4*>(X + r * ldx + 4 * kq);
+                        o.x = fmaf(y[r], x.x, o.x); o.y = fmaf(y[r], x.y, o.y); o.z = fmaf(y[r], x.z, o.z); o.w = fmaf(y[r], x.w, o.w);
+                    }
+                    if (acc) { o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w; }
+                    __stcg(reinterpret_cast<float4*>(G + (size_t)n * K + 4 * kq), o);
+                }
+            }
+            continue;
+        }
         for (int kq = s; kq < KQ; kq += nseg) {
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll

@@ -243,7 +243,10 @@ __device__ __forceinline__ void gemm_yW(const float* __restrict__ W, const float
 // ------------------------------------------------------------------------------------------------
 // G[n*K+k] (+)= sum_r Yt[n*R+r] * X[r*ldx+k]       (per-CTA partial weight gradient -> global)
 // ------------------------------------------------------------------------------------------------
-template <int R, int V>
+// PF > 0 (kernels whose CTAs run several tiles per step and therefore accumulate): rows are processed in groups of PF and
+// the PF old values are requested from L2 BEFORE the group's FMAs, so that their round trips overlap each other and
+// the arithmetic instead of one exposed L2 latency per row (which was half of the tile time at cfg 5).
+template <int R, int V, int PF = 0>
 __device__ __forceinline__ void outer_store(float* __restrict__ G, const float* __restrict__ Yt,
                                             const float* __restrict__ X, int ldx, int N, int K, int t, int nth,
                                             bool acc) {
@@ -266,6 +269,46 @@ __device__ __forceinline__ void outer_store(float* __restrict__ G, const float* 
             }
         }
         const int n_end = min(N, (ns + 1) * Nper);
+        if (PF) {
+            constexpr int NB = PF > 0 ? PF : 1;
+            for (int n0 = ns * Nper; n0 < n_end; n0 += NB) {
+                float old[NB][V];
+                if (acc) {
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        if (n0 + j < n_end) {
+                            if (V == 4) {
+                                const float4 q = __ldcg(reinterpret_cast<const float4*>(G + (size_t)(n0 + j) * K + kc * 4));
+                                old[j][0] = q.x; old[j][1 % V] = q.y; old[j][2 % V] = q.z; old[j][3 % V] = q.w;
+                            } else {
+                                old[j][0] = __ldcg(G + (size_t)(n0 + j) * K + kc);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) {
+                    const int n = n0 + j;
+                    if (n >= n_end) break;
+                    float y[R];
+                    load_rows_t<R>(Yt, n, y);
+                    float o[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) o[v] = 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+#pragma unroll
+                        for (int v = 0; v < V; ++v) o[v] = fmaf(y[r], xr[r][v], o[v]);
+                    if (acc) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) o[v] += old[j][v];
+                    }
+                    if (V == 4) __stcg(reinterpret_cast<float4*>(G + (size_t)n * K + kc * 4), make_float4(o[0], o[1 % V], o[2 % V], o[3 % V]));
+                    else __stcg(G + (size_t)n * K + kc, o[0]);
+                }
+            }
+            continue;
+        }
         for (int n = ns * Nper; n < n_end; ++n) {
             float y[R];
             load_rows_t<R>(Yt, n, y);

@@ -74,9 +74,12 @@ struct PpoSmem {
 
 // ---- phase A: one tile of R minibatch rows --------------------------------------------------------
 // W = flat parameter image the weights are read from (global through L2, or the CTA's shared copy).
-template <int R, class WL>
+// MULTI: the CTA runs several tiles per step and accumulates its partial gradient across them (acc); single-tile
+// kernels compile without any accumulate code.
+template <int R, class WL, bool MULTI>
 __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step, int tile, float* __restrict__ gout,
-                         float* __restrict__ lossout, PpoSmem<R>& sm, bool acc) {
+                         float* __restrict__ lossout, PpoSmem<R>& sm, bool acc_in) {
+    const bool acc = MULTI && acc_in;
     static_assert(R == 8, "the per-row loss warp below maps 8 rows x 4 lanes");
     const int tid = threadIdx.x;
     const int O = a.O, H = a.H, A = a.A;
@@ -200,8 +203,8 @@ __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step
     {
         float* gW = gout + (half ? a.L.vw : a.L.mw);
         float* gB = gout + (half ? a.L.vb : a.L.mb);
-        if (vecH) outer_store<R, 4>(gW, Dh, h2, ldh, NH, H, t, kHalf, acc);
-        else outer_store<R, 1>(gW, Dh, h2, ldh, NH, H, t, kHalf, acc);
+        if (vecH) outer_store<R, 4, MULTI ? 8 : 0>(gW, Dh, h2, ldh, NH, H, t, kHalf, acc);
+        else outer_store<R, 1, MULTI ? 8 : 0>(gW, Dh, h2, ldh, NH, H, t, kHalf, acc);
         rowsum_store<R>(gB, Dh, NH, t, kHalf, acc);
         if (!half) rowsum_store<R>(gout + a.L.ls, sm.DLSt, A, t, kHalf, acc);
     }
@@ -213,25 +216,25 @@ __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step
     {
         float* gW2 = gout + (half ? a.L.cw2 : a.L.aw2);
         float* gB2 = gout + (half ? a.L.cb2 : a.L.ab2);
-        if (vecH) outer_store<R, 4>(gW2, dz2, h1, ldh, H, H, t, kHalf, acc);
-        else outer_store<R, 1>(gW2, dz2, h1, ldh, H, H, t, kHalf, acc);
+        if (vecH) outer_store<R, 4, MULTI ? 8 : 0>(gW2, dz2, h1, ldh, H, H, t, kHalf, acc);
+        else outer_store<R, 1, MULTI ? 8 : 0>(gW2, dz2, h1, ldh, H, H, t, kHalf, acc);
         rowsum_store<R>(gB2, dz2, H, t, kHalf, acc);
         float* gW1 = gout + (half ? a.L.cw1 : a.L.aw1);
         float* gB1 = gout + (half ? a.L.cb1 : a.L.ab1);
-        if (vecO) outer_store<R, 4>(gW1, dz1, T.X, T.ldo, H, O, t, kHalf, acc);
-        else outer_store<R, 1>(gW1, dz1, T.X, T.ldo, H, O, t, kHalf, acc);
+        if (vecO) outer_store<R, 4, MULTI ? 8 : 0>(gW1, dz1, T.X, T.ldo, H, O, t, kHalf, acc);
+        else outer_store<R, 1, MULTI ? 8 : 0>(gW1, dz1, T.X, T.ldo, H, O, t, kHalf, acc);
         rowsum_store<R>(gB1, dz1, H, t, kHalf, acc);
     }
     __syncthreads();   // smem is reused by the next tile
 }
 
-template <int R, class WL>
+template <int R, class WL, bool MULTI>
 __device__ __forceinline__ void ppo_phaseA(const PpoArgs& a, const float* W, int step, int cta, int ncta, float* smem) {
     PpoSmem<R> sm;
     sm.carve(smem, a.O, a.H, a.A);
     bool acc = false;
     for (int tile = cta; tile < a.ntiles; tile += ncta) {
-        ppo_tile<R, WL>(a, W, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
+        ppo_tile<R, WL, MULTI>(a, W, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc);
         acc = true;
     }
 }
@@ -349,9 +352,13 @@ __device__ __forceinline__ void ppo_prefetch_rows(const PpoArgs& a, PpoPrefetch&
     pf.valid = true;
 }
 
-template <int R, int RG>
+template <int R, int RG, bool MULTI>
 __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int step, int tile, float* __restrict__ gout,
-                             float* __restrict__ lossout, PpoSmemCol<R>& sm, bool acc, PpoPrefetch& pf) {
+                             float* __restrict__ lossout, PpoSmemCol<R>& sm, bool acc_in, PpoPrefetch& pf) {
+    // old-value prefetch depth of the outer products when accumulating: 8 (as in the generic tile) spills inside the hot
+    // loops of this kernel, which is already at the register limit -- measured slower than no prefetch at all
+    constexpr int CPF = MULTI ? 4 : 0;
+    const bool acc = MULTI && acc_in;
     constexpr int RT = R / RG;            // rows per thread
     constexpr int NC = kHalf / RG;        // column lanes per net
     constexpr int LPR = 32 / R;           // lanes per row in the loss warp
@@ -556,24 +563,24 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
     {
         const float* Dh = half ? sm.DVt : sm.DMUt;
         const int NH = half ? 1 : A;
-        outer_cols_seg<R>(gout + (half ? a.L.vw : a.L.mw), Dh, h2, ldh, NH, H, t, kHalf, acc);
+        outer_cols_seg<R, CPF>(gout + (half ? a.L.vw : a.L.mw), Dh, h2, ldh, NH, H, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.vb : a.L.mb), Dh, NH, t, kHalf, acc);
         if (!half) rowsum_store<R>(gout + a.L.ls, sm.DLSt, A, t, kHalf, acc);
-        outer_cols_seg<R>(gout + (half ? a.L.cw2 : a.L.aw2), dz2t, h1, ldh, H, H, t, kHalf, acc);
+        outer_cols_seg<R, CPF>(gout + (half ? a.L.cw2 : a.L.aw2), dz2t, h1, ldh, H, H, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.cb2 : a.L.ab2), dz2t, H, t, kHalf, acc);
     }
     __syncthreads();
     {
         float* gW1 = gout + (half ? a.L.cw1 : a.L.aw1);
-        if ((O & 3) == 0) outer_cols_seg<R>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
-        else outer_store<R, 1>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
+        if ((O & 3) == 0) outer_cols_seg<R, CPF>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
+        else outer_store<R, 1, CPF>(gW1, dz1t, sm.X, ldo, H, O, t, kHalf, acc);
         rowsum_store<R>(gout + (half ? a.L.cb1 : a.L.ab1), dz1t, H, t, kHalf, acc);
     }
     if (pf_next) ppo_prefetch_rows<R>(a, pf, ldo, lda);                        // stage 2: the rows themselves
     __syncthreads();   // smem is reused by the next tile
 }
 
-template <int R>
+template <int R, bool MULTI>
 __device__ __forceinline__ void ppo_phaseA_col(const PpoArgs& a, const float* Wi, int step, int cta, int ncta, float* smem,
                                                PpoPrefetch& pf) {
     PpoSmemCol<R> sm;
@@ -582,8 +589,8 @@ __device__ __forceinline__ void ppo_phaseA_col(const PpoArgs& a, const float* Wi
     for (int tile = cta; tile < a.ntiles; tile += ncta) {
         float* g = a.gpart + (size_t)cta * a.P;
         float* l = a.losspart + cta * 4;
-        if (a.H > 64) ppo_tile_col<R, 1>(a, Wi, step, tile, g, l, sm, acc, pf);
-        else ppo_tile_col<R, 2>(a, Wi, step, tile, g, l, sm, acc, pf);
+        if (a.H > 64) ppo_tile_col<R, 1, MULTI>(a, Wi, step, tile, g, l, sm, acc, pf);
+        else ppo_tile_col<R, 2, MULTI>(a, Wi, step, tile, g, l, sm, acc, pf);
         acc = true;
     }
 }
@@ -745,7 +752,7 @@ __device__ __forceinline__ void poison_trace_on_timeout(const PpoArgs& a) {
 // RESIDENT: every CTA refreshes a private shared-memory image of the parameters after each Adam step and
 // the tile phase reads its weights from there; otherwise weights are read from global memory through L2.
 // RESIDENT 2 = column-owner tile with the NQ weight image (H % 4 == 0), 1 = generic tile on a natural image.
-template <int R, int RESIDENT>
+template <int R, int RESIDENT, bool MULTI>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[kStepThreads / 32];
@@ -769,24 +776,24 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
     for (int step = 0; step < a.nsteps; ++step) {
         float4 mine;
         bool have;
-        if (RESIDENT == 2) {
+        if constexpr (RESIDENT == 2) {
             load_policy_image(Ws, stage, a.params, a.L, a.LI, a.H, threadIdx.x, &img_bar, (unsigned int)(step & 1));
             pc.lap(0);
-            ppo_phaseA_col<R>(a, Ws, step, blockIdx.x, gridDim.x, tile, pf);
+            ppo_phaseA_col<R, MULTI>(a, Ws, step, blockIdx.x, gridDim.x, tile, pf);
             pc.lap(1);
             gb.sync();
             pc.lap(2);
             have = ppo_reduce_slice<LdShared, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.LI.ls, mine);
-        } else if (RESIDENT == 1) {
+        } else if constexpr (RESIDENT == 1) {
             load_param_image(Ws, a.params, a.P, threadIdx.x);
             pc.lap(0);
-            ppo_phaseA<R, LdShared>(a, Ws, step, blockIdx.x, gridDim.x, tile);
+            ppo_phaseA<R, LdShared, MULTI>(a, Ws, step, blockIdx.x, gridDim.x, tile);
             pc.lap(1);
             gb.sync();
             pc.lap(2);
             have = ppo_reduce_slice<LdShared, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), Ws + a.L.ls, mine);
         } else {
-            ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, tile);
+            ppo_phaseA<R, LdGlobal, MULTI>(a, a.params, step, blockIdx.x, gridDim.x, tile);
             pc.lap(1);
             gb.sync();
             pc.lap(2);
@@ -818,7 +825,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
 template <int R>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_phaseA_kernel(PpoArgs a, int step) {
     extern __shared__ __align__(16) float smem[];
-    ppo_phaseA<R, LdGlobal>(a, a.params, step, blockIdx.x, gridDim.x, smem);
+    ppo_phaseA<R, LdGlobal, true>(a, a.params, step, blockIdx.x, gridDim.x, smem);
 }
 __global__ void __launch_bounds__(kStepThreads) ppo_phaseB_kernel(PpoArgs a) {
     __shared__ float4 scr4[kStepThreads];
@@ -834,7 +841,20 @@ __global__ void __launch_bounds__(kStepThreads) ppo_phaseC_kernel(PpoArgs a, int
     ppo_adam_slice(a, step, blockIdx.x, red, false, make_float4(0.f, 0.f, 0.f, 0.f));
 }
 
-static int ppo_tiles(const sg_ppo_config* c) { return (c->row_end - c->row_begin + kRows - 1) / kRows; }
+static bool ppo_col_ok(const sg_ppo_config* c);
+static size_t ppo_resident_smem_bytes_r(const sg_ppo_config* c, int rows);
+constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus static shared memory headroom
+// rows per tile: 8; 16 for the column-owner resident kernel once every CTA has several tiles per step anyway (large
+// minibatches): half as many tiles, twice the FMAs per weight fetched from shared memory, half the read-modify-write
+// traffic of the per-CTA partial gradient
+static int ppo_rows(const sg_ppo_config* c) {
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const int rows = c->row_end - c->row_begin;
+    const bool resident_col = (c->mode == 0 || c->mode == 3) && ppo_col_ok(c) && ppo_resident_smem_bytes_r(c, 16) <= kMaxDynSmem;
+    return (resident_col && rows >= 4 * kRows * sms) ? 16 : kRows;
+}
+static int ppo_tiles(const sg_ppo_config* c) { const int r = ppo_rows(c); return (c->row_end - c->row_begin + r - 1) / r; }
 
 // number of CTAs of the tile phase == number of partial-gradient slots == number of gradient slices
 static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
@@ -855,10 +875,11 @@ static size_t ppo_tile_smem_floats(const sg_ppo_config* c) {
     return f < 4 * (kStepThreads + 128) ? 4 * (kStepThreads + 128) : f;      // phase B needs 256+128 float4 of scratch
 }
 static bool ppo_col_ok(const sg_ppo_config* c) { return (c->hidden & 3) == 0; }
-static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
+static size_t ppo_resident_smem_bytes_r(const sg_ppo_config* c, int rows) {
     if (ppo_col_ok(c)) {
         PolicyLayout LI = make_policy_image_layout(c->obs_dim, c->hidden, c->act_dim);
-        size_t tile = (size_t)PpoSmemCol<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
+        size_t tile = rows == 16 ? (size_t)PpoSmemCol<16>::floats(c->obs_dim, c->hidden, c->act_dim)
+                                 : (size_t)PpoSmemCol<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
         const size_t stage = 2 * (size_t)c->hidden * c->hidden;            // TMA landing zone of the two W2 blocks
         if (tile + stage < 4 * (kStepThreads + 128)) tile = 4 * (kStepThreads + 128);
         return ((size_t)LI.total + tile + stage) * sizeof(float);
@@ -866,7 +887,7 @@ static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) {
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
     return ((size_t)L.total + ppo_tile_smem_floats(c)) * sizeof(float);
 }
-constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus static shared memory headroom
+static size_t ppo_resident_smem_bytes(const sg_ppo_config* c) { return ppo_resident_smem_bytes_r(c, kRows); }
 
 static int ppo_validate(const sg_ppo_config* c) {
     SG_REQUIRE(c, "sg_ppo: null config");
@@ -972,15 +993,24 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     }
 
     const size_t smem_tile = ppo_tile_smem_floats(cfg) * sizeof(float);
-    const size_t smem_res = ppo_resident_smem_bytes(cfg);
+    const int tile_rows = ppo_rows(cfg);
+    const size_t smem_res = ppo_resident_smem_bytes_r(cfg, tile_rows);
     int mode = cfg->mode;
     if (mode == 0) mode = smem_res <= kMaxDynSmem ? 3 : 2;
     // partial-gradient padding lanes must be zero; barrier words must be zero
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
 
     if (mode == 3 || mode == 2) {
-        const void* fn = mode == 3 ? (ppo_col_ok(cfg) ? (const void*)ppo_persistent_kernel<kRows, 2> : (const void*)ppo_persistent_kernel<kRows, 1>)
-                                   : (const void*)ppo_persistent_kernel<kRows, 0>;
+        const bool multi = a.ntiles > grid;
+        const void* fn;
+        if (mode == 3 && ppo_col_ok(cfg)) {
+            if (tile_rows == 16) fn = (const void*)ppo_persistent_kernel<16, 2, true>;
+            else fn = multi ? (const void*)ppo_persistent_kernel<kRows, 2, true> : (const void*)ppo_persistent_kernel<kRows, 2, false>;
+        } else if (mode == 3) {
+            fn = multi ? (const void*)ppo_persistent_kernel<kRows, 1, true> : (const void*)ppo_persistent_kernel<kRows, 1, false>;
+        } else {
+            fn = multi ? (const void*)ppo_persistent_kernel<kRows, 0, true> : (const void*)ppo_persistent_kernel<kRows, 0, false>;
+        }
         const size_t smem = mode == 3 ? smem_res : smem_tile;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;

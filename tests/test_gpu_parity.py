@@ -746,3 +746,35 @@ def test_relabel_running_stats_bitexact_vs_numpy(T, N, scale, start):
     assert got[0] == float(ref.mean) and got[1] == float(ref.var) and got[2] == float(ref.count), (got, ref.mean, ref.var, ref.count)
     assert np.array_equal(rewards.cpu().numpy()[:, :, 0], ref_rewards)
     assert torch.equal(dret.cpu()[:, 0], ret)
+
+
+@pytest.mark.parametrize("O,H,A", [(11, 16, 3), (13, 64, 7)])
+def test_large_minibatch_uses_16_row_tiles(O, H, A):
+    """Minibatches of >= 4*8*#SM rows run the column-owner kernel with 16-row tiles and several tiles per CTA
+    (per-CTA partial gradients accumulated across tiles); a ragged last tile included.  Against the oracle, and
+    against the generic 8-row kernel (kernel_mode 2)."""
+    torch.manual_seed(1)
+    T, N = 1251, 8                                             # 10008 samples -> 2 minibatches of 5004 rows (312.75 tiles)
+    p = orc.init_policy(O, H, A)
+    buf = orc.synth_rollout(T, N, O, A, 3, p, seed=4, ep_len=50.0)
+    nv = orc.policy_forward(p, buf["obs"][-1])[0]
+    orc.compute_returns(buf, nv, True, 0.99, 0.95, True)
+    hyper = orc.PPOHyper(ppo_epoch=2, num_mini_batch=2)
+    ora = orc.PPOOracle(p, hyper)
+    torch.manual_seed(7)
+    trace = []
+    ora.update(buf, trace=trace)
+    tr_o = np.array(trace)
+    outs = []
+    for mode in (0, 2):
+        pol = gu.make_policy(p, O, H, A)
+        agent = sg.PPO(pol, 0.2, 2, 2, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+        agent.kernel_mode = mode
+        torch.manual_seed(7)
+        agent.update(gu.make_storage(buf, O, A, 3))
+        outs.append((agent.last_trace.double().numpy(), pol.flat_params().cpu().clone()))
+    scale = np.abs(tr_o).max(axis=0)
+    scale[1] = max(scale[1], 0.5)
+    for tr, _ in outs:
+        assert np.all(np.abs(tr - tr_o) <= LOSS_RTOL * scale + 1e-6), np.abs(tr - tr_o).max(axis=0) / scale
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-3, atol=2e-5)
