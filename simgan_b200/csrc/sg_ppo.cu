@@ -388,10 +388,23 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
             rValid[r] = ok ? 1.f : 0.f;
         }
     } else {
-        for (int e = tid; e < R * ldo; e += kStepThreads) {
-            const int r = e / ldo, k = e - r * ldo;
-            const int row = row0 + r;
-            sm.X[e] = (row < a.row_end && k < O) ? a.obs[(size_t)idx[row] * O + k] : 0.f;
+        // batches of 8 elements per thread: all sampler-index loads, then all row loads, then the stores -- two exposed
+        // L2 round trips per batch instead of two per element (multi-tile CTAs cannot prefetch across barriers)
+        constexpr int GB = 8;
+        for (int e0 = tid; e0 < R * ldo; e0 += GB * kStepThreads) {
+            float v[GB];
+#pragma unroll
+            for (int j = 0; j < GB; ++j) {
+                const int e = e0 + j * kStepThreads;
+                const int r = e / ldo, k = e - r * ldo;
+                const int row = row0 + r;
+                v[j] = (e < R * ldo && row < a.row_end && k < O) ? a.obs[(size_t)idx[row] * O + k] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < GB; ++j) {
+                const int e = e0 + j * kStepThreads;
+                if (e < R * ldo) sm.X[e] = v[j];
+            }
         }
         for (int e = tid; e < R * lda; e += kStepThreads) {
             const int r = e / lda, k = e - r * lda;
