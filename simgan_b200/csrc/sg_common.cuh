@@ -38,6 +38,22 @@ void count_launches(int n);   // kernel launches issued by this library (sg_laun
         }                                                  \
     } while (0)
 
+// Largest dynamic shared-memory size already granted to one kernel, per device (function attributes are per device;
+// a process normally drives one GPU, but nothing here may assume it).
+struct SmemGrant {
+    size_t granted[64] = {};
+};
+template <class K>
+inline int grant_smem(SmemGrant& g, K kernel, size_t smem) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > g.granted[dev]) {
+        SG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        g.granted[dev] = smem;
+    }
+    return SG_OK;
+}
+
 constexpr int kStepThreads = 256;   // threads per CTA of the step kernels
 constexpr int kHalf = 128;          // actor / critic halves
 constexpr int kRows = 8;            // minibatch rows per CTA tile

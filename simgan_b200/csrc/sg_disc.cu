@@ -860,11 +860,8 @@ static int launch_reward(const float* params, int F, int H, const float* d_in, i
     DiscLayout L = make_disc_layout(F, H);
     const size_t smem = (size_t)(L.total + kRows * round_up(F, 4) + 2 * kRows * round_up(H, 4) + kRows) * sizeof(float);
     SG_REQUIRE(smem <= 220 * 1024, "disc reward: tile + parameter image need %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SG_CUDA(cudaFuncSetAttribute(disc_reward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_smem(grant, disc_reward_kernel, smem)) return rc;
     int tiles = (n_rows + kRows - 1) / kRows;
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
@@ -998,11 +995,8 @@ static int relabel_from_raw(const float* raw, const float* masks, float* rewards
     float* bmean = (float*)(ws + w.bmean);
     float* bvar = (float*)(ws + w.bvar);
     double* scale = (double*)(ws + w.scale);
-    static bool scan_smem_set = false;
-    if (!scan_smem_set) {
-        SG_CUDA(cudaFuncSetAttribute(relabel_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRlScanSmemBytes));
-        scan_smem_set = true;
-    }
+    static SmemGrant scan_grant;
+    if (int rc = grant_smem(scan_grant, relabel_scan_kernel, kRlScanSmemBytes)) return rc;
     relabel_scan_kernel<<<(N + 31) / 32, 256, kRlScanSmemBytes, s>>>(raw, masks, ret_all, disc_returns, T, N, (float)gamma, has_returns);
     relabel_moments_kernel<<<(T + 127) / 128, 128, 0, s>>>(ret_all, T, N, bmean, bvar, mean_returns);
     relabel_rms_kernel<<<1, 256, 0, s>>>(bmean, bvar, T, N, rms_state, scale);

@@ -361,13 +361,13 @@ int sg_compute_returns(const float* rewards, float* value_preds, const float* ma
     const float g = (float)gamma, gl = (float)(gamma * gae_lambda);
     const int mode = use_gae ? (use_proper_time_limits ? 0 : 1) : (use_proper_time_limits ? 2 : 3);
     const int sb = (N + 31) / 32;
-    static bool smem_set = false;
-    if (!smem_set) {
-        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
-        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
-        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
-        SG_CUDA(cudaFuncSetAttribute(returns_scan_staged_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmemBytes));
-        smem_set = true;
+    static SmemGrant grants[4];
+    {
+        int rc = mode == 0 ? grant_smem(grants[0], returns_scan_staged_kernel<0>, kScanSmemBytes)
+               : mode == 1 ? grant_smem(grants[1], returns_scan_staged_kernel<1>, kScanSmemBytes)
+               : mode == 2 ? grant_smem(grants[2], returns_scan_staged_kernel<2>, kScanSmemBytes)
+                           : grant_smem(grants[3], returns_scan_staged_kernel<3>, kScanSmemBytes);
+        if (rc) return rc;
     }
     switch (mode) {
         case 0: returns_scan_staged_kernel<0><<<sb, 256, kScanSmemBytes, s>>>(rewards, value_preds, masks, bad_masks, returns, next_value, T, N, g, gl); break;
@@ -441,11 +441,8 @@ int sg_policy_forward(const float* params, int obs_dim, int hidden, int act_dim,
     PolicyLayout L = make_policy_layout(obs_dim, hidden, act_dim);
     const size_t smem = (size_t)PolicyTile<kRows>::floats(obs_dim, hidden, act_dim) * sizeof(float);
     SG_REQUIRE(smem <= 200 * 1024, "sg_policy_forward: tile needs %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SG_CUDA(cudaFuncSetAttribute(policy_forward_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_smem(grant, policy_forward_kernel<kRows>, smem)) return rc;
     int tiles = (B + kRows - 1) / kRows;
     int grid = tiles < 1184 ? tiles : 1184;
     policy_forward_kernel<kRows><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(params, L, obs_dim, hidden, act_dim, obs, B,
@@ -474,11 +471,8 @@ int sg_rollout_feed(const float* params, int obs_dim, int hidden, int act_dim, i
     a.action_log_probs = action_log_probs; a.actions = actions; a.masks = masks; a.bad_masks = bad_masks; a.action_out = action_out;
     const size_t smem = (size_t)PolicyTile<kRows>::floats(obs_dim, hidden, act_dim) * sizeof(float);
     SG_REQUIRE(smem <= 200 * 1024, "sg_rollout_feed: tile needs %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SG_CUDA(cudaFuncSetAttribute(rollout_feed_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_smem(grant, rollout_feed_kernel<kRows>, smem)) return rc;
     int tiles = (N + kRows - 1) / kRows;
     int grid = tiles < 1184 ? tiles : 1184;
     rollout_feed_kernel<kRows><<<grid, kStepThreads, smem, (cudaStream_t)stream>>>(a);

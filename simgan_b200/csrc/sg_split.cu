@@ -500,11 +500,8 @@ int sg_split_forward(const float* params, int obs_dim, int hidden, int num_feet,
     SplitLayout L = make_split_layout(obs_dim, hidden, num_feet);
     const size_t smem = split_smem_bytes(obs_dim, hidden, num_feet);
     SG_REQUIRE(smem <= 226 * 1024, "sg_split_forward: tile needs %zu bytes of shared memory", smem);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        SG_CUDA(cudaFuncSetAttribute(split_forward_kernel<kRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemGrant grant;
+    if (int rc = grant_smem(grant, split_forward_kernel<kRows>, smem)) return rc;
     int tiles = (B + kRows - 1) / kRows;
     int grid = tiles < 592 ? tiles : 592;
     split_forward_kernel<kRows><<<grid, kSplitThreads, smem, (cudaStream_t)stream>>>(params, L, obs_dim, hidden, num_feet, obs, B, noise,
