@@ -80,7 +80,8 @@ template <int R, class WL, bool MULTI>
 __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step, int tile, float* __restrict__ gout,
                          float* __restrict__ lossout, PpoSmem<R>& sm, bool acc_in) {
     const bool acc = MULTI && acc_in;
-    static_assert(R == 8, "the per-row loss warp below maps 8 rows x 4 lanes");
+    static_assert(R == 8 || R == 16, "the per-row loss warp below maps R rows x 32/R lanes");
+    constexpr int LPR = 32 / R;           // lanes per row in the loss warp
     const int tid = threadIdx.x;
     const int O = a.O, H = a.H, A = a.A;
     const PolicyTile<R>& T = sm.T;
@@ -117,22 +118,22 @@ __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step
 
     policy_tile_forward<R, WL>(W, a.L, O, H, A, T, tid);
 
-    // per-row losses and the gradient seeds d loss / d mu, d loss / d value: one warp, 4 lanes per row
+    // per-row losses and the gradient seeds d loss / d mu, d loss / d value: one warp, LPR lanes per row
     const float* ls = W + a.L.ls;
     if (tid < 32) {
-        const int r = tid >> 2, sub = tid & 3;
+        const int r = tid / LPR, sub = tid % LPR;
         const bool ok = rValid[r] != 0.f;
         const float invB = 1.f / (float)a.mbs;
         // log-prob of the stored action, summed over the action dim (A2C/distributions.py:52-53)
         float lp = 0.f;
-        for (int k = sub; k < A; k += 4) {
+        for (int k = sub; k < A; k += LPR) {
             const float sigma = expf(WL::ld(ls + k));
             const float var = sigma * sigma;
             const float d = T.ACT[r * T.lda + k] - T.MU[r * T.lda + k];
             lp += -(d * d) / (2.f * var) - logf(sigma) - SG_LOG_SQRT_2PI;
         }
-        lp += __shfl_xor_sync(0xffffffffu, lp, 1);
-        lp += __shfl_xor_sync(0xffffffffu, lp, 2);
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
         float vl = 0.f, al = 0.f, dv = 0.f, coef = 0.f;
         if (ok) {
             const float ratio = expf(lp - rOlp[r]);
@@ -161,7 +162,7 @@ __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step
                 dv = a.c_v * invB * (v - ret);
             }
         }
-        for (int k = sub; k < A; k += 4) {
+        for (int k = sub; k < A; k += LPR) {
             const float sigma = expf(WL::ld(ls + k));
             const float var = sigma * sigma;
             const float d = T.ACT[r * T.lda + k] - T.MU[r * T.lda + k];
@@ -172,7 +173,7 @@ __device__ void ppo_tile(const PpoArgs& a, const float* __restrict__ W, int step
         // loss sums over the tile's rows (lanes sub==0 carry them), fixed butterfly order
         float svl = sub == 0 ? vl : 0.f, sal = sub == 0 ? al : 0.f;
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
+        for (int o = LPR; o < 32; o <<= 1) {
             svl += __shfl_xor_sync(0xffffffffu, svl, o);
             sal += __shfl_xor_sync(0xffffffffu, sal, o);
         }
@@ -860,12 +861,17 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus stat
 // rows per tile: 8; 16 for the column-owner resident kernel once every CTA has several tiles per step anyway (large
 // minibatches): half as many tiles, twice the FMAs per weight fetched from shared memory, half the read-modify-write
 // traffic of the per-CTA partial gradient
+static size_t ppo_tile_smem_floats_r(const sg_ppo_config* c, int rows);
 static int ppo_rows(const sg_ppo_config* c) {
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
     const int rows = c->row_end - c->row_begin;
-    const bool resident_col = (c->mode == 0 || c->mode == 3) && ppo_col_ok(c) && ppo_resident_smem_bytes_r(c, 16) <= kMaxDynSmem;
-    return (resident_col && rows >= 4 * kRows * sms) ? 16 : kRows;
+    if (rows < 4 * kRows * sms || c->mode == 1) return kRows;
+    const bool want_res = c->mode == 0 || c->mode == 3;
+    if (want_res && ppo_resident_smem_bytes_r(c, kRows) <= kMaxDynSmem)      // a resident kernel will run
+        return (ppo_col_ok(c) && ppo_resident_smem_bytes_r(c, 16) <= kMaxDynSmem) ? 16 : kRows;
+    if (c->mode == 3) return kRows;                                           // (validation rejects it anyway)
+    return ppo_tile_smem_floats_r(c, 16) * sizeof(float) <= kMaxDynSmem ? 16 : kRows;   // weights through L2
 }
 static int ppo_tiles(const sg_ppo_config* c) { const int r = ppo_rows(c); return (c->row_end - c->row_begin + r - 1) / r; }
 
@@ -883,10 +889,12 @@ static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
     return g < 1 ? 1 : g;
 }
 
-static size_t ppo_tile_smem_floats(const sg_ppo_config* c) {
-    size_t f = (size_t)PpoSmem<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
+static size_t ppo_tile_smem_floats_r(const sg_ppo_config* c, int rows) {
+    size_t f = rows == 16 ? (size_t)PpoSmem<16>::floats(c->obs_dim, c->hidden, c->act_dim)
+                          : (size_t)PpoSmem<kRows>::floats(c->obs_dim, c->hidden, c->act_dim);
     return f < 4 * (kStepThreads + 128) ? 4 * (kStepThreads + 128) : f;      // phase B needs 256+128 float4 of scratch
 }
+static size_t ppo_tile_smem_floats(const sg_ppo_config* c) { return ppo_tile_smem_floats_r(c, kRows); }
 static bool ppo_col_ok(const sg_ppo_config* c) { return (c->hidden & 3) == 0; }
 static size_t ppo_resident_smem_bytes_r(const sg_ppo_config* c, int rows) {
     if (ppo_col_ok(c)) {
@@ -1005,8 +1013,8 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
         memset(&a.dp, 0, sizeof(a.dp));
     }
 
-    const size_t smem_tile = ppo_tile_smem_floats(cfg) * sizeof(float);
     const int tile_rows = ppo_rows(cfg);
+    const size_t smem_tile = ppo_tile_smem_floats_r(cfg, tile_rows) * sizeof(float);
     const size_t smem_res = ppo_resident_smem_bytes_r(cfg, tile_rows);
     int mode = cfg->mode;
     if (mode == 0) mode = smem_res <= kMaxDynSmem ? 3 : 2;
@@ -1021,6 +1029,8 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
             else fn = multi ? (const void*)ppo_persistent_kernel<kRows, 2, true> : (const void*)ppo_persistent_kernel<kRows, 2, false>;
         } else if (mode == 3) {
             fn = multi ? (const void*)ppo_persistent_kernel<kRows, 1, true> : (const void*)ppo_persistent_kernel<kRows, 1, false>;
+        } else if (tile_rows == 16) {
+            fn = (const void*)ppo_persistent_kernel<16, 0, true>;
         } else {
             fn = multi ? (const void*)ppo_persistent_kernel<kRows, 0, true> : (const void*)ppo_persistent_kernel<kRows, 0, false>;
         }

@@ -748,11 +748,12 @@ def test_relabel_running_stats_bitexact_vs_numpy(T, N, scale, start):
     assert torch.equal(dret.cpu()[:, 0], ret)
 
 
-@pytest.mark.parametrize("O,H,A", [(11, 16, 3), (13, 64, 7)])
+@pytest.mark.parametrize("O,H,A", [(11, 16, 3), (13, 64, 7), (20, 256, 5)])
 def test_large_minibatch_uses_16_row_tiles(O, H, A):
-    """Minibatches of >= 4*8*#SM rows run the column-owner kernel with 16-row tiles and several tiles per CTA
-    (per-CTA partial gradients accumulated across tiles); a ragged last tile included.  Against the oracle, and
-    against the generic 8-row kernel (kernel_mode 2)."""
+    """Minibatches of >= 4*8*#SM rows run 16-row tiles and several tiles per CTA (per-CTA partial gradients
+    accumulated across tiles); a ragged last tile included.  kernel_mode 0 = column-owner kernel (or, at H=256 where
+    the weights do not fit shared memory, the generic tile through L2), kernel_mode 2 = generic tile through L2.
+    Against the oracle and against each other."""
     torch.manual_seed(1)
     T, N = 1251, 8                                             # 10008 samples -> 2 minibatches of 5004 rows (312.75 tiles)
     p = orc.init_policy(O, H, A)
