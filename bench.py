@@ -394,6 +394,23 @@ def run_cuda(args):
                     us_per_optimizer_step=1e3 * kernels[dom]["ms_per_launch"] / steps_in_launch,
                     note="fp32 FMA kernel on a serial chain of optimizer steps (grid barriers between phases): "
                          "latency-bound, neither roofline binds at this size")
+        # what does bind (SURVEY.md 8d caveat): the CUDA-core fp32 peak the arithmetic actually runs against, and the
+        # serial-step floor = grid barriers + weight refresh that every one of the dependent steps has to pay
+        sm_mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+        sms = int(lib.sg_device_sm_count()) or 148
+        fma_peak = sms * 128 * 2 * sm_mhz * 1e6 / 1e12
+        if roof.get("unit") == "TFLOP/s":
+            roof.update(fp32_fma_peak_tflops=fma_peak, frac_of_fp32_fma_peak=roof["achieved"] / fma_peak)
+        try:
+            if dom in ("disc_update", "ppo_update") and not c.get("split"):
+                ph = dict(zip(["image", "tile", "bar1", "reduce_adam", "bar2"], w.disc.phase_cycles())) if dom == "disc_update" else \
+                    dict(zip(["image", "tile", "bar1", "reduce_ssq", "bar2", "clip_adam", "bar3"], w.agent.phase_cycles()))
+                sync = sum(v for k, v in ph.items() if k.startswith("bar") or k == "image")
+                roof["serial_chain"] = dict(steps_per_launch=steps_in_launch,
+                                            us_sync_and_refresh_per_step=sync / steps_in_launch / sm_mhz,
+                                            us_tile_phase_per_step=ph["tile"] / steps_in_launch / sm_mhz)
+        except Exception:
+            pass
     out = {
         "metric": "PPO+GAIL update-steps/sec", "value": w.opt_steps * args.steps / (ms_total * 1e-3),
         "unit": "optimizer steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
