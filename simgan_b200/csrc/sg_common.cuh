@@ -470,7 +470,9 @@ __device__ __forceinline__ bool reduce_partials_slice(const float* __restrict__ 
     mine = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n4 <= 0) { __syncthreads(); return true; }
     if (n4 <= 128) {
-        const int NQ = NT / n4;
+        // threads per float4 column; capped so that the serial combine below stays short for a very short slice
+        // (the last slice of the vector: 3 float4 -> 85 partial sums per column made that CTA the straggler of the phase)
+        const int NQ = NT / n4 < 16 ? NT / n4 : 16;
         const int j = tid % n4, q = tid / n4;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q < NQ) {
