@@ -123,9 +123,10 @@ class PPO(object):
         cfg.use_clipped_value_loss = int(bool(self.use_clipped_value_loss))
         cfg.first_adam_step = opt.step_count + 1
         cfg.row_begin, cfg.row_end = (0, mbs) if self.dp is None else self.dp.shard(mbs)
-        if is_split and self.dp is not None:
-            raise NotImplementedError("data-parallel updates are not wired for SplitPolicy yet")
         p2p = self.dp is not None and self.dp.p2p_ok(mbs)
+        if is_split and self.dp is not None and not p2p:
+            raise NotImplementedError("SplitPolicy data-parallel updates need the p2p transport and a minibatch size "
+                                      "divisible by the world size (there is no phased split kernel for the nccl callback)")
         cfg.mode = self.kernel_mode if (self.dp is None or p2p) else 1
         if cfg.mode == 1 and p2p:
             cfg.mode = 0
@@ -183,7 +184,8 @@ class PPO(object):
 
         self._prof_view = (ws, 0 if is_split else int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
         if p2p:
-            self.dp.sum_trace_(trace, 2)      # value / action loss columns are per-rank partial sums
+            # value / action loss columns (and SplitPolicy's state-dependent entropy) are per-rank partial sums
+            self.dp.sum_trace_(trace, 3 if is_split else 2)
         _spec.host_idle()           # the next consumer of the CPU generator draws while the last epoch runs
         tr = _lib.read_back(trace)  # the one host sync of the update
         if not bool(torch.isfinite(tr).all()):

@@ -15,8 +15,12 @@
 // two means before the two log-stds.
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
+#include "sg_dp.cuh"
+#include <string.h>
 
 namespace sg {
+
+DpView dp_view(const void* ctx);
 
 constexpr int kSplitThreads = 384;
 constexpr int kNets = 3;
@@ -181,6 +185,9 @@ struct SplitArgs {
     float *gpart, *grad, *losspart;
     double* ssq;
     unsigned int* bar;
+    int first_adam_step;
+    int dp_on;            // fused peer-memory gradient exchange (sg_dp.cuh), as in sg_ppo.cu
+    DpView dp;
 };
 
 template <int R, class WL2>
@@ -378,6 +385,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) split_ppo_kernel(SplitArgs a
             s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
             if (tid == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2); }
         }
+        // data parallel: swap my locally reduced slice with the peers' over NVLink, keep the rank-ordered total
+        if (a.dp_on) dp_exchange_slice<NT>(a.dp, a.grad, p0, p1, cta, (unsigned int)(a.first_adam_step + step), nullptr);
         {
             double s = 0.0;
             for (int p = p0 + 4 * tid; p < p1; p += 4 * NT) {
@@ -451,7 +460,6 @@ static int split_validate(const sg_ppo_config* c) {
     SG_REQUIRE(c->row_begin >= 0 && c->row_begin < c->row_end && c->row_end <= c->mini_batch_size,
                "sg_split_ppo: shard [%d,%d) outside minibatch of %d rows", c->row_begin, c->row_end, c->mini_batch_size);
     SG_REQUIRE(c->first_adam_step >= 1, "sg_split_ppo: first_adam_step is 1-based");
-    SG_REQUIRE(c->dp_ctx == nullptr, "sg_split_ppo: data-parallel exchange is not wired for SplitPolicy yet");
     SG_REQUIRE(split_smem_bytes(c->obs_dim, c->hidden, split_feet(c)) <= 226 * 1024, "sg_split_ppo: tile does not fit shared memory");
     return SG_OK;
 }
@@ -552,6 +560,14 @@ int sg_split_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, 
     a.perm = perm; a.step_size = step_size; a.bc2_sqrt = bc2_sqrt; a.trace = trace;
     a.gpart = (float*)(ws + w.gpart); a.grad = (float*)(ws + w.grad); a.losspart = (float*)(ws + w.losspart);
     a.ssq = (double*)(ws + w.ssq); a.bar = (unsigned int*)(ws + w.bar);
+    a.first_adam_step = cfg->first_adam_step;
+    a.dp_on = cfg->dp_ctx != nullptr;
+    if (a.dp_on) {
+        a.dp = dp_view(cfg->dp_ctx);
+        SG_REQUIRE(a.dp.cap >= a.P + 4 && a.nslices < kDpMaxSlices, "sg_split_ppo_update: dp context too small (%d floats, %d slices)", a.dp.cap, a.nslices);
+    } else {
+        memset(&a.dp, 0, sizeof(a.dp));
+    }
     const size_t smem_tile = split_smem_bytes(a.O, a.H, a.f);
     const bool r4 = split_rows(cfg) == 4;
     const size_t tile_floats = r4 ? (size_t)SplitSmem<4>::floats(a.O, a.H, a.f) : (size_t)SplitSmem<kRows>::floats(a.O, a.H, a.f);

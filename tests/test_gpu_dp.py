@@ -95,3 +95,68 @@ def test_data_parallel_matches_single_gpu(case, transport, tmp_path):
     out = str(tmp_path / "ok")
     mp.spawn(_worker, args=(world, _free_port(), case, out, transport), nprocs=world, join=True)
     assert os.path.exists(out)
+
+
+def _split_case(g, dp_on, dev):
+    import gpu_util as gu
+    import simgan_b200 as sg
+    from oracle import ppo_gail_oracle as orc
+    from oracle.ref_shim import BoxSpace
+    from simgan_b200 import dist as sg_dist
+    gu.DEV = dev
+    sp = sg.SplitPolicy((g.O,), BoxSpace(g.A), base_kwargs={"hidden_size": g.H, "num_feet": g.feet})
+    for q, k in zip(sp.parameters(), orc.SPLIT_KEYS):
+        q.data.copy_(g.t("sp0_%s" % k).reshape(q.shape))
+    sp.to(dev)
+    agent = sg.PPO(sp, 0.2, g.ppo_epoch, g.nmb, 0.5, g.entropy_coef, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    if dp_on:
+        sg_dist.attach(ppo=agent, transport="p2p")
+    rs = gu.make_storage(g.buffer(), g.O, g.A, 3)
+    out = agent.update(rs, permutations=g.t("ppo_perm"))
+    return np.array(out), agent.last_trace.clone(), sp.flat_params().cpu().clone()
+
+
+def _split_worker(rank, world, port, case, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.cuda.set_device(rank)
+    dev = "cuda:%d" % rank
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        from test_split_oracle import SplitGolden
+        torch.set_num_threads(1)
+        g = SplitGolden(case)
+        if (g.T * g.N // g.nmb) % world:
+            if rank == 0:
+                open(out, "w").write("skipped: minibatch not divisible by the world size")
+            return
+        res = _split_case(g, True, dev)
+        torch.cuda.synchronize()
+        ref = res[2].to(dev).clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref.cpu(), res[2]), "ranks diverged"
+        dist.barrier()
+        if rank == 0:
+            one = _split_case(g, False, dev)
+            assert np.all(np.abs(res[0] - one[0]) <= 1e-5 * np.maximum(np.abs(one[0]), 0.05)), (res[0], one[0])
+            scale = one[1].abs().max(dim=0).values.clamp_min(0.5)
+            assert bool(((res[1] - one[1]).abs() <= 2e-5 * scale).all())
+            assert torch.allclose(res[2], one[2], rtol=1e-4, atol=2e-6)
+            open(out, "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_policy_data_parallel_matches_single_gpu(tmp_path):
+    """SplitPolicy's PPO update with the in-kernel peer-memory exchange (p2p transport)."""
+    from test_split_oracle import SPLIT_CASES
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    world = min(n, int(os.environ.get("SG_DP_WORLD", "2")))
+    for case in SPLIT_CASES:
+        out = str(tmp_path / ("ok_" + case))
+        mp.spawn(_split_worker, args=(world, _free_port(), case, out), nprocs=world, join=True)
+        assert os.path.exists(out)
