@@ -282,14 +282,21 @@ __device__ __forceinline__ void load_policy_image(float* __restrict__ Wi, float*
         tma_bulk_g2s(Wi + LI.cb2, params + L.cb2, (unsigned int)((L.total - L.cb2) * sizeof(float)), bar);         // cb2 .. logstd
     }
     mbar_wait(bar, parity);
-    // natural (n,k) -> NQ: lanes walk k-quads of one row; the 4 scalar stores of a quad go to 4 consecutive k slots
-    for (int q = tid; q < 2 * (HH >> 2); q += kStepThreads) {
-        const int net = q >= (HH >> 2);
-        const int rel = 4 * (q - net * (HH >> 2));
-        const float4 v = *reinterpret_cast<const float4*>(stage + net * HH + rel);
-        const int n = rel / H, k = rel - n * H;
-        float* d = Wi + (net ? LI.cw2 : LI.aw2) + nq_index(n, k, H);
-        d[0] = v.x; d[4] = v.y; d[8] = v.z; d[12] = v.w;
+    // natural (n,k) -> NQ.  Work item = (net, n-quad, k): four scalar reads of column k from rows 4q..4q+3 (lanes walk k:
+    // consecutive floats, conflict-free) and ONE float4 store to NQ slot (q*(H+1)+k)*4 (lanes walk k: consecutive float4
+    // slots, conflict-free).  The first version read k-quads of one row and scattered four scalar stores with a lane
+    // stride of 16 floats -- a 16-way bank conflict per store, 4.3k port cycles per refresh against ~0.5k now.
+    const int NQH = H >> 2;
+    const int items = 2 * NQH * H;
+    const int lg = (H & (H - 1)) == 0 ? __ffs(H) - 1 : -1;
+    for (int e = tid; e < items; e += kStepThreads) {
+        int r, k;
+        if (lg >= 0) { r = e >> lg; k = e & (H - 1); }
+        else { r = e / H; k = e - r * H; }
+        const int net = r >= NQH, nq = r - net * NQH;
+        const float* src = stage + net * HH + (4 * nq) * H + k;
+        const float4 v = make_float4(src[0], src[H], src[2 * H], src[3 * H]);
+        *reinterpret_cast<float4*>(Wi + (net ? LI.cw2 : LI.aw2) + ((size_t)nq * (H + 1) + k) * 4) = v;
     }
     __syncthreads();
 }
