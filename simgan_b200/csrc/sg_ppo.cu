@@ -565,8 +565,11 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
             const float h = h2[(r0 + i) * ldh + k];
             s[i] *= (1.f - h * h);
             dz2[(r0 + i) * ldh + k] = s[i];
-            dz2t[k * R + r0 + i] = s[i];
         }
+        // transposed copy [unit][R]: one float4 per 4 rows (scalar stores would be 8-way bank conflicts: lane stride R floats)
+#pragma unroll
+        for (int i = 0; i < RT; i += 4)
+            *reinterpret_cast<float4*>(dz2t + k * R + r0 + i) = make_float4(s[i], s[i + 1], s[i + 2], s[i + 3]);
     }
     __syncthreads();
     // ---- layer-2 back-propagation dZ1 = (dZ2 . W2) * (1 - h1^2), then every gradient that needs dZ2 ---------
@@ -578,8 +581,11 @@ __device__ void ppo_tile_col(const PpoArgs& a, const float* __restrict__ Wi, int
 #pragma unroll
         for (int i = 0; i < RT; ++i) {
             const float h = h1[(r0 + i) * ldh + k];
-            dz1t[k * R + r0 + i] = s[i] * (1.f - h * h);
+            s[i] *= (1.f - h * h);
         }
+#pragma unroll
+        for (int i = 0; i < RT; i += 4)
+            *reinterpret_cast<float4*>(dz1t + k * R + r0 + i) = make_float4(s[i], s[i + 1], s[i + 2], s[i + 3]);
     }
     {
         const float* Dh = half ? sm.DVt : sm.DMUt;
