@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_persistent_kernel(DiscAr
 // Register-resident variant (H = 4*HQ known at compile time, H <= 128): W2 lives in registers, the rest of the
 // parameters in a small shared image; both are refreshed from global memory after every Adam step.
 // TB = row triples per tile: 2 (disc_tile_reg), or 1 (disc_tile_reg1) when that still leaves at most one tile per SM.
-template <int HQ, int TB>
+template <int HQ, int TB, bool MULTI>
 __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
     extern __shared__ __align__(16) float smem[];
     const DiscRegImage I = make_disc_reg_image(a.F, a.H);
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) disc_reg_kernel(DiscArgs a) {
         bool acc = false;
         for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
             if (TB == 1) disc_tile_reg1<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
-            else disc_tile_reg<HQ>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
+            else disc_tile_reg<HQ, MULTI>(a, w, img, I, step, t, a.gpart + (size_t)blockIdx.x * a.P, a.losspart + blockIdx.x * 4, sm, acc, pf);
             acc = true;
         }
         pc.lap(1);
@@ -940,13 +940,16 @@ int sg_disc_update(const sg_disc_config* cfg, float* params, float* adam_m, floa
         if (mode == 3) {
             fn = (const void*)disc_persistent_kernel<true>;
             if (disc_reg_ok(cfg)) {
-                const bool one = disc_tb(cfg) == 1;
+                const bool one = disc_tb(cfg) == 1, multi = a.ntiles > grid;
+#define SG_DISC_REG_FN(HQ_) (one ? (const void*)disc_reg_kernel<HQ_, 1, false>                                      \
+                                 : (multi ? (const void*)disc_reg_kernel<HQ_, 2, true> : (const void*)disc_reg_kernel<HQ_, 2, false>))
                 switch (cfg->hidden) {
-                    case 48: fn = one ? (const void*)disc_reg_kernel<12, 1> : (const void*)disc_reg_kernel<12, 2>; break;
-                    case 64: fn = one ? (const void*)disc_reg_kernel<16, 1> : (const void*)disc_reg_kernel<16, 2>; break;
-                    case 100: fn = one ? (const void*)disc_reg_kernel<25, 1> : (const void*)disc_reg_kernel<25, 2>; break;
-                    default: fn = one ? (const void*)disc_reg_kernel<32, 1> : (const void*)disc_reg_kernel<32, 2>; break;
+                    case 48: fn = SG_DISC_REG_FN(12); break;
+                    case 64: fn = SG_DISC_REG_FN(16); break;
+                    case 100: fn = SG_DISC_REG_FN(25); break;
+                    default: fn = SG_DISC_REG_FN(32); break;
                 }
+#undef SG_DISC_REG_FN
             }
         }
         const size_t smem = mode == 3 ? smem_res : smem_tile;

@@ -161,10 +161,13 @@ __device__ __forceinline__ void disc_prefetch_rows(const Args& a, DiscPrefetch& 
 }
 
 // One tile = 2 (expert, policy, mixup) row triples.  `img` = small natural image (DiscRegImage), `w` = W2 slices.
-template <int HQ, class Args>
+// MULTI: the CTA runs several tiles per step and accumulates its partial gradient across them; single-tile kernels
+// compile without any accumulate code.
+template <int HQ, bool MULTI, class Args>
 __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float* __restrict__ img, const DiscRegImage& I,
                               int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                              DiscRegSmem& sm, bool acc, DiscPrefetch& pf) {
+                              DiscRegSmem& sm, bool acc_in, DiscPrefetch& pf) {
+    const bool acc = MULTI && acc_in;
     constexpr int H = 4 * HQ, TB = 2, R = 8;
     const int tid = threadIdx.x, nth = kStepThreads;
     const int F = a.F, ldf = sm.ldf, ldh = sm.ldh;
@@ -403,7 +406,8 @@ __device__ void disc_tile_reg(const Args& a, const DiscRegW2<HQ>& w, const float
 template <int HQ, class Args>
 __device__ void disc_tile_reg1(const Args& a, const DiscRegW2<HQ>& w, const float* __restrict__ img, const DiscRegImage& I,
                                int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                               DiscRegSmem& sm, bool acc, DiscPrefetch& pf) {
+                               DiscRegSmem& sm, bool /*acc: never -- this tile is only used with one tile per CTA*/, DiscPrefetch& pf) {
+    constexpr bool acc = false;           // compile-time: no read-modify-write code (and no speculative L2 loads) in the stores
     constexpr int H = 4 * HQ, R = 4;
     const int tid = threadIdx.x, nth = kStepThreads;
     const int F = a.F, ldf = sm.ldf, ldh = sm.ldh;
