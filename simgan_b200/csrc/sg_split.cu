@@ -190,9 +190,12 @@ struct SplitArgs {
     DpView dp;
 };
 
-template <int R, class WL2>
+// MULTI: the CTA runs several tiles per step and accumulates across them; single-tile kernels compile without any
+// accumulate code (with a run-time flag the compiler issues the old-value loads speculatively, exposed L2 latency).
+template <int R, class WL2, bool MULTI>
 __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __restrict__ gout, float* __restrict__ lossout,
-                           SplitSmem<R>& sm, bool acc, const float* __restrict__ W2, int hh4) {
+                           SplitSmem<R>& sm, bool acc_in, const float* __restrict__ W2, int hh4) {
+    const bool acc = MULTI && acc_in;
     static_assert(R == 8 || R == 4, "loss warp maps R rows x 32/R lanes");
     constexpr int LPR = 32 / R;           // lanes per row in the loss warp
     const int tid = threadIdx.x;
@@ -337,7 +340,7 @@ __device__ void split_tile(const SplitArgs& a, int step, int tile, float* __rest
 // W2RES: the three H x H second-layer matrices (the bulk of the weights, walked twice per tile) live in a
 // shared-memory copy that every CTA refreshes with three TMA bulk copies after each Adam step; everything else is
 // read through L2.  (The whole parameter vector + tile does not fit 227 KB at the shipped hidden size of 100.)
-template <int R, bool W2RES>
+template <int R, bool W2RES, bool MULTI>
 __global__ void __launch_bounds__(kSplitThreads, 1) split_ppo_kernel(SplitArgs a) {
     extern __shared__ __align__(16) float smem[];
     __shared__ double red[kSplitThreads / 32];
@@ -369,8 +372,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) split_ppo_kernel(SplitArgs a
             mbar_wait(&img_bar, (unsigned int)(step & 1));
         }
         for (int tile = cta; tile < a.ntiles; tile += gridDim.x) {
-            if (W2RES) split_tile<R, LdShared>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc, W2s, hhs);
-            else split_tile<R, LdGlobal>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc, a.params + a.L.w2[0], hh4);
+            if (W2RES) split_tile<R, LdShared, MULTI>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc, W2s, hhs);
+            else split_tile<R, LdGlobal, MULTI>(a, step, tile, a.gpart + (size_t)cta * a.P, a.losspart + cta * 4, sm, acc, a.params + a.L.w2[0], hh4);
             acc = true;
         }
         gb.sync();
@@ -575,8 +578,11 @@ int sg_split_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, 
     const bool w2res = smem_res <= 226 * 1024 && (cfg->mode == 0 || cfg->mode == 3);      // mode 2: weights through L2 only
     const size_t smem = w2res ? (smem_res > smem_tile ? smem_res : smem_tile) : smem_tile;
     SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
-    const void* fn = r4 ? (w2res ? (const void*)split_ppo_kernel<4, true> : (const void*)split_ppo_kernel<4, false>)
-                        : (w2res ? (const void*)split_ppo_kernel<kRows, true> : (const void*)split_ppo_kernel<kRows, false>);
+    const bool multi = a.ntiles > grid;
+#define SG_SPLIT_FN(R_) (w2res ? (multi ? (const void*)split_ppo_kernel<R_, true, true> : (const void*)split_ppo_kernel<R_, true, false>) \
+                               : (multi ? (const void*)split_ppo_kernel<R_, false, true> : (const void*)split_ppo_kernel<R_, false, false>))
+    const void* fn = r4 ? SG_SPLIT_FN(4) : SG_SPLIT_FN(kRows);
+#undef SG_SPLIT_FN
     SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSplitThreads, smem));
