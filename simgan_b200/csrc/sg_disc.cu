@@ -245,8 +245,9 @@ __device__ void disc_tile(const DiscArgs& a, const float* __restrict__ W, int st
 
 // ---- phase B: slice `cta` of the flat gradient (+ loss sums by CTA 0) --------------------------------
 // Returns true when thread tid < n4 holds float4 tid of the reduced slice in `mine` (narrow slices).
+// `loss_smem` (3 floats, optional): CTA 0 also leaves the loss sums there for its own trace write (no L2 round trip).
 template <int NT = kStepThreads, bool KEEP = false>
-__device__ bool disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4, float4& mine) {
+__device__ bool disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4, float4& mine, float* loss_smem = nullptr) {
     const int tid = threadIdx.x;
     const int p0 = min(a.P, cta * a.SL), p1 = min(a.P, p0 + a.SL);
     // CTA 0 also sums the loss partials: its LAST warp issues those loads first so that they ride along with the
@@ -270,7 +271,10 @@ __device__ bool disc_reduce_slice(const DiscArgs& a, int cta, float4* scr4, floa
 #pragma unroll
         for (int i = 0; i < MAXC; ++i) { s0 += l0[i]; s1 += l1[i]; s2 += l2[i]; }
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if ((tid & 31) == 0) { __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2); }
+        if ((tid & 31) == 0) {
+            __stcg(a.grad + a.P, s0); __stcg(a.grad + a.P + 1, s1); __stcg(a.grad + a.P + 2, s2);
+            if (loss_smem) { loss_smem[0] = s0; loss_smem[1] = s1; loss_smem[2] = s2; }
+        }
     }
     return narrow;
 }
@@ -327,7 +331,8 @@ __device__ void disc_reduce_adam_fused(const DiscArgs& a, int step, int cta, flo
     float pv = 0.f, mv = 0.f, vv = 0.f;
     if (own) { pv = __ldcg(a.params + pe); mv = __ldcg(a.m + pe); vv = __ldcg(a.v + pe); }
     float4 mine;
-    disc_reduce_slice<NT, true>(a, cta, scr4, mine);
+    __shared__ float loss_smem[4];
+    disc_reduce_slice<NT, true>(a, cta, scr4, mine, loss_smem);
     if (a.dp_on)
         dp_exchange_slice<NT>(a.dp, a.grad, p0, p1, cta, (unsigned int)(a.first_adam_step + step),
                               n4 <= 128 ? reinterpret_cast<float*>(scr4 + NT) : nullptr);
@@ -350,8 +355,8 @@ __device__ void disc_reduce_adam_fused(const DiscArgs& a, int step, int cta, flo
         __syncthreads();                       // loss sums were stored by the last warp
         if (tid == 0) {
             const float invB = 1.f / (float)a.B;
-            const float le = ld_cg(a.grad + a.P) * invB, lp = ld_cg(a.grad + a.P + 1) * invB;
-            const float gp = a.gp_lambda * ld_cg(a.grad + a.P + 2) * invB;
+            const float le = loss_smem[0] * invB, lp = loss_smem[1] * invB;
+            const float gp = a.gp_lambda * loss_smem[2] * invB;
             float* tr = a.trace + (size_t)step * 3;
             tr[0] = (le + lp) + gp; tr[1] = le; tr[2] = lp;
         }

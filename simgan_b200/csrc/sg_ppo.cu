@@ -687,12 +687,23 @@ __device__ void ppo_ssq_slice(const PpoArgs& a, int cta, double* red, bool have,
     if (tid == 0) __stcg(a.ssq + cta, tot);
 }
 
-__device__ __forceinline__ void ppo_write_trace(const PpoArgs& a, int step, float norm) {
+// The trace row of a step is written by thread 0 of CTA 0.  Its three inputs (loss sums, entropy: stored by CTA 0 itself
+// in phase B) are requested BEFORE the global norm is formed, so their L2 round trips hide behind that reduction instead
+// of extending the Adam phase of the CTA every other CTA waits for at the next barrier.
+struct PpoTraceIn {
+    float vl, al, ent;
+};
+__device__ __forceinline__ PpoTraceIn ppo_trace_prefetch(const PpoArgs& a, bool writer) {
+    PpoTraceIn t{0.f, 0.f, 0.f};
+    if (writer) { t.vl = ld_cg(a.grad + a.P); t.al = ld_cg(a.grad + a.P + 1); t.ent = ld_cg(a.scal); }
+    return t;
+}
+__device__ __forceinline__ void ppo_write_trace(const PpoArgs& a, int step, float norm, const PpoTraceIn& t) {
     const float invB = 1.f / (float)a.mbs;
     float* tr = a.trace + (size_t)step * 4;
-    tr[0] = ld_cg(a.grad + a.P) * invB;
-    tr[1] = ld_cg(a.grad + a.P + 1) * invB;
-    tr[2] = ld_cg(a.scal);
+    tr[0] = t.vl * invB;
+    tr[1] = t.al * invB;
+    tr[2] = t.ent;
     tr[3] = norm;
 }
 
@@ -707,6 +718,7 @@ __device__ void ppo_adam_slice(const PpoArgs& a, int step, int cta, double* red,
     const bool mineok = have && pq < p1;
     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = w4, v4 = w4;
     if (mineok) { w4 = ld_cg4(a.params + pq); m4 = ld_cg4(a.m + pq); v4 = ld_cg4(a.v + pq); }
+    const PpoTraceIn tin = ppo_trace_prefetch(a, cta == 0 && tid == 0);
     // global gradient norm from the slice partials, identical in every CTA (clip_grad_norm_, ppo.py:143-144)
     double s = 0.0;
     for (int c = tid; c < a.nslices; c += kStepThreads) s += __ldcg(a.ssq + c);
@@ -714,7 +726,7 @@ __device__ void ppo_adam_slice(const PpoArgs& a, int step, int cta, double* red,
     const float norm = (float)sqrt(tot);
     float clip = a.max_norm / (norm + 1e-6f);
     if (clip > 1.f) clip = 1.f;
-    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
+    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm, tin);
     if (have) {
         if (mineok) {
             float w[4] = {w4.x, w4.y, w4.z, w4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -757,13 +769,14 @@ __device__ __forceinline__ PpoOwnElem ppo_own_prefetch(const PpoArgs& a, int cta
 }
 __device__ void ppo_adam_own(const PpoArgs& a, int step, int cta, double* red, PpoOwnElem e) {
     const int tid = threadIdx.x;
+    const PpoTraceIn tin = ppo_trace_prefetch(a, cta == 0 && tid == 0);
     double s = 0.0;
     for (int c = tid; c < a.nslices; c += kStepThreads) s += __ldcg(a.ssq + c);
     const double tot = block_sum_256(s, red);
     const float norm = (float)sqrt(tot);
     float clip = a.max_norm / (norm + 1e-6f);
     if (clip > 1.f) clip = 1.f;
-    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm);
+    if (cta == 0 && tid == 0) ppo_write_trace(a, step, norm, tin);
     if (e.idx >= 0) {
         adam_update(e.p, e.m, e.v, eff_grad(a, e.idx, e.g) * clip, a.one_minus_b1, a.b2, a.one_minus_b2, a.step_size[step],
                     a.bc2_sqrt[step], a.eps);
