@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import math
 import pickle
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np

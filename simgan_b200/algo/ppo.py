@@ -10,7 +10,6 @@ per-step trace at the end.
 """
 import ctypes as C
 
-import numpy as np
 import torch
 
 from .. import _lib, _spec

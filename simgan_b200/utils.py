@@ -1,6 +1,5 @@
 """AddBias / init / linear LR schedule with the reference's contracts
 (third_party/a2c_ppo_acktr/utils.py:54-78)."""
-import torch
 import torch.nn as nn
 
 
