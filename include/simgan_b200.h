@@ -159,8 +159,11 @@ int sg_split_layout(int obs_dim, int hidden, int num_feet, int* offsets);
  * entropy is state dependent: entropy_rows (B) receives the per-row entropies (their mean is dist_entropy). */
 int sg_split_forward(const float* params, int obs_dim, int hidden, int num_feet, const float* obs, int B, const float* noise,
                      const float* actions_in, float* value, float* action, float* logp, float* entropy_rows, void* stream);
-/* PPO.update (A2C/algo/ppo.py:65-157) for a SplitPolicy: arguments as sg_ppo_update (cfg->act_dim = 7*num_feet;
- * persistent kernel only: cfg->mode and cfg->dp_ctx must be 0 / NULL); trace columns as sg_ppo_update. */
+/* PPO.update (A2C/algo/ppo.py:65-157) for a SplitPolicy: arguments as sg_ppo_update (cfg->act_dim = 7*num_feet).
+ * Persistent kernel only, no allreduce callback: cfg->mode 0 / 3 keep the three H x H matrices in a shared-memory copy
+ * when it fits, mode 2 reads every weight through L2 (bit-identical results); cfg->dp_ctx enables the fused peer-memory
+ * exchange as in sg_ppo_update (the value / action loss AND the entropy columns of `trace` are then per-rank partial sums).
+ * trace columns: {value_loss, action_loss, dist_entropy (mean over the minibatch rows), grad_norm}. */
 int64_t sg_split_ppo_workspace_bytes(const sg_ppo_config* cfg);
 int sg_split_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float* adam_v, const float* obs,
                         const float* actions, const float* value_preds, const float* returns, const float* old_logp,
