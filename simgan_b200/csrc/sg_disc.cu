@@ -9,7 +9,8 @@
 //                           applies Adam to that slice -- the discriminator has no gradient clipping, so
 //                           no global norm is needed), grid barrier.  Variants: register-resident
 //                           (disc_reg_kernel, sg_disc_reg.cuh: hidden widths 48/64/100/128; W2 lives in
-//                           registers, refreshed through a TMA-staged shared copy after every Adam step),
+//                           registers, refreshed through a TMA-staged shared copy after every Adam step;
+//                           one row triple per tile while the minibatch has at most one per SM, else two),
 //                           resident (natural shared-memory image), persistent (weights through L2) and
 //                           phased (one launch per phase; NCCL data-parallel path).
 //   sg_disc_predict_reward  predict_reward_combined (gail.py:201-210) for one (N,F) block

@@ -20,6 +20,9 @@
 //   phased     (mode 1) one launch per phase; the NCCL data-parallel path (host allreduce callback).
 // persistent and phased run the same arithmetic in the same order (bit-identical); the column-owner tile sums in
 // another order and agrees to fp32 reassociation.
+// Template axes of ppo_persistent_kernel<R, RESIDENT, MULTI>: R = rows per tile (8; 16 once a minibatch has >= 32 rows
+// per SM, ppo_rows()), RESIDENT = 2 column-owner / 1 generic on a shared image / 0 through L2, MULTI = a CTA runs several
+// tiles per step and accumulates its partial gradient across them -- only those variants contain accumulate code.
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
 #include "sg_colgemm.cuh"
