@@ -242,6 +242,17 @@ int sg_relabel_normalize(const float* raw_reward, const float* masks, float* rew
 int sg_selftest_division(uint64_t seed, int blocks, int per_thread, double b_lo, double b_hi, uint64_t* mismatches,
                          void* stream);
 
+/* Diagnostics (no reference counterpart): D (M,N) = A . B^T formed by ONE CTA on the 5th-generation tensor cores
+ * (tcgen05.mma kind::tf32, accumulator in tensor memory) exactly the way the large-minibatch tiles issue their
+ * contractions.  A is (M,K) row-major, or (K,M) row-major when a_mn_major != 0; B is (N,K), or (K,N) when b_mn_major != 0.
+ * passes = 3: fp32 operands split hi + lo, hi*hi + hi*lo + lo*hi ("3xTF32"); passes = 1: plain TF32.
+ * M in {64,128}, N a multiple of 16 in [16,256], K a multiple of 8.
+ * h_raw_strides (HOST, 6 ints {a_lbo, a_sbo, a_k_step, b_lbo, b_sbo, b_k_step} in bytes, or NULL): descriptor probe --
+ * A and B are then copied verbatim into shared memory (M*K and N*K floats) and read through descriptors with these
+ * strides (passes must be 1). */
+int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int passes, const float* A, const float* B,
+                    float* D, const int* h_raw_strides, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

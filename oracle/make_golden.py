@@ -9,6 +9,7 @@ and stores inputs, RNG states, intermediate and final outputs.  Also writes:
   * hopper_expert_sas_f32.npy   merged (17555,25) expert matrix of hopper_new11_deform_n200_3.pkl
                                 (--gail-traj-num 200 --gail_downsample_frequency 1), fp32 as the
                                 reference narrows it with Tensor(...) (main_gail_dyn_ppo.py:165)
+  * laika_expert_sas_f32.npy    merged (15678,86) expert matrix of laika_70_deform_n200_0.pkl (--laika)
   * mini_expert.pkl / mini_expert_merged.npy   3-trajectory slice of that pkl in the on-disk format
                                 (collect_tarsim_traj.py:261-265) + the reference's merged matrix
 """
@@ -206,6 +207,18 @@ def main():
         split_cases(ref)
 
 
+def laika_expert(ref):
+    """Merged (15678, 86) expert matrix of laika_70_deform_n200_0.pkl (BASELINE configs[2] / [3]) through the
+    reference's own select_and_merge_sas (my_pybullet_envs/utils.py:233-263), --gail-traj-num 200, downsample 1."""
+    torch.manual_seed(0)
+    path = os.path.join(ref_shim.REF_ROOT, "laika_70_deform_n200_0.pkl")
+    cols = orc.load_sas_wpast(path, downsample_freq=1, load_num_trajs=200)
+    merged = ref.env_utils.select_and_merge_sas(cols, s_idx=np.array([0]), a_idx=np.array([0]))
+    expert = torch.Tensor(merged)
+    np.save(os.path.join(OUT, "laika_expert_sas_f32.npy"), expert.numpy())
+    print("laika expert", expert.shape)
+
+
 def split_cases(ref):
     # SplitPolicy, shipped-script dims (Hopper: O=14, A=7, hidden 100, entropy_coef 0; train_hopper_deform.sh:5)
     run_split_case(ref, "split_hopper_seed3.npz", 3, 40, 4, 14, 100, 1, ppo_epoch=2, nmb=4, entropy_coef=0.0, ep_len=9.0)
@@ -215,7 +228,9 @@ def split_cases(ref):
 
 
 if __name__ == "__main__":
-    if "--split" in sys.argv and "--all" not in sys.argv:
+    if "--laika" in sys.argv:
+        laika_expert(ref_shim.load())
+    elif "--split" in sys.argv and "--all" not in sys.argv:
         split_cases(ref_shim.load())
     else:
         main()

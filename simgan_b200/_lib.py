@@ -79,6 +79,7 @@ SIGNATURES = {
     "sg_disc_relabel": (C.c_int, [c_void, C.c_int, C.c_int, c_void, c_void, c_void, C.c_int, C.c_int, C.c_double,
                                   C.c_double, c_void, C.c_int, c_void, c_void, c_void, c_void]),
     "sg_selftest_division": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double, c_void, c_void]),
+    "sg_selftest_mma": (C.c_int, [C.c_int] * 6 + [c_void] * 3 + [C.POINTER(C.c_int), c_void]),
     "sg_relabel_normalize": (C.c_int, [c_void, c_void, c_void, C.c_int, C.c_int, C.c_double, c_void, C.c_int, c_void,
                                        c_void, c_void, c_void]),
 }
@@ -100,6 +101,26 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def on_device(get_device):
+    """Decorator for hot-path methods: run the body with the tensors' own CUDA device current.  Every sg_* entry point
+    launches on the CURRENT device's current stream, so an object living on cuda:1 must not launch while cuda:0 is
+    current (illegal addresses or silent peer access).  ``get_device(self, *args)`` returns a torch.device or None."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            import torch
+            dev = get_device(*args, **kwargs)
+            if dev is not None and dev.type == "cuda" and torch.cuda.is_available() and dev.index is not None \
+                    and dev.index != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    return fn(*args, **kwargs)
+            return fn(*args, **kwargs)
+        return wrapper
+    return deco
 
 
 def check(rc, what=""):

@@ -14,6 +14,26 @@ class FusedAdam(object):
         self.step_count = 0
         self.exp_avg = None
         self.exp_avg_sq = None
+        self._pending = None        # per-parameter moments imported from a torch.optim.Adam (from_torch_adam)
+
+    @classmethod
+    def from_torch_adam(cls, opt, params):
+        """FusedAdam equivalent of a ``torch.optim.Adam`` over ``params`` (a reference checkpoint's optimizer):
+        lr / betas / eps of its first group and, when it has stepped, exp_avg / exp_avg_sq / step of every parameter.
+        The moments are folded into the flat buffers at the first ``ensure_state``."""
+        g = opt.param_groups[0]
+        new = cls(params, lr=g["lr"], betas=g["betas"], eps=g["eps"])
+        moments, step = [], 0
+        for p_old in g["params"]:
+            st = opt.state.get(p_old, {})
+            if "exp_avg" not in st:
+                moments = None
+                break
+            moments.append((st["exp_avg"].detach().clone(), st["exp_avg_sq"].detach().clone()))
+            step = int(st["step"]) if not torch.is_tensor(st["step"]) else int(st["step"].item())
+        if moments:
+            new._pending = (moments, step)
+        return new
 
     @property
     def lr(self):
@@ -28,6 +48,15 @@ class FusedAdam(object):
             self.exp_avg = torch.zeros_like(flat)
             self.exp_avg_sq = torch.zeros_like(flat)
             self.step_count = 0
+            pending, self._pending = getattr(self, "_pending", None), None
+            if pending is not None:
+                moments, step = pending
+                for p, (m, v) in zip(self.param_groups[0]["params"], moments):
+                    off = (p.data_ptr() - flat.data_ptr()) // 4        # the parameters are views of the flat vector
+                    assert 0 <= off and off + p.numel() <= flat.numel(), "parameters are not bound to the flat vector"
+                    self.exp_avg[off:off + p.numel()].copy_(m.reshape(-1))
+                    self.exp_avg_sq[off:off + p.numel()].copy_(v.reshape(-1))
+                self.step_count = step
         return self.exp_avg, self.exp_avg_sq
 
     def schedule(self, n_steps):

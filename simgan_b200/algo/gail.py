@@ -72,15 +72,37 @@ class Discriminator(nn.Module):
         return flat
 
     def __getstate__(self):
+        """Whole-object ``torch.save(discr)`` (main_gail_dyn_ppo.py:319-320): only what the reference's object holds
+        travels.  Staging buffers, workspaces and the data-parallel handle (ctypes pointers to CUDA IPC mappings, a
+        process group) are per-process state and are dropped; ``dist.attach`` re-creates the handle after a load."""
         state = dict(self.__dict__)
         state.pop("_flat", None)
         state["_ws"] = None
+        state["dp"] = None
+        state["last_trace"] = None
         state.pop("_prof_view", None)
         state.pop("_rms_dev", None)
         state.pop("_predraw", None)
         for k in ("_stage", "_stage_cur", "_side_upload", "_copy_stream", "_last_key", "_relabel_ws"):
             state.pop(k, None)
         return state
+
+    def __setstate__(self, state):
+        """Also accepts a pickle written by the REFERENCE's Discriminator (loaded through ``compat.install()``): its
+        ``__dict__`` has none of the kernel-side attributes and its optimizer is a ``torch.optim.Adam``, which is
+        replaced by a FusedAdam carrying over lr / betas / eps and, when present, the moment estimates and step."""
+        self.__dict__.update(state)
+        d = self.__dict__
+        d.setdefault("kernel_mode", 0)
+        d.setdefault("dp", None)
+        d.setdefault("last_trace", None)
+        d.setdefault("_ws", None)
+        d.setdefault("returns", None)
+        if "ret_rms" not in d:
+            d["ret_rms"] = RunningMeanStd(shape=())
+        opt = d.get("optimizer")
+        if opt is not None and not isinstance(opt, FusedAdam):
+            d["optimizer"] = FusedAdam.from_torch_adam(opt, list(self.trunk.parameters()))
 
     # ---- update --------------------------------------------------------------------------------------------
     @staticmethod
@@ -91,11 +113,8 @@ class Discriminator(nn.Module):
         RandomSampler seed (one int64 random_()), expert permutation on a PRIVATE generator, the rollout
         sampler's randperm(S), then one rand(B,1) per zipped minibatch (gail.py:72).
         Returns (expert_idx (n,B) int64, policy_idx (n,B) int64, alpha (n,B) fp32)."""
-        torch.empty((), dtype=torch.int64).random_()
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
-        gen = torch.Generator()
-        gen.manual_seed(seed)
-        e_perm = torch.randperm(n_expert, generator=gen)
+        # configurations that cannot run are refused BEFORE anything is drawn, so a caller that catches the error
+        # finds the generator where it left it
         n_e = n_expert // batch_size
         if not drop_last and n_expert % batch_size:
             raise NotImplementedError(
@@ -104,10 +123,15 @@ class Discriminator(nn.Module):
                 "configuration" % (n_expert, batch_size))
         if n_e == 0:
             raise ZeroDivisionError("no full expert minibatch (gail.py:193 divides by n=0)")
-        p_perm = torch.randperm(n_rollout)
         n = min(n_e, n_rollout // batch_size)
         if n == 0:
             raise ZeroDivisionError("rollout smaller than gail_batch_size (gail.py:193 divides by n=0)")
+        torch.empty((), dtype=torch.int64).random_()
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+        gen = torch.Generator()
+        gen.manual_seed(seed)
+        e_perm = torch.randperm(n_expert, generator=gen)
+        p_perm = torch.randperm(n_rollout)
         alpha = torch.rand(n * batch_size)          # == n consecutive torch.rand(B,1) draws (tests pin this)
         return (e_perm[:n * batch_size].view(n, batch_size), p_perm[:n * batch_size].view(n, batch_size),
                 alpha.view(n, batch_size))
@@ -118,6 +142,7 @@ class Discriminator(nn.Module):
     # block on a side stream -- then rewinds the CPU generator.  The next call uses the staged block only if the
     # generator is still exactly where the early draw started and the Adam schedule it baked in is still the right
     # one; otherwise it is discarded and the call draws / stages as usual.
+    @_lib.on_device(lambda self, *a, **k: self.trunk[0].weight.device)
     def _speculate(self):
         key = self.__dict__.get("_last_key")
         flat = self.__dict__.get("_flat")
@@ -175,6 +200,7 @@ class Discriminator(nn.Module):
             stage_dev.copy_(stage, non_blocking=True)
         return which, self._sched_sig(n), event
 
+    @_lib.on_device(lambda self, *a, **k: self.trunk[0].weight.device)
     def _run_update(self, expert, policy_feat, e_idx, p_idx, alpha, staged=None):
         flat = self.flat_params()
         dev = flat.device
@@ -259,6 +285,7 @@ class Discriminator(nn.Module):
         bypasses the generator (parity tests)."""
         if not self.training:
             self.train()
+        self._check_loader(expert_loader)
         expert = expert_loader.dataset.tensors[0]
         if not expert.is_cuda or not rollouts.obs_feat.is_cuda:
             raise _lib.SgError("update_gail_dyn needs the expert set and the rollout buffer on the CUDA device")
@@ -277,12 +304,26 @@ class Discriminator(nn.Module):
                                    for x in replay]
         return self._run_update(expert, policy_feat, e_idx, p_idx, alpha, staged)
 
+    @staticmethod
+    def _check_loader(expert_loader):
+        """The index emulation reproduces exactly one loader shape -- the caller's DataLoader(shuffle=True) on the default
+        generator (main_gail_dyn_ppo.py:170-175).  Anything else would silently get that stream too: refuse it."""
+        from torch.utils.data import RandomSampler
+        sampler = getattr(expert_loader, "sampler", None)
+        if not isinstance(sampler, RandomSampler) or getattr(sampler, "replacement", False):
+            raise NotImplementedError("update_gail_dyn emulates DataLoader(shuffle=True) (RandomSampler without replacement); "
+                                      "got sampler %r" % type(sampler).__name__)
+        if getattr(expert_loader, "generator", None) is not None or getattr(sampler, "generator", None) is not None:
+            raise NotImplementedError("update_gail_dyn emulates a DataLoader on the DEFAULT CPU generator; a loader with its own "
+                                      "generator would consume a different stream")
+
     def update(self, expert_loader, rollouts, obsfilt=None, is_gail_dyn=False, a_dim=None):
         """Legacy (state, action)-split variant (gail.py:91-152): the D input is cat([state, action]) on
         both sides, so it maps onto the same kernel over concatenated row matrices."""
         if obsfilt is not None:
             raise NotImplementedError("obsfilt (VecNormalize observation filter) is not used by the GAIL-dyn path")
         self.train()
+        self._check_loader(expert_loader)
         es, ea = expert_loader.dataset.tensors[:2]
         expert = torch.cat([es, ea], dim=1).float().contiguous()
         T, N = rollouts.rewards.shape[:2]
@@ -310,6 +351,7 @@ class Discriminator(nn.Module):
                                               torch.cat([policy_state, policy_action], dim=1), lambda_)
 
     # ---- rewards ---------------------------------------------------------------------------------------------
+    @_lib.on_device(lambda self, *a, **k: self.trunk[0].weight.device)
     def predict_reward_combined(self, d_in, gamma, masks, offset=0.0):
         """gail.py:201-210: (reward (N,1), running returns (N,1)); ``self.returns`` persists across calls."""
         flat = self.flat_params()
@@ -341,6 +383,7 @@ class Discriminator(nn.Module):
             self.eval()
             return torch.sigmoid(self.trunk(torch.cat([state, action], dim=1)))
 
+    @_lib.on_device(lambda self, *a, **k: self.trunk[0].weight.device)
     def relabel_rollout(self, rollouts, gamma, offset, ret_rms, sync=True):
         """The caller's whole relabel loop (main_gail_dyn_ppo.py:275-297) in one device pass:
         for every step t, reward_t = predict_reward_combined(obs_feat[t+1], gamma, masks[t], offset),

@@ -92,6 +92,7 @@ class PPO(object):
         ws, off = self._prof_view
         return ws[off:off + 64 * n_ctas].view(torch.int64).view(n_ctas, 8).cpu()
 
+    @_lib.on_device(lambda self, *a, **k: next(self.actor_critic.parameters()).device)
     def update(self, rollouts, permutations=None):
         """PPO.update (ppo.py:65-157).  ``permutations`` (ppo_epoch, S) overrides the sampler draw (used by
         parity tests to replay a recorded index stream)."""

@@ -46,6 +46,10 @@ class DataParallel(object):
         self._cb = None
         self._ctx = {}           # key -> sg_dp context (one per optimizer)
 
+    def __getstate__(self):
+        raise TypeError("simgan_b200.dist.DataParallel holds per-process handles (CUDA IPC mappings, a process group) and "
+                        "cannot be pickled; PPO / Discriminator drop it from their own pickles")
+
     # ---- fused peer-memory exchange -----------------------------------------------------------------------
     def p2p_ok(self, n_rows):
         """The in-kernel exchange needs identical shard sizes (identical grids / slice tables) on every rank."""

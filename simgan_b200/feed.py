@@ -40,6 +40,7 @@ class RolloutFeeder(object):
         self.action_host = torch.empty(N, self.A, dtype=torch.float32).pin_memory()
         self.done_event = torch.cuda.Event()
 
+    @_lib.on_device(lambda self, *a, **k: self.dev)
     def _launch(self, step, deterministic):
         rs, ac = self.rs, self.ac
         flat = ac.flat_params()

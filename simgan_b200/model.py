@@ -170,6 +170,7 @@ class Policy(nn.Module):
         state.pop("_flat", None)       # rebuilt on demand; parameters carry the data
         return state
 
+    @_lib.on_device(lambda self, inputs, *a, **k: inputs.device)
     def _forward_cuda(self, inputs, noise=None, actions_in=None, want=("value", "action", "logp")):
         flat = self.flat_params()
         x = inputs.detach()

@@ -71,6 +71,7 @@ class RolloutStorage(object):
         rc = _lib.lib().sg_copy_blocks(srcs, dsts, cnts, n, _lib.current_stream())
         _lib.check(rc, "sg_copy_blocks")
 
+    @_lib.on_device(lambda self, *a, **k: self.obs.device)
     def insert(self, obs, recurrent_hidden_states, actions, action_log_probs, value_preds, rewards, masks, bad_masks,
                obs_feat=None):
         """Slot step+1 for obs/feat/hxs/masks/bad_masks, slot step for the rest (storage.py:70-84)."""
@@ -92,11 +93,13 @@ class RolloutStorage(object):
             t = (t - 1) % self.num_steps
             self.rewards[t] += offset.view(n, 1)
 
+    @_lib.on_device(lambda self, *a, **k: self.obs.device)
     def after_update(self):
         """Slot T -> slot 0 for the five (T+1)-long tensors (storage.py:96-101)."""
         self._copy_blocks([(getattr(self, k)[0], getattr(self, k)[-1]) for k in _T1_FIELDS])
 
     # ---- returns ---------------------------------------------------------------------------------------
+    @_lib.on_device(lambda self, *a, **k: self.obs.device)
     def compute_returns(self, next_value, use_gae, gamma, gae_lambda, use_proper_time_limits=True):
         """All four branches of storage.py:103-142 in the kernel sg_compute_returns (bit-exact)."""
         _require_cuda(self.rewards, "compute_returns")
@@ -154,6 +157,7 @@ class RolloutStorage(object):
         raise NotImplementedError("recurrent policies are outside the PPO+GAIL hot path (SURVEY.md section 2, row 1)")
 
 
+@_lib.on_device(lambda srcs, idx: srcs[0].device)
 def gather_rows(srcs, idx):
     """dst[i] = srcs[i][idx] for several (S, D_i) fp32 CUDA tensors in one launch (sg_gather_rows)."""
     n = len(srcs)

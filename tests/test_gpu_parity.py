@@ -589,6 +589,55 @@ def test_rollout_feeder_matches_act_insert():
     assert rs_b.step == rs_a.step == 0
 
 
+def test_rollout_feeder_vs_oracle_insert_and_act():
+    """The fused feed step against the ORACLE's buffer_insert + policy_act (A2C/storage.py:70-84, A2C/model.py:89-101) on
+    the same env outputs and the same CUDA-generator noise stream: everything the step copies is bit-exact, what the
+    policy computes (actions, log-probs, values) agrees to fp32 forward tolerance (2e-6 of the largest magnitude)."""
+    from oracle.ref_shim import BoxSpace
+    T, N, O, A, F, H = 7, 6, 14, 7, 25, 64
+    torch.manual_seed(1)
+    p = orc.init_policy(O, H, A)
+    pol = gu.make_policy(p, O, H, A)
+    rs = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, F); rs.to(gu.DEV)
+    buf = orc.new_buffer(T, N, O, A, F)
+    rng = np.random.RandomState(3)
+    obs0 = rng.randn(N, O).astype(np.float32)
+    rs.obs[0].copy_(torch.from_numpy(obs0)); buf["obs"][0].copy_(torch.from_numpy(obs0))
+    env = [(rng.randn(N, O).astype(np.float32), rng.randn(N).astype(np.float32), rng.rand(N) < 0.3, rng.rand(N) < 0.1,
+            rng.randn(N, F)) for _ in range(T)]
+    # the noise the feeder will draw: one randn(N, A) on the CUDA generator per act
+    torch.cuda.manual_seed(21)
+    noise = [torch.randn(N, A, device=gu.DEV).cpu() for _ in range(T + 1)]
+    # oracle loop (main_gail_dyn_ppo.py:209-236)
+    step = 0
+    acts_o = []
+    for t in range(T):
+        value, action, logp = orc.policy_act(p, buf["obs"][step], noise=noise[t])
+        acts_o.append(action)
+        obs, rew, done, bad, feat = env[t]
+        masks = torch.tensor([[0.0] if d else [1.0] for d in done])
+        bad_masks = torch.tensor([[0.0] if b else [1.0] for b in bad])
+        step = orc.buffer_insert(buf, step, torch.from_numpy(obs), torch.zeros(N, 1), action, logp, value,
+                                 torch.from_numpy(rew).unsqueeze(1), masks, bad_masks, torch.Tensor(feat))
+    nv_o = orc.policy_forward(p, buf["obs"][-1])[0]
+    # fused feed
+    torch.cuda.manual_seed(21)
+    feeder = sg.RolloutFeeder(pol, rs)
+    acts = [torch.from_numpy(feeder.begin().copy())]
+    for t in range(T):
+        obs, rew, done, bad, feat = env[t]
+        acts.append(torch.from_numpy(feeder.step(obs, rew, done, bad, feat).copy()))
+    assert rs.step == step == 0
+    for k in ("obs", "obs_feat", "recurrent_hidden_states", "rewards", "masks", "bad_masks"):
+        assert torch.equal(getattr(rs, k).cpu(), buf[k]), k
+    for a, b in zip(acts, acts_o):
+        assert gu.rel_err(a, b) <= 2e-6
+    for k in ("actions", "action_log_probs"):
+        assert gu.rel_err(getattr(rs, k).cpu(), buf[k]) <= 2e-6, k
+    assert gu.rel_err(rs.value_preds[:-1].cpu(), buf["value_preds"][:-1]) <= 2e-6
+    assert gu.rel_err(rs.value_preds[-1].cpu(), nv_o) <= 2e-6        # slot T already holds next_value
+
+
 # ------------------------------------------------------------------------------------ remaining API surface
 def test_legacy_discriminator_update_and_mod_reward():
     """Discriminator.update (the (state, action)-split form, gail.py:91-152) maps onto the same kernel over

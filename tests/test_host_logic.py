@@ -178,6 +178,96 @@ def test_reference_checkpoint_loads_into_our_classes():
     assert (ours.obs_dim, ours.hidden_size, ours.act_dim) == (11, 64, 3)
 
 
+def test_discriminator_pickles_after_a_data_parallel_attach(tmp_path):
+    """main_gail_dyn_ppo.py:317-320 does torch.save(discr) right after the first update; with data parallelism on, the
+    object then holds ctypes pointers to CUDA IPC mappings (dist.DataParallel._ctx) that must not travel."""
+    import ctypes as C
+    from simgan_b200 import dist as sg_dist
+
+    d = sg.Discriminator(25, 100, torch.device("cpu"))
+    dp = sg_dist.DataParallel.__new__(sg_dist.DataParallel)
+    dp.__dict__.update(group=None, rank=0, world=2, transport="p2p", n_allreduce=0, _cb=None, _ctx={"disc": C.c_void_p(1234)})
+    d.dp = dp
+    d.last_trace = torch.zeros(3, 3)
+    path = str(tmp_path / "d.pt")
+    torch.save(d, path)
+    d2 = torch.load(path, weights_only=False)
+    assert d2.dp is None and d2.last_trace is None and d.dp is dp
+    with pytest.raises(TypeError, match="per-process handles"):
+        import pickle
+        pickle.dumps(dp)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (GPU box)")
+def test_reference_discriminator_checkpoint_loads_into_our_class(tmp_path):
+    """A whole-object ``*_D.pt`` written by the REFERENCE's Discriminator (after it has stepped its torch Adam) loads
+    through the aliases into simgan_b200's class with the kernel-side attributes defaulted and the optimizer replaced
+    by a FusedAdam that carries lr / betas / eps / step and, once bound to the flat vector, the moment estimates."""
+    import sys
+    from simgan_b200.algo.adam import FusedAdam
+    ref = ref_shim.load()
+    saved = {k: v for k, v in sys.modules.items() if k.startswith("third_party")}
+    path = str(tmp_path / "ref_D.pt")
+    try:
+        sys.modules.update(ref.modules)
+        torch.manual_seed(3)
+        theirs = ref.gail.Discriminator(9, 16, torch.device("cpu"))
+        x = torch.randn(32, 9)
+        loss = theirs.trunk(x).pow(2).mean()
+        theirs.optimizer.zero_grad(); loss.backward(); theirs.optimizer.step()
+        torch.save(theirs, path)
+        for k in list(sys.modules):
+            if k.startswith("third_party") or k in ("pybullet",) or k.startswith("my_pybullet_envs"):
+                del sys.modules[k]
+        compat.install()
+        ours = torch.load(path, weights_only=False, map_location="cpu")
+    finally:
+        compat.uninstall()
+        for k in list(sys.modules):
+            if k.startswith("third_party"):
+                del sys.modules[k]
+        sys.modules.update(saved)
+    assert type(ours) is sg.Discriminator and ours.dp is None and ours.kernel_mode == 0 and ours.last_trace is None
+    assert isinstance(ours.optimizer, FusedAdam)
+    g = ours.optimizer.param_groups[0]
+    assert (g["lr"], tuple(g["betas"]), g["eps"]) == (1e-3, (0.9, 0.999), 1e-8)
+    for a, b in zip(ours.trunk.parameters(), theirs.trunk.parameters()):
+        assert torch.equal(a, b)
+    # moments fold into flat buffers laid out like the parameter vector (simulated binding on the CPU)
+    ps = list(ours.trunk.parameters())
+    flat = torch.zeros(sum(p.numel() for p in ps) + 8)
+    off = 0
+    for p_ in ps:
+        flat[off:off + p_.numel()].copy_(p_.data.reshape(-1)); p_.data = flat[off:off + p_.numel()].view(p_.shape); off += p_.numel()
+    m, v = ours.optimizer.ensure_state(flat)
+    assert ours.optimizer.step_count == 1
+    off = 0
+    for p_, q in zip(ps, theirs.trunk.parameters()):
+        st = theirs.optimizer.state[q]
+        assert torch.equal(m[off:off + p_.numel()], st["exp_avg"].reshape(-1))
+        assert torch.equal(v[off:off + p_.numel()], st["exp_avg_sq"].reshape(-1))
+        off += p_.numel()
+
+
+def test_update_gail_dyn_refuses_loaders_it_cannot_emulate():
+    from torch.utils.data import SequentialSampler
+    d = sg.Discriminator(5, 8, torch.device("cpu"))
+    x = torch.zeros(64, 5)
+    with pytest.raises(NotImplementedError, match="RandomSampler"):
+        d._check_loader(DataLoader(TensorDataset(x), batch_size=16, shuffle=False))
+    with pytest.raises(NotImplementedError, match="generator"):
+        d._check_loader(DataLoader(TensorDataset(x), batch_size=16, shuffle=True, generator=torch.Generator()))
+    d._check_loader(DataLoader(TensorDataset(x), batch_size=16, shuffle=True, drop_last=True))
+    # unrunnable configurations are refused before the generator is touched
+    torch.manual_seed(0)
+    before = torch.get_rng_state()
+    with pytest.raises(ZeroDivisionError):
+        sg.Discriminator.draw_epoch_indices(64, 128, True, 1000)
+    with pytest.raises(NotImplementedError):
+        sg.Discriminator.draw_epoch_indices(94, 64, False, 1000)
+    assert torch.equal(torch.get_rng_state(), before)
+
+
 def test_hot_path_refuses_to_run_without_cuda():
     pol = sg.Policy((14,), BoxSpace(7), base_kwargs={"recurrent": False, "hidden_size": 64})
     agent = sg.PPO(pol, 0.2, 1, 2, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
@@ -253,6 +343,27 @@ def test_expert_tensor_reproduces_the_committed_fixture():
     torch.manual_seed(0)
     x = sg.expert_tensor(os.path.join(ref_shim.REF_ROOT, "hopper_new11_deform_n200_3.pkl"), "cpu")
     assert np.array_equal(x.numpy(), np.load(os.path.join(GOLDEN_DIR, "hopper_expert_sas_f32.npy")))
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="reference tree not mounted (GPU box)")
+def test_laikago_expert_tensor_reproduces_the_committed_fixture():
+    """laika_70_deform_n200_0.pkl (BASELINE configs[2]/[3]): our loader == the reference's merge stored by
+    oracle/make_golden.py --laika, (15678, 86), s_dim 37 / a_dim 12 (SURVEY section 8 glossary)."""
+    from golden_util import GOLDEN_DIR
+    torch.manual_seed(0)
+    x = sg.expert_tensor(os.path.join(ref_shim.REF_ROOT, "laika_70_deform_n200_0.pkl"), "cpu", load_num_trajs=200)
+    ref = np.load(os.path.join(GOLDEN_DIR, "laika_expert_sas_f32.npy"))
+    assert x.shape == (15678, 86) and np.array_equal(x.numpy(), ref)
+
+
+def test_laikago_expert_fixture_shape_and_content():
+    """The committed Laikago fixture is what the bench and the full-size tests feed the discriminator (no reference
+    tree needed): [s_t (37) | a_t (12) | s_{t+1} (37)], finite, consecutive rows of one trajectory chain s_{t+1} -> s_t."""
+    from golden_util import GOLDEN_DIR
+    x = np.load(os.path.join(GOLDEN_DIR, "laika_expert_sas_f32.npy"))
+    assert x.shape == (15678, 86) and x.dtype == np.float32 and np.isfinite(x).all()
+    chained = np.all(x[1:, :37] == x[:-1, 49:], axis=1)
+    assert chained.mean() > 0.95          # breaks only at the 200 trajectory boundaries
 
 
 class _FakeConsumer(object):
