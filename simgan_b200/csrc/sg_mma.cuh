@@ -4,17 +4,19 @@
 // as hi*hi + hi*lo + lo*hi on the tensor cores (kind::tf32, fp32 accumulate in TMEM): "3xTF32", ~2^-22 relative per
 // product, which keeps the 1e-4 loss contract of north_star (plain TF32 is ~2^-11 and does not).
 //
-// Shared-memory operand layout ("granule layout", no swizzle): an operand with MN extent E and K extent Kx is stored
-// as 16-byte granules of 4 consecutive floats.
-//   K-major  source element (e, k), k contiguous : granule index (k/4)*E + e   holds k%4 = 0..3
-//   MN-major source element (k, e), e contiguous : granule index (e/4)*Kx + k  holds e%4 = 0..3
-// Eight consecutive granules form one 128-byte UMMA core matrix (8 x 16 bytes) either way, so ONE buffer written as
-// [col/4][row][col%4] can be read K-major (row = MN, col = K) by one GEMM and MN-major (col = MN, row = K) by another --
-// this is what lets an activation tile serve the forward layer (A, K-major), the data back-propagation and both weight
-// gradients (A and B, MN-major) from a single copy.
-//   descriptor strides: SBO = byte distance between core matrices along MN, LBO = along K
-//     K-major : SBO = 128,    LBO = 16*E ;  advancing K by 8 elements (one kind::tf32 MMA) = +2*16*E bytes
-//     MN-major: SBO = 16*Kx,  LBO = 128  ;  advancing K by 8 elements                       = +128 bytes
+// Shared-memory operand layouts (E = MN extent, Kx = K extent of the image, floats):
+//   K-major  (SWIZZLE_NONE / "interleave"): 16-byte granules of 4 consecutive k; element (e, k) lives in granule
+//            (k/4)*E + e.  Eight consecutive granules (8 rows x 16 bytes) are one UMMA core matrix.
+//            descriptor: LBO = 16*E (next 4 k), SBO = 128 (next 8 rows); one kind::tf32 MMA (K = 8) advances 2*16*E bytes.
+//   MN-major (SWIZZLE_128B_BASE32B -- the ONLY layout the tensor core accepts for MN-major 32-bit operands; with any
+//            other layout type the MMA silently produces zeros.  Address function decoded on B200 with
+//            profiles/mma_probe.py): atoms of 4 k-rows x 32 consecutive e (128 bytes per row, 512 bytes per atom); row
+//            k%4 of an atom stores its four 32-byte chunks (8 floats) at chunk position c ^ (k%4), i.e. byte-address bits
+//            [5,7) ^= bits [7,9).  Atoms are laid out [k/4][e/32]:
+//            float offset = ((k/4)*(E/32) + e/32)*128 + (k%4)*32 + ((e%32) ^ ((k%4) << 3))
+//            descriptor: LBO = 512 (next 32 e), SBO = 16*E (next 4 k), layout type 1; one MMA (K = 8) advances 2*SBO bytes.
+//            An aligned quad of 4 consecutive e is one 16-byte granule in natural order.
+//            A K-chunk of an image is contiguous in both layouts; images must be 1024-byte aligned.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -48,9 +50,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // ---- descriptors --------------------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): bits [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4,
-// [46,48) = 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
+// [46,48) = 1, [61,64) layout type (0 = no swizzle, 1 = SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 0) {
+    uint64_t d = (uint64_t)(layout_type & 7u) << 61;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
@@ -88,6 +90,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// float offset of element (e, k) in the images described at the top of this file
+__host__ __device__ __forceinline__ int kmajor_off(int e, int k, int E) { return (((k >> 2) * E + e) << 2) + (k & 3); }
+__host__ __device__ __forceinline__ int mnmajor_off(int e, int k, int E) {
+    return (((k >> 2) * (E >> 5) + (e >> 5)) << 7) + ((k & 3) << 5) + ((e & 31) ^ ((k & 3) << 3));
+}
 
 // ---- 3xTF32 operand split ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tf32_rn(float x) {

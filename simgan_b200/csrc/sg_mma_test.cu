@@ -10,7 +10,7 @@ struct MmaTestArgs {
     int M, N, K;
     int a_mn, b_mn;       // operand given MN-major ((K, M) / (K, N) row-major) instead of K-major ((M, K) / (N, K))
     int raw;              // probe: A / B are verbatim shared-memory images and the descriptor strides come from rs[]
-    int rs[6];            // {a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step} in bytes
+    int rs[8];            // {a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step} in bytes, {a_layout_type, b_layout_type}
     int passes;           // 3 = 3xTF32 (hi*hi + hi*lo + lo*hi), 1 = plain TF32
     const float *A, *B;
     float* D;
@@ -29,20 +29,22 @@ __device__ void fill_operand(float4* hi, float4* lo, const float* __restrict__ s
             hi[g] = h; lo[g] = l;
         }
     } else {
-        // source (k, e) row-major; granule (e/4)*Kx + k
+        // source (k, e) row-major -> SWIZZLE_128B_BASE32B image: the aligned quad e..e+3 is one granule
         const int EB = E >> 2;
-        for (int g = tid; g < EB * Kx; g += nth) {
-            const int eb = g / Kx, k = g - eb * Kx;
-            const float4 x = *reinterpret_cast<const float4*>(src + (size_t)k * E + 4 * eb);
+        for (int q = tid; q < EB * Kx; q += nth) {
+            const int k = q / EB, e = 4 * (q - k * EB);
+            const float4 x = *reinterpret_cast<const float4*>(src + (size_t)k * E + e);
             float4 h, l;
             mma::split4(x, h, l);
-            hi[g] = h; lo[g] = l;
+            const int off = mma::mnmajor_off(e, k, E);
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(hi) + off) = h;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(lo) + off) = l;
         }
     }
 }
 
 __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(MmaTestArgs a) {
-    extern __shared__ __align__(128) float4 smem4[];
+    extern __shared__ __align__(1024) float4 smem4[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -75,14 +77,18 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(MmaTestArgs a) {
     if (warp == 0) {
         if (mma::elect_one()) {
             const uint32_t idesc = mma::make_idesc_tf32(M, N, a.a_mn, a.b_mn);
-            uint32_t a_lbo = a.a_mn ? 128u : 16u * M, a_sbo = a.a_mn ? 16u * K : 128u, a_step = a.a_mn ? 128u : 32u * M;
-            uint32_t b_lbo = a.b_mn ? 128u : 16u * N, b_sbo = a.b_mn ? 16u * K : 128u, b_step = a.b_mn ? 128u : 32u * N;
-            if (a.raw) { a_lbo = a.rs[0]; a_sbo = a.rs[1]; a_step = a.rs[2]; b_lbo = a.rs[3]; b_sbo = a.rs[4]; b_step = a.rs[5]; }
+            uint32_t a_lbo = a.a_mn ? 512u : 16u * M, a_sbo = a.a_mn ? 16u * M : 128u, a_step = 32u * M;
+            uint32_t b_lbo = a.b_mn ? 512u : 16u * N, b_sbo = a.b_mn ? 16u * N : 128u, b_step = 32u * N;
+            uint32_t a_lt = a.a_mn ? 1u : 0u, b_lt = a.b_mn ? 1u : 0u;
+            if (a.raw) {
+                a_lbo = a.rs[0]; a_sbo = a.rs[1]; a_step = a.rs[2]; b_lbo = a.rs[3]; b_sbo = a.rs[4]; b_step = a.rs[5];
+                a_lt = a.rs[6]; b_lt = a.rs[7];
+            }
             const uint32_t ah = mma::smem_addr(Ahi), al = mma::smem_addr(Alo), bh = mma::smem_addr(Bhi), bl = mma::smem_addr(Blo);
             uint32_t accum = 0;
             for (int ks = 0; ks < K / 8; ++ks) {
-                const uint64_t dAh = mma::make_desc(ah + ks * a_step, a_lbo, a_sbo), dAl = mma::make_desc(al + ks * a_step, a_lbo, a_sbo);
-                const uint64_t dBh = mma::make_desc(bh + ks * b_step, b_lbo, b_sbo), dBl = mma::make_desc(bl + ks * b_step, b_lbo, b_sbo);
+                const uint64_t dAh = mma::make_desc(ah + ks * a_step, a_lbo, a_sbo, a_lt), dAl = mma::make_desc(al + ks * a_step, a_lbo, a_sbo, a_lt);
+                const uint64_t dBh = mma::make_desc(bh + ks * b_step, b_lbo, b_sbo, b_lt), dBl = mma::make_desc(bl + ks * b_step, b_lbo, b_sbo, b_lt);
                 if (a.passes == 3) {
                     mma::mma_tf32(tbase, dAl, dBh, idesc, accum); accum = 1;
                     mma::mma_tf32(tbase, dAh, dBl, idesc, accum);
@@ -133,9 +139,11 @@ int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int pas
     const size_t smem = (size_t)2 * (M + N) * K * sizeof(float);
     SG_REQUIRE(smem <= 200 * 1024, "sg_selftest_mma: operands need %zu bytes of shared memory", smem);
     SG_REQUIRE(!h_raw_strides || passes == 1, "sg_selftest_mma: raw images run a single pass");
-    MmaTestArgs a{M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, h_raw_strides ? 1 : 0, {0, 0, 0, 0, 0, 0}, passes, A, B, D};
+    SG_REQUIRE(h_raw_strides || ((!a_mn_major || M % 32 == 0) && (!b_mn_major || N % 32 == 0)),
+               "sg_selftest_mma: an MN-major operand needs an MN extent that is a multiple of 32");
+    MmaTestArgs a{M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, h_raw_strides ? 1 : 0, {0, 0, 0, 0, 0, 0, 0, 0}, passes, A, B, D};
     if (h_raw_strides)
-        for (int i = 0; i < 6; ++i) a.rs[i] = h_raw_strides[i];
+        for (int i = 0; i < 8; ++i) a.rs[i] = h_raw_strides[i];
     SG_CUDA(cudaFuncSetAttribute(mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     mma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a);
     count_launches(1);

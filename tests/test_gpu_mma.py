@@ -28,8 +28,10 @@ def run(M, N, K, a_mn, b_mn, passes, seed=0):
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 32, 128), (128, 16, 8), (64, 64, 128), (128, 112, 128)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 32, 128), (128, 16, 8), (64, 64, 128), (128, 112, 64), (128, 128, 96)])
 def test_3xtf32_matches_float64(M, N, K, a_mn, b_mn):
+    if b_mn and N % 32:
+        pytest.skip("MN-major operands come in 32-element atoms")
     err = run(M, N, K, a_mn, b_mn, 3)
     assert err < 2e-6, err
 
