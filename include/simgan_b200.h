@@ -120,9 +120,11 @@ typedef struct sg_ppo_config {
                                  processed locally (0, mini_batch_size on a single GPU) */
     int mode;                 /* 0 = auto (resident if the parameter image fits in shared memory, else
                                  persistent), 1 = one launch per phase, 2 = persistent (weights through L2),
-                                 3 = resident (weights in shared memory) */
+                                 3 = resident (weights in shared memory), 4 = tensor cores: tcgen05 kind::tf32 MMAs
+                                 with 3xTF32 operand splitting over 64/128-row jobs (hidden in {64,128,256}, act_dim <= 32,
+                                 obs_dim <= 256); mode 0 picks them once a minibatch fills the SMs with such jobs */
     void* dp_ctx;             /* sg_dp_create context: fused peer-memory gradient exchange inside the persistent
-                                 kernel (modes 0/2/3; every rank must pass shards of equal size); NULL = none */
+                                 kernel (modes 0/2/3/4; every rank must pass shards of equal size); NULL = none */
 } sg_ppo_config;
 
 int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg);

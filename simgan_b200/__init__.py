@@ -4,6 +4,7 @@ Classes mirror third_party/a2c_ppo_acktr of jyf588/SimGAN (Policy, PPO, gail.Dis
 RolloutStorage); the minibatch math runs in hand-written sm_100a kernels behind the C ABI declared
 in include/simgan_b200.h (loaded by simgan_b200._lib).
 """
+from ._lib import SgError  # noqa: F401
 from .model import Policy, MLPBase  # noqa: F401
 from .model_split import SplitPolicy  # noqa: F401
 from .storage import RolloutStorage  # noqa: F401

@@ -17,6 +17,8 @@ from .adam import FusedAdam
 
 
 class PPO(object):
+    MMA_MODE = 4        # kernel_mode: tcgen05 3xTF32 tensor-core tiles (sg_ppo_config.mode 4)
+
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
                  symmetry_coef=0, lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True,
                  mirror_obs=None, mirror_act=None):
@@ -36,7 +38,7 @@ class PPO(object):
         self.mirror_obs = mirror_obs
         self.mirror_act = mirror_act
         self.is_cuda = next(actor_critic.parameters()).is_cuda
-        self.kernel_mode = 0            # 0: persistent cooperative kernel, 1: one launch per phase
+        self.kernel_mode = 0            # 0: automatic, 1: one launch per phase, 2/3: CUDA-core tiles, 4: tensor-core tiles
         self.dp = None                  # simgan_b200.dist.DataParallel or None
         self.last_trace = None          # (n_steps, 4) {value_loss, action_loss, entropy, grad_norm}
         self._ws = None

@@ -55,6 +55,10 @@ struct PpoArgs {
     DpView dp;
 };
 
+}  // namespace sg
+#include "sg_ppo_mma.cuh"
+namespace sg {
+
 template <int R>
 struct PpoSmem {
     PolicyTile<R> T;
@@ -865,6 +869,63 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_persistent_kernel(PpoArgs
     poison_trace_on_timeout(a);
 }
 
+// Tensor-core variant (mode 4): the tile phase is sg_ppo_mma.cuh (jobs of MR rows x one net, tcgen05 3xTF32), phases B / C
+// are the ones above with the weights read through L2.
+template <int MR>
+__global__ void __launch_bounds__(kStepThreads, 1) ppo_mma_kernel(PpoArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double red[kStepThreads / 32];
+    const MmaDims d = make_mma_dims(a.O, a.H, a.A, MR);
+    MmaSmem S;
+    S.carve(smem_raw, d);
+    MmaPipe P;
+    P.init();
+    if (threadIdx.x < 32) {
+        mma::tmem_alloc(S.tmem_slot, (uint32_t)d.tmem_cols);
+        mma::tmem_relinquish();
+    }
+    if (threadIdx.x == 0) { mbar_init(S.bar, 1); mbar_init(S.bar + 1, 1); }
+    mma::fence_before_sync();
+    __syncthreads();
+    mma::fence_after_sync();
+    const uint32_t tbase = *S.tmem_slot;
+    float* tile = S.stage[0];                    // scratch of phases B / C (no MMA is in flight there)
+    GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
+    PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
+    pc.start();
+    const bool own1 = a.SL <= kStepThreads && a.SL <= 512;
+    for (int step = 0; step < a.nsteps; ++step) {
+        float4 mine;
+        ppo_phaseA_mma<MR>(a, d, S, P, tbase, step, blockIdx.x, gridDim.x);
+        pc.lap(1);
+        gb.sync();
+        pc.lap(2);
+        bool have = ppo_reduce_slice<LdGlobal, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), a.params + a.L.ls, mine);
+        if (a.dp_on) {
+            const int p0 = min(a.P, (int)blockIdx.x * a.SL), p1 = min(a.P, p0 + a.SL);
+            float4* scr4 = reinterpret_cast<float4*>(tile);
+            dp_exchange_slice<kStepThreads>(a.dp, a.grad, p0, p1, blockIdx.x, (unsigned int)(a.first_adam_step + step),
+                                            have ? reinterpret_cast<float*>(scr4 + kStepThreads) : nullptr);
+            if (have) mine = (4 * (int)threadIdx.x < p1 - p0) ? scr4[kStepThreads + threadIdx.x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        PpoOwnElem own;
+        if (own1) own = ppo_own_prefetch(a, blockIdx.x, reinterpret_cast<const float4*>(tile));
+        ppo_ssq_slice(a, blockIdx.x, red, have, mine);
+        pc.lap(3);
+        gb.sync();
+        pc.lap(4);
+        if (own1) ppo_adam_own(a, step, blockIdx.x, red, own);
+        else ppo_adam_slice(a, step, blockIdx.x, red, have, mine);
+        pc.lap(5);
+        gb.sync();
+        pc.lap(6);
+    }
+    poison_trace_on_timeout(a);
+    mma::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) mma::tmem_dealloc(tbase, (uint32_t)d.tmem_cols);
+}
+
 template <int R>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_phaseA_kernel(PpoArgs a, int step) {
     extern __shared__ __align__(16) float smem[];
@@ -891,7 +952,25 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus stat
 // minibatches): half as many tiles, twice the FMAs per weight fetched from shared memory, half the read-modify-write
 // traffic of the per-CTA partial gradient
 static size_t ppo_tile_smem_floats_r(const sg_ppo_config* c, int rows);
+// tensor-core tiles: 128 rows per job when the masters fit shared memory, else 64; 0 = not available for these sizes
+static int ppo_mma_rows(const sg_ppo_config* c) {
+    if (!ppo_mma_supported(c->obs_dim, c->hidden, c->act_dim)) return 0;
+    if ((size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, 128).total <= kMaxDynSmem) return 128;
+    if ((size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, 64).total <= kMaxDynSmem) return 64;
+    return 0;
+}
+// mode 0 picks the tensor-core tiles once a minibatch (shard) keeps every SM busy with full 64/128-row jobs
+static bool ppo_use_mma(const sg_ppo_config* c) {
+    if (c->mode == 4) return true;
+    if (c->mode != 0) return false;
+    const int mr = ppo_mma_rows(c);
+    if (!mr) return false;
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    return (long long)2 * (c->row_end - c->row_begin) >= (long long)mr * sms * 3 / 4;
+}
 static int ppo_rows(const sg_ppo_config* c) {
+    if (ppo_use_mma(c)) return ppo_mma_rows(c);
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
     const int rows = c->row_end - c->row_begin;
@@ -910,7 +989,8 @@ static int ppo_grid(const sg_ppo_config* c, int* sm_count_out) {
     if (sms <= 0) sms = 148;
     if (sm_count_out) *sm_count_out = sms;
     int tiles = ppo_tiles(c);
-    int g = tiles < sms ? tiles : sms;
+    if (ppo_use_mma(c)) tiles *= 2;              // jobs = (tile, net); the grid stays even so that a CTA keeps its net
+    int g = tiles < sms ? tiles : (sms & ~1);
     // never fewer than 64 CTAs: CTAs without a tile skip phase A but still own a slice of the reduce / Adam phases,
     // which keeps those phases on the narrow one-parameter-per-thread path for small (or sharded) minibatches
     const int gmin = sms < 64 ? sms : 64;
@@ -948,7 +1028,11 @@ static int ppo_validate(const sg_ppo_config* c) {
     SG_REQUIRE(c->row_begin >= 0 && c->row_begin < c->row_end && c->row_end <= c->mini_batch_size,
                "sg_ppo: shard [%d,%d) outside minibatch of %d rows", c->row_begin, c->row_end, c->mini_batch_size);
     SG_REQUIRE(c->first_adam_step >= 1, "sg_ppo: first_adam_step is 1-based");
-    SG_REQUIRE(c->mode >= 0 && c->mode <= 3, "sg_ppo: mode must be 0 (auto), 1 (phased), 2 (persistent) or 3 (resident)");
+    SG_REQUIRE(c->mode >= 0 && c->mode <= 4, "sg_ppo: mode must be 0 (auto), 1 (phased), 2 (persistent), 3 (resident) or 4 (tensor cores)");
+    SG_REQUIRE(c->mode != 4 || ppo_mma_rows(c) > 0,
+               "sg_ppo: the tensor-core tiles need hidden in {64,128,256}, act_dim <= 32, obs_dim <= 256 (got %d/%d/%d)", c->hidden,
+               c->act_dim, c->obs_dim);
+    if (ppo_use_mma(c)) return SG_OK;
     const size_t smem = ppo_tile_smem_floats(c) * sizeof(float);
     SG_REQUIRE(smem <= kMaxDynSmem, "sg_ppo: tile needs %zu bytes of shared memory (hidden too large)", smem);
     SG_REQUIRE(c->mode != 3 || ppo_resident_smem_bytes(c) <= kMaxDynSmem,
@@ -1018,7 +1102,9 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     a.nsteps = cfg->ppo_epoch * cfg->num_mini_batch;
     a.row_begin = cfg->row_begin; a.row_end = cfg->row_end;
     a.ntiles = ppo_tiles(cfg);
-    a.nslots = grid < a.ntiles ? grid : a.ntiles;
+    const bool use_mma = ppo_use_mma(cfg);
+    const int njobs = use_mma ? 2 * a.ntiles : a.ntiles;
+    a.nslots = grid < njobs ? grid : njobs;
     a.SL = round_up((a.P + grid - 1) / grid, 4);
     a.nslices = (a.P + a.SL - 1) / a.SL;
     a.clipped_vloss = cfg->use_clipped_value_loss;
@@ -1043,6 +1129,19 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     }
 
     const int tile_rows = ppo_rows(cfg);
+    if (use_mma) {
+        SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
+        const void* fn = tile_rows == 128 ? (const void*)ppo_mma_kernel<128> : (const void*)ppo_mma_kernel<64>;
+        const size_t smem = (size_t)make_mma_dims(a.O, a.H, a.A, tile_rows).total;
+        SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepThreads, smem));
+        SG_REQUIRE(per_sm >= 1 && grid <= per_sm * sms, "sg_ppo_update: cooperative grid of %d CTAs does not fit", grid);
+        void* kargs[] = {(void*)&a};
+        SG_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kStepThreads), kargs, smem, s));
+        count_launches(1);
+        return SG_OK;
+    }
     const size_t smem_tile = ppo_tile_smem_floats_r(cfg, tile_rows) * sizeof(float);
     const size_t smem_res = ppo_resident_smem_bytes_r(cfg, tile_rows);
     int mode = cfg->mode;

@@ -170,7 +170,7 @@ def _ppo_objects(g, mode):
 
 
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("mode", [1, 2, 0])
+@pytest.mark.parametrize("mode", [1, 2, 0, 4])
 def test_ppo_per_step_trace_vs_oracle(case, mode):
     """Every optimizer step's (value_loss, action_loss, entropy, grad_norm) against the oracle replaying the
     same recorded index stream; parameters after the whole update."""
