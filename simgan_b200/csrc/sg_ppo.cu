@@ -51,6 +51,9 @@ struct PpoArgs {
     double* ssq;
     unsigned int* bar;
     long long* prof;      // per-phase clock64 totals of CTA 0 (sg_ppo_phase_cycles)
+    float* wimg;          // hi / lo operand images of the weights (tensor-core tiles, sg_ppo_mma.cuh)
+    int mma_ns;           // stage buffers of the tensor-core tiles
+    int slots_by_net;     // partial-gradient slot c only holds net c & 1 (tensor-core tiles)
     int dp_on;            // fused peer-memory gradient exchange (sg_dp.cuh)
     DpView dp;
 };
@@ -655,7 +658,16 @@ __device__ bool ppo_reduce_slice(const PpoArgs& a, int cta, float4* scr4, const 
             l1[i] = ok ? ld_cg(a.losspart + c * 4 + 1) : 0.f;
         }
     }
-    const bool narrow = reduce_partials_slice<kStepThreads, KEEP>(a.gpart, (size_t)a.P, a.nslots, p0, p1, a.grad, scr4, tid, mine);
+    // tensor-core tiles: slot c holds the partial gradient of net c & 1 only (zeros elsewhere), so a slice that lies inside
+    // one net's parameters is summed over that net's slots -- half the L2 reads
+    const float* part = a.gpart;
+    size_t stride = (size_t)a.P;
+    int nslots = a.nslots;
+    if (a.slots_by_net) {
+        const int net = (p1 <= a.L.cw1 || p0 >= a.L.mw) ? 0 : ((p0 >= a.L.cw1 && p1 <= a.L.mw) ? 1 : -1);
+        if (net >= 0) { part += (size_t)net * a.P; stride *= 2; nslots = (a.nslots - net + 1) / 2; }
+    }
+    const bool narrow = reduce_partials_slice<kStepThreads, KEEP>(part, stride, nslots, p0, p1, a.grad, scr4, tid, mine);
     if (lossw) {
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -875,7 +887,7 @@ template <int MR>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_mma_kernel(PpoArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double red[kStepThreads / 32];
-    const MmaDims d = make_mma_dims(a.O, a.H, a.A, MR);
+    const MmaDims d = make_mma_dims(a.O, a.H, a.A, MR, a.mma_ns);
     MmaSmem S;
     S.carve(smem_raw, d);
     MmaPipe P;
@@ -884,25 +896,31 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_mma_kernel(PpoArgs a) {
         mma::tmem_alloc(S.tmem_slot, (uint32_t)d.tmem_cols);
         mma::tmem_relinquish();
     }
-    if (threadIdx.x == 0) { mbar_init(S.bar, 1); mbar_init(S.bar + 1, 1); }
+    if (threadIdx.x == 0)
+        for (int s = 0; s < kMmaMaxStages; ++s) { mbar_init(S.full + s, 1); mbar_init(S.done + s, 1); }
     mma::fence_before_sync();
     __syncthreads();
     mma::fence_after_sync();
     const uint32_t tbase = *S.tmem_slot;
-    float* tile = S.stage[0];                    // scratch of phases B / C (no MMA is in flight there)
+    float* tile = S.stage0;                    // scratch of phases B / C (no MMA or TMA is in flight there)
     GridBarrier gb{a.bar, a.bar + 1, gridDim.x, 0};
     PhaseClock pc{a.prof + 8 * blockIdx.x, threadIdx.x == 0};
     pc.start();
     const bool own1 = a.SL <= kStepThreads && a.SL <= 512;
+    const int p0 = min(a.P, (int)blockIdx.x * a.SL), p1 = min(a.P, p0 + a.SL);
+    // operand images of my slice of the parameter vector (kept current after every Adam step below)
+    mma_img_refresh(a.wimg, a.params, a.L, a.O, a.H, a.A, p0, p1);
+    gb.sync();
+    pc.lap(0);
     for (int step = 0; step < a.nsteps; ++step) {
         float4 mine;
+        mma::fence_async_smem();                 // the stage buffers were scratch of the previous step's phases B / C
         ppo_phaseA_mma<MR>(a, d, S, P, tbase, step, blockIdx.x, gridDim.x);
         pc.lap(1);
         gb.sync();
         pc.lap(2);
         bool have = ppo_reduce_slice<LdGlobal, true>(a, blockIdx.x, reinterpret_cast<float4*>(tile), a.params + a.L.ls, mine);
         if (a.dp_on) {
-            const int p0 = min(a.P, (int)blockIdx.x * a.SL), p1 = min(a.P, p0 + a.SL);
             float4* scr4 = reinterpret_cast<float4*>(tile);
             dp_exchange_slice<kStepThreads>(a.dp, a.grad, p0, p1, blockIdx.x, (unsigned int)(a.first_adam_step + step),
                                             have ? reinterpret_cast<float*>(scr4 + kStepThreads) : nullptr);
@@ -916,6 +934,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_mma_kernel(PpoArgs a) {
         pc.lap(4);
         if (own1) ppo_adam_own(a, step, blockIdx.x, red, own);
         else ppo_adam_slice(a, step, blockIdx.x, red, have, mine);
+        __syncthreads();
+        mma_img_refresh(a.wimg, a.params, a.L, a.O, a.H, a.A, p0, p1);
         pc.lap(5);
         gb.sync();
         pc.lap(6);
@@ -953,10 +973,14 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus stat
 // traffic of the per-CTA partial gradient
 static size_t ppo_tile_smem_floats_r(const sg_ppo_config* c, int rows);
 // tensor-core tiles: 128 rows per job when the masters fit shared memory, else 64; 0 = not available for these sizes
-static int ppo_mma_rows(const sg_ppo_config* c) {
+static int ppo_mma_rows(const sg_ppo_config* c, int* stages = nullptr) {
     if (!ppo_mma_supported(c->obs_dim, c->hidden, c->act_dim)) return 0;
-    if ((size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, 128).total <= kMaxDynSmem) return 128;
-    if ((size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, 64).total <= kMaxDynSmem) return 64;
+    for (int mr = 128; mr >= 64; mr -= 64)
+        for (int ns = kMmaMaxStages; ns >= 2; --ns)
+            if ((size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, mr, ns).total <= kMaxDynSmem) {
+                if (stages) *stages = ns;
+                return mr;
+            }
     return 0;
 }
 // mode 0 picks the tensor-core tiles once a minibatch (shard) keeps every SM busy with full 64/128-row jobs
@@ -1041,7 +1065,7 @@ static int ppo_validate(const sg_ppo_config* c) {
 }
 
 struct PpoWs {
-    size_t gpart, grad, losspart, scal, ssq, bar, prof, total;
+    size_t gpart, grad, losspart, scal, ssq, bar, prof, wimg, total;
 };
 static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     PolicyLayout L = make_policy_layout(c->obs_dim, c->hidden, c->act_dim);
@@ -1055,6 +1079,7 @@ static PpoWs ppo_ws(const sg_ppo_config* c, int grid) {
     w.ssq = take((size_t)grid * sizeof(double));
     w.bar = take(2 * sizeof(unsigned int));
     w.prof = take((size_t)grid * 8 * sizeof(long long));
+    w.wimg = take(ppo_use_mma(c) ? mma_img_total_floats(c->obs_dim, c->hidden) * sizeof(float) : 0);
     w.total = o;
     return w;
 }
@@ -1129,10 +1154,14 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
     }
 
     const int tile_rows = ppo_rows(cfg);
+    a.wimg = (float*)(ws + w.wimg);
+    a.mma_ns = 2;
+    a.slots_by_net = use_mma ? 1 : 0;
     if (use_mma) {
         SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
+        ppo_mma_rows(cfg, &a.mma_ns);
         const void* fn = tile_rows == 128 ? (const void*)ppo_mma_kernel<128> : (const void*)ppo_mma_kernel<64>;
-        const size_t smem = (size_t)make_mma_dims(a.O, a.H, a.A, tile_rows).total;
+        const size_t smem = (size_t)make_mma_dims(a.O, a.H, a.A, tile_rows, a.mma_ns).total;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepThreads, smem));

@@ -13,56 +13,73 @@
 // fp32 accuracy on TF32 tensor cores: every operand is split a = hi + lo (hi = RN_tf32(a), lo = RN_tf32(a - hi)) and a
 // product is three MMAs lo*hi + hi*lo + hi*hi ("3xTF32", ~2^-21 relative), which keeps the 1e-4 loss contract.
 //
-// Data flow: activations live once, in fp32, in shared-memory "masters" laid out [col/4][row][col%4] (16-byte granules,
-// row pitch MR+4 granules); weights stay in global memory (L2).  For every K-chunk all 256 threads build the hi / lo operand
-// images of the chunk in one of two stage buffers (K-major or MN-major, sg_mma.cuh) while the tensor core works on the
-// other one (tcgen05.commit -> mbarrier per stage); the next chunk's source values are already in registers when the
-// current one is stored, so the L2 latency of the weight reads hides behind the MMAs.  Epilogues read the accumulator
-// with tcgen05.ld (thread = row, or = hidden unit for the weight gradients), apply bias / tanh / tanh' and write the
-// next master or the CTA's partial gradient.
+// Data flow
+//   activations  live once, in fp32, in shared-memory "masters" laid out [col/4][row][col%4] (16-byte granules, row
+//                pitch MR+1 granules); for every K-chunk the 256 threads build the hi / lo operand images of the chunk in a
+//                ring of stage buffers (K-major or MN-major, sg_mma.cuh);
+//   weights      are kept as ready-made hi / lo operand images of the whole K extent in global memory (L2): the CTA that
+//                owns a slice of the parameter vector rewrites the image entries of its parameters right after their Adam
+//                update, so a K-chunk of a weight operand is two contiguous TMA bulk copies (cp.async.bulk -> mbarrier
+//                transaction bytes) issued one to two chunks ahead -- no register staging, no split arithmetic;
+//   accumulators live in tensor memory; epilogues read them with tcgen05.ld (thread = row, or = hidden unit for the weight
+//                gradients), apply bias / tanh / tanh' and write the next master or the CTA's partial gradient.  When the
+//                three weight-gradient accumulators fit beside the working accumulator (hidden <= 128) they stay in
+//                tensor memory across all jobs of the CTA and are flushed once per optimizer step.
 #pragma once
 #include "sg_common.cuh"
 #include "sg_policy.cuh"
 #include "sg_mma.cuh"
+#ifdef SG_MMA_PROFILE
+#include <stdio.h>
+#endif
 
 namespace sg {
 
-constexpr int kMmaStageBytes = 24 * 1024;      // one stage buffer (hi + lo images of the A and B chunk); two of them
+constexpr int kMmaStageBytes = 24 * 1024;      // one stage: hi + lo images of the A chunk and of the B chunk
 constexpr int kMmaRedStride = 36;
+constexpr int kMmaMaxStages = 3;
 
 struct MmaDims {
     int MR, MRP;            // rows per job; master row pitch in granules
     int O, H, A;
     int Op8, Op32;          // K extent of layer 1; N extent of the dW1 contraction
-    int xg, hg, dg;         // granule columns of the X / hidden / dHead masters
+    int xg, hg, dg, ag;     // granule columns of the X / hidden / dHead / action masters
     int Mb, nblk;           // weight-gradient contractions: rows (hidden units) per MMA and number of such blocks
+    int NS;                 // stage buffers
+    int tacc;               // weight-gradient accumulators stay in tensor memory across the CTA's jobs
+    int c_dwh, c_dw2, c_dw1;// their columns (tacc)
     int tmem_cols;
     // shared-memory carve-up (bytes from the 1024-aligned base)
-    int o_stage, o_X, o_H1, o_H2, o_DH, o_small, total;
+    int o_stage, o_X, o_ACT, o_H1, o_H2, o_DH, o_small, total;
 };
 
-__host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR) {
+__host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR, int NS) {
     MmaDims d;
-    d.MR = MR; d.MRP = MR + 4;
+    d.MR = MR; d.MRP = MR + 1;
     d.O = O; d.H = H; d.A = A;
     d.Op8 = round_up(O, 8); d.Op32 = round_up(O, 32);
-    d.xg = d.Op8 / 4; d.hg = H / 4; d.dg = 8;
+    d.xg = d.Op8 / 4; d.hg = H / 4; d.dg = 8; d.ag = round_up(A, 4) / 4;
     d.Mb = H >= 128 ? 128 : 64;
     d.nblk = H / d.Mb;
-    int cols = H > d.Op32 ? H : d.Op32;
+    d.NS = NS;
+    const int work = H > 32 ? H : 32;
+    d.c_dwh = work; d.c_dw2 = work + 32; d.c_dw1 = work + 32 + H;
+    d.tacc = (d.nblk == 1 && d.c_dw1 + d.Op32 <= 512) ? 1 : 0;
+    int cols = d.tacc ? d.c_dw1 + d.Op32 : (H > d.Op32 ? H : d.Op32);
     int t = 32;
     while (t < cols) t <<= 1;
     d.tmem_cols = t;
     int o = 0;
-    d.o_stage = o; o += 2 * kMmaStageBytes;
+    d.o_stage = o; o += NS * kMmaStageBytes;
     d.o_X = o; o += d.xg * d.MRP * 16;
+    d.o_ACT = o; o += d.ag * d.MRP * 16;
     d.o_H1 = o; o += d.hg * d.MRP * 16;
     d.o_H2 = o; o += d.hg * d.MRP * 16;
     d.o_DH = o; o += d.dg * d.MRP * 16;
     d.o_small = o;
-    // B1 B2 (H each), BH LS (32 each), 5 row-scalar arrays + IDX (MR each), GB1 GB2 (H), GBH GLS (32), LOSS (4),
-    // RED (8 warps x 36), 2 mbarriers + tmem slot (32 bytes)
-    o += (4 * H + 4 * 32 + 6 * MR + 4 + 8 * kMmaRedStride) * 4 + 32;
+    // B1 B2 GB1 GB2 (H each), BH LS SIG VAR LSG GBH GLS (32 each), 5 row-scalar arrays + IDX (MR each), LOSS (4),
+    // RED (8 warps x 36), 2*3 mbarriers + tmem slot (64 bytes)
+    o += (4 * H + 7 * 32 + 6 * MR + 4 + 8 * kMmaRedStride) * 4 + 64;
     d.total = round_up(o, 16);
     return d;
 }
@@ -70,199 +87,291 @@ __host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR) {
 // H in {64,128,256}, A <= 32, O <= 256
 __host__ inline bool ppo_mma_supported(int O, int H, int A) { return (H == 64 || H == 128 || H == 256) && A >= 1 && A <= 32 && O >= 1 && O <= 256; }
 
+// ---- weight operand images in global memory -----------------------------------------------------------------------------
+// per net, hi image then lo image (net_floats apart): W1 K-major (E = H, K = Op8), W2 K-major (E = H, K = H), head K-major
+// (E = NA16, K = H), head MN-major (E = H, K = NA8), W2 MN-major (E = H, K = H); zero where padded.
+struct MmaImg {
+    int w1k, w2k, whk, whm, w2m, net_floats;
+};
+__host__ __device__ inline MmaImg make_mma_img(int O, int H) {
+    MmaImg g;
+    int o = 0;
+    g.w1k = o; o += H * round_up(O, 8);
+    g.w2k = o; o += H * H;
+    g.whk = o; o += 32 * H;
+    g.whm = o; o += 32 * H;
+    g.w2m = o; o += H * H;
+    g.net_floats = o;
+    return g;
+}
+__host__ __device__ inline size_t mma_img_total_floats(int O, int H) { return (size_t)4 * make_mma_img(O, H).net_floats; }
+
+// image entries of parameter p (flat index) <- w.  Called by the owner of the parameter slice after Adam.
+__device__ __forceinline__ void mma_img_put(float* __restrict__ wimg, const MmaImg& g, const PolicyLayout& L, int O, int H, int A,
+                                            int p, float w) {
+    int net, off0, off1 = -1;
+    if (p >= L.aw1 && p < L.aw1 + H * O) { net = 0; const int i = p - L.aw1, n = i / O, k = i - n * O; off0 = g.w1k + mma::kmajor_off(n, k, H); }
+    else if (p >= L.cw1 && p < L.cw1 + H * O) { net = 1; const int i = p - L.cw1, n = i / O, k = i - n * O; off0 = g.w1k + mma::kmajor_off(n, k, H); }
+    else if (p >= L.aw2 && p < L.aw2 + H * H) {
+        net = 0; const int i = p - L.aw2, n = i / H, k = i - n * H;
+        off0 = g.w2k + mma::kmajor_off(n, k, H); off1 = g.w2m + mma::mnmajor_off(k, n, H);
+    } else if (p >= L.cw2 && p < L.cw2 + H * H) {
+        net = 1; const int i = p - L.cw2, n = i / H, k = i - n * H;
+        off0 = g.w2k + mma::kmajor_off(n, k, H); off1 = g.w2m + mma::mnmajor_off(k, n, H);
+    } else if (p >= L.mw && p < L.mw + A * H) {
+        net = 0; const int i = p - L.mw, n = i / H, k = i - n * H;
+        off0 = g.whk + mma::kmajor_off(n, k, round_up(A, 16)); off1 = g.whm + mma::mnmajor_off(k, n, H);
+    } else if (p >= L.vw && p < L.vw + H) {
+        net = 1; const int k = p - L.vw;
+        off0 = g.whk + mma::kmajor_off(0, k, 16); off1 = g.whm + mma::mnmajor_off(k, 0, H);
+    } else return;
+    float hi, lo;
+    mma::split_tf32(w, hi, lo);
+    float* base = wimg + (size_t)(2 * net) * g.net_floats;
+    __stcg(base + off0, hi);
+    __stcg(base + g.net_floats + off0, lo);
+    if (off1 >= 0) { __stcg(base + off1, hi); __stcg(base + g.net_floats + off1, lo); }
+}
+// refresh the images of the parameter range [p0, p1) from the (just updated) flat vector; all threads of the CTA call
+__device__ __forceinline__ void mma_img_refresh(float* __restrict__ wimg, const float* __restrict__ params, const PolicyLayout& L,
+                                                int O, int H, int A, int p0, int p1) {
+    const MmaImg g = make_mma_img(O, H);
+    for (int p = p0 + threadIdx.x; p < p1; p += kStepThreads) mma_img_put(wimg, g, L, O, H, A, p, ld_cg(params + p));
+}
+
 struct MmaSmem {
-    float* stage[2];
-    float4 *X, *H1, *H2, *DH;
-    float *B1, *B2, *BH, *LS, *RET, *VP, *OLP, *ADV, *VALID, *GB1, *GB2, *GBH, *GLS, *LOSS, *RED;
+    float* stage0;
+    __device__ __forceinline__ float* stage(int s) const { return stage0 + s * (kMmaStageBytes / 4); }
+    float4 *X, *ACT, *H1, *H2, *DH;
+    float *B1, *B2, *GB1, *GB2, *BH, *LS, *IVAR, *I2VAR, *LSG, *GBH, *GLS, *RET, *VP, *OLP, *ADV, *VALID, *LOSS, *RED;
     int* IDX;
-    unsigned long long* bar;
+    unsigned long long *full, *done;
     uint32_t* tmem_slot;
     __device__ void carve(unsigned char* base, const MmaDims& d) {
-        stage[0] = reinterpret_cast<float*>(base + d.o_stage);
-        stage[1] = reinterpret_cast<float*>(base + d.o_stage + kMmaStageBytes);
+        stage0 = reinterpret_cast<float*>(base + d.o_stage);
         X = reinterpret_cast<float4*>(base + d.o_X);
+        ACT = reinterpret_cast<float4*>(base + d.o_ACT);
         H1 = reinterpret_cast<float4*>(base + d.o_H1);
         H2 = reinterpret_cast<float4*>(base + d.o_H2);
         DH = reinterpret_cast<float4*>(base + d.o_DH);
         float* f = reinterpret_cast<float*>(base + d.o_small);
         B1 = f; f += d.H;
         B2 = f; f += d.H;
+        GB1 = f; f += d.H;
+        GB2 = f; f += d.H;
         BH = f; f += 32;
         LS = f; f += 32;
+        IVAR = f; f += 32;
+        I2VAR = f; f += 32;
+        LSG = f; f += 32;
+        GBH = f; f += 32;
+        GLS = f; f += 32;
         RET = f; f += d.MR;
         VP = f; f += d.MR;
         OLP = f; f += d.MR;
         ADV = f; f += d.MR;
         VALID = f; f += d.MR;
         IDX = reinterpret_cast<int*>(f); f += d.MR;
-        GB1 = f; f += d.H;
-        GB2 = f; f += d.H;
-        GBH = f; f += 32;
-        GLS = f; f += 32;
         LOSS = f; f += 4;
         RED = f; f += 8 * kMmaRedStride;
-        bar = reinterpret_cast<unsigned long long*>(f);
-        tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+        full = reinterpret_cast<unsigned long long*>(f);
+        done = full + kMmaMaxStages;
+        tmem_slot = reinterpret_cast<uint32_t*>(done + kMmaMaxStages);
     }
 };
 
 // ---- operand sources -------------------------------------------------------------------------------------------------------
 struct MmaOperand {
-    int kind;                 // 0 K-major <- master, 1 MN-major <- master, 2 K-major <- global, 3 MN-major <- global
+    int kind;                 // 0 K-major <- master, 1 MN-major <- master, 2 K-major <- global image (TMA), 3 MN-major image
     int E;                    // MN extent of the stage image (multiple of 8; of 32 when MN-major)
     const float4* m4;         // master (kinds 0, 1)
     int e0, ecols;            // kind 1: first master column of the image and number of valid master columns
-    const float* g;           // global row-major matrix (kinds 2, 3), read through L2 (rewritten by Adam between steps)
-    int ld, nvalid, kvalid;   // row pitch in floats; valid MN extent; valid K extent
+    const float* img;         // kinds 2, 3: hi image of the whole K extent in global memory; lo image img_lo floats further
+    int img_lo;
 };
-__device__ __forceinline__ MmaOperand op_master_k(const float4* m4, int E) { return MmaOperand{0, E, m4, 0, 0, nullptr, 0, 0, 0}; }
-__device__ __forceinline__ MmaOperand op_master_mn(const float4* m4, int E, int e0, int ecols) {
-    return MmaOperand{1, E, m4, e0, ecols, nullptr, 0, 0, 0};
-}
-// W is (nvalid, kvalid) row-major with pitch ld: element (e, k) = W[e*ld + k]
-__device__ __forceinline__ MmaOperand op_global_k(const float* W, int E, int ld, int nvalid, int kvalid) {
-    return MmaOperand{2, E, nullptr, 0, 0, W, ld, nvalid, kvalid};
-}
-// W is (kvalid, nvalid) row-major with pitch ld: element (e, k) = W[k*ld + e]
-__device__ __forceinline__ MmaOperand op_global_mn(const float* W, int E, int ld, int nvalid, int kvalid) {
-    return MmaOperand{3, E, nullptr, 0, 0, W, ld, nvalid, kvalid};
-}
-
-// granule gi of the chunk [k0, k0+kc): its four source floats and where they go in the stage image (float offset)
-__device__ __forceinline__ float4 mma_src(const MmaOperand& op, int gi, int k0, int MRP, int& dst) {
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (op.kind == 0) {
-        const int kq = gi / op.E, e = gi - kq * op.E;
-        dst = gi << 2;
-        return op.m4[((k0 >> 2) + kq) * MRP + e];
-    }
-    if (op.kind == 2) {
-        const int kq = gi / op.E, e = gi - kq * op.E;
-        dst = gi << 2;
-        const int k = k0 + 4 * kq;
-        if (e >= op.nvalid || k >= op.kvalid) return zero;
-        const float* p = op.g + (size_t)e * op.ld + k;
-        if ((op.ld & 3) == 0 && k + 3 < op.kvalid) return ld_cg4(p);
-        float4 v = zero;
-        v.x = ld_cg(p);
-        if (k + 1 < op.kvalid) v.y = ld_cg(p + 1);
-        if (k + 2 < op.kvalid) v.z = ld_cg(p + 2);
-        if (k + 3 < op.kvalid) v.w = ld_cg(p + 3);
-        return v;
-    }
-    // MN-major: lanes walk (kk = 4 k-rows, eq8 = 8 quads of one 32-element block): conflict-free stores of whole atoms
-    const int kk = gi & 3, eq8 = (gi >> 2) & 7, t = gi >> 5;
-    const int EB = op.E >> 5;
-    const int kb = t / EB, eb = t - kb * EB;
-    const int k = 4 * kb + kk, e = 32 * eb + 4 * eq8;
-    dst = mma::mnmajor_off(e, k, op.E);
-    if (op.kind == 1) {
-        const int c = op.e0 + e;
-        return c < op.ecols ? op.m4[(c >> 2) * MRP + k0 + k] : zero;
-    }
-    const int kg = k0 + k;
-    if (kg >= op.kvalid || e >= op.nvalid) return zero;
-    const float* p = op.g + (size_t)kg * op.ld + e;
-    if ((op.ld & 3) == 0 && e + 3 < op.nvalid) return ld_cg4(p);
-    float4 v = zero;
-    v.x = ld_cg(p);
-    if (e + 1 < op.nvalid) v.y = ld_cg(p + 1);
-    if (e + 2 < op.nvalid) v.z = ld_cg(p + 2);
-    if (e + 3 < op.nvalid) v.w = ld_cg(p + 3);
-    return v;
-}
+__device__ __forceinline__ MmaOperand op_master_k(const float4* m4, int E) { return MmaOperand{0, E, m4, 0, 0, nullptr, 0}; }
+__device__ __forceinline__ MmaOperand op_master_mn(const float4* m4, int E, int e0, int ecols) { return MmaOperand{1, E, m4, e0, ecols, nullptr, 0}; }
+__device__ __forceinline__ MmaOperand op_image(const float* img, int lo, int E, int mn) { return MmaOperand{2 + mn, E, nullptr, 0, 0, img, lo}; }
 
 constexpr int kMmaMaxG = 3;       // granules per thread, operand and chunk: 24 KiB / 8 bytes per element / 4 / 256 threads
 
-struct MmaRegs {
-    float4 v[kMmaMaxG];
-    int dst[kMmaMaxG];
+// per-thread, per-GEMM plan of a master operand: which master granule each of my (up to 3) stage granules comes from at
+// k0 = 0 and where it goes; both are independent of the chunk, so a chunk only adds an offset
+struct MmaPlan {
+    int src[kMmaMaxG], dst[kMmaMaxG];      // master granule index at k0 = 0 (-1: zero fill), stage float offset
 };
-__device__ __forceinline__ void mma_load(const MmaOperand& op, int k0, int kc, int MRP, MmaRegs& r) {
-    const int ng = (kc * op.E) >> 2;
+__device__ __forceinline__ void mma_plan(const MmaOperand& op, int MRP, MmaPlan& pl) {
 #pragma unroll
     for (int i = 0; i < kMmaMaxG; ++i) {
         const int gi = threadIdx.x + i * kStepThreads;
-        r.dst[i] = -1;
-        if (gi < ng) r.v[i] = mma_src(op, gi, k0, MRP, r.dst[i]);
+        if (op.kind == 0) {
+            const int kq = gi / op.E, e = gi - kq * op.E;
+            pl.src[i] = kq * MRP + e;
+            pl.dst[i] = gi << 2;
+        } else {
+            // MN-major: lanes walk (kk = 4 k-rows, eq8 = 8 quads of one 32-element block): conflict-free stores of whole atoms
+            const int kk = gi & 3, eq8 = (gi >> 2) & 7, t = gi >> 5;
+            const int EB = op.E >> 5;
+            const int kb = t / EB, eb = t - kb * EB;
+            const int k = 4 * kb + kk, e = 32 * eb + 4 * eq8;
+            const int c = op.e0 + e;
+            pl.src[i] = c < op.ecols ? (c >> 2) * MRP + k : -1;
+            pl.dst[i] = mma::mnmajor_off(e, k, op.E);
+        }
     }
 }
-__device__ __forceinline__ void mma_store(const MmaRegs& r, float* hi, float* lo) {
+// chunk [k0, k0+kc) of a master operand -> hi / lo stage images.  hi = x with the 13 low mantissa bits cleared (what the
+// tensor core reads of an fp32 word anyway), lo = x - hi exactly (13 significant bits, of which the tensor core keeps 11):
+// x = hi + lo to 2^-21 relative, two instructions per element
+__device__ __forceinline__ void mma_fill(const MmaOperand& op, const MmaPlan& pl, int MRP, int k0, int kc, float* hi, float* lo) {
+    const int ng = (kc * op.E) >> 2;
+    const int delta = op.kind == 0 ? (k0 >> 2) * MRP : k0;
 #pragma unroll
     for (int i = 0; i < kMmaMaxG; ++i) {
-        if (r.dst[i] >= 0) {
-            float4 h, l;
-            mma::split4(r.v[i], h, l);
-            *reinterpret_cast<float4*>(hi + r.dst[i]) = h;
-            *reinterpret_cast<float4*>(lo + r.dst[i]) = l;
+        if (i * kStepThreads >= ng) break;
+        const int gi = threadIdx.x + i * kStepThreads;
+        if (gi < ng) {
+            const float4 x = pl.src[i] >= 0 ? op.m4[pl.src[i] + delta] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+            *reinterpret_cast<float4*>(hi + pl.dst[i]) = h;
+            *reinterpret_cast<float4*>(lo + pl.dst[i]) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
     }
 }
 
 // ---- stage pipeline ------------------------------------------------------------------------------------------------------
+// Stage s is released by the completion of the MMAs that read it (tcgen05.commit -> done[s]); its weight chunk arrives by
+// TMA on full[s].  Every thread tracks the same phase bits (all control flow around them is uniform).
 struct MmaPipe {
-    unsigned int par[2];
-    bool pend[2];
-    int cur;
-    __device__ __forceinline__ void init() { par[0] = par[1] = 0u; pend[0] = pend[1] = false; cur = 0; }
-    // the MMAs that read stage s have completed (its buffer may be rewritten)
-    __device__ __forceinline__ void wait(unsigned long long* bar, int s) {
-        if (pend[s]) { mbar_wait(bar + s, par[s]); par[s] ^= 1u; pend[s] = false; }
+    unsigned int done_par, done_pend, full_par;      // bit s
+    int cur;                                         // stage of the next chunk
+#ifdef SG_MMA_PROFILE
+    long long prof[8];
+#endif
+    __device__ __forceinline__ void init() {
+        done_par = done_pend = full_par = 0u; cur = 0;
+#ifdef SG_MMA_PROFILE
+        for (int i = 0; i < 8; ++i) prof[i] = 0;
+#endif
+    }
+    __device__ __forceinline__ void wait_done(unsigned long long* done, int s) {
+        if ((done_pend >> s) & 1u) {
+            mbar_wait(done + s, (done_par >> s) & 1u);
+            done_par ^= 1u << s;
+            done_pend &= ~(1u << s);
+        }
     }
 };
 
-// D[tmem columns dcol .. dcol+N) (Mi rows) = A . B^T over K, 3xTF32.  All 256 threads call; ends with every MMA complete
-// and visible to tcgen05.ld (callers run their epilogue right away).
-__device__ void mma_gemm(MmaSmem& S, MmaPipe& P, int MRP, uint32_t tbase, uint32_t dcol, int Mi, int N, int K,
-                         const MmaOperand& A, const MmaOperand& B) {
+#ifdef SG_MMA_PROFILE
+#define SG_MMA_T(var) const long long var = clock64()
+#define SG_MMA_ACC(i, expr) P.prof[i] += (expr)
+#else
+#define SG_MMA_T(var)
+#define SG_MMA_ACC(i, expr)
+#endif
+
+// D[tmem columns dcol .. dcol+N) (Mi rows) (+)= A . B^T over K, 3xTF32.  A is a master operand; B a master operand or a
+// weight image.  All 256 threads call; returns with every MMA complete and visible to tcgen05.ld.
+__device__ __forceinline__ void mma_gemm(MmaSmem& S, MmaPipe& P, int NS, int MRP, uint32_t tbase, uint32_t dcol, int Mi, int N, int K,
+                                      MmaOperand A, MmaOperand B, uint32_t accum) {
     const int tid = threadIdx.x;
     const int a_mn = A.kind & 1, b_mn = B.kind & 1;
+    const bool b_img = B.kind >= 2;
     int KC = (kMmaStageBytes / ((A.E + B.E) * 8)) & ~7;
     if (KC > K) KC = K;
+    const int nchunks = (K + KC - 1) / KC;
     const uint32_t idesc = mma::make_idesc_tf32(Mi, N, a_mn, b_mn);
-    const uint32_t a_lbo = a_mn ? 512u : 16u * A.E, a_sbo = a_mn ? 16u * A.E : 128u;
-    const uint32_t b_lbo = b_mn ? 512u : 16u * B.E, b_sbo = b_mn ? 16u * B.E : 128u;
-    MmaRegs ra, rb;
-    mma_load(A, 0, KC < K ? KC : K, MRP, ra);
-    mma_load(B, 0, KC < K ? KC : K, MRP, rb);
-    uint32_t accum = 0;
-    for (int k0 = 0; k0 < K; k0 += KC) {
-        const int kc = K - k0 < KC ? K - k0 : KC;
-        const int s = P.cur;
-        P.cur ^= 1;
-        P.wait(S.bar, s);
-        float* Ahi = S.stage[s];
+    // descriptor templates (everything but the start address) and the per-MMA (K = 8) address step in 16-byte units
+    const uint64_t a_tmpl = mma::make_desc(0u, a_mn ? 512u : 16u * A.E, a_mn ? 16u * A.E : 128u, a_mn);
+    const uint64_t b_tmpl = mma::make_desc(0u, b_mn ? 512u : 16u * B.E, b_mn ? 16u * B.E : 128u, b_mn);
+    const uint32_t a_step = 2u * A.E, b_step = 2u * B.E;
+    MmaPlan pa, pb;
+    mma_plan(A, MRP, pa);
+    if (!b_img) mma_plan(B, MRP, pb);
+    const int s0 = P.cur;
+    // prologue: the first NS-1 weight chunks
+    if (b_img) {
+        const int npre = nchunks < NS - 1 ? nchunks : NS - 1;
+        for (int c = 0; c < npre; ++c) {
+            int s = s0 + c; if (s >= NS) s -= NS;
+            P.wait_done(S.done, s);
+            if (tid == 0) {
+                const int k0 = c * KC, kc = K - k0 < KC ? K - k0 : KC;
+                float* Bhi = S.stage(s) + 2 * A.E * kc;
+                const unsigned int bytes = (unsigned int)(kc * B.E * 4);
+                fence_proxy_async();
+                mbar_expect_tx(S.full + s, 2u * bytes);
+                tma_bulk_g2s(Bhi, B.img + (size_t)k0 * B.E, bytes, S.full + s);
+                tma_bulk_g2s(Bhi + B.E * kc, B.img + B.img_lo + (size_t)k0 * B.E, bytes, S.full + s);
+            }
+        }
+    }
+    for (int c = 0; c < nchunks; ++c) {
+        const int k0 = c * KC, kc = K - k0 < KC ? K - k0 : KC;
+        int s = s0 + c % NS; if (s >= NS) s -= NS;
+        SG_MMA_T(t0);
+        P.wait_done(S.done, s);
+        SG_MMA_T(t1);
+        float* Ahi = S.stage(s);
         float* Alo = Ahi + A.E * kc;
         float* Bhi = Alo + A.E * kc;
         float* Blo = Bhi + B.E * kc;
-        mma_store(ra, Ahi, Alo);
-        mma_store(rb, Bhi, Blo);
-        if (k0 + kc < K) {
-            const int kn = K - (k0 + kc) < KC ? K - (k0 + kc) : KC;
-            mma_load(A, k0 + kc, kn, MRP, ra);
-            mma_load(B, k0 + kc, kn, MRP, rb);
-        }
+        mma_fill(A, pa, MRP, k0, kc, Ahi, Alo);
+        if (!b_img) mma_fill(B, pb, MRP, k0, kc, Bhi, Blo);
+        SG_MMA_T(t2);
         mma::fence_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        SG_MMA_T(t3);
+        if (tid < 32 && mma::elect_one()) {
+            if (b_img) { mbar_wait(S.full + s, (P.full_par >> s) & 1u); }
+            SG_MMA_T(t4);
             mma::fence_after_sync();
-            const uint32_t ah = mma::smem_addr(Ahi), al = mma::smem_addr(Alo), bh = mma::smem_addr(Bhi), bl = mma::smem_addr(Blo);
-            for (int ks = 0; ks < (kc >> 3); ++ks) {
-                const uint32_t sa = (uint32_t)ks * 32u * A.E, sb = (uint32_t)ks * 32u * B.E;
-                const uint64_t dAh = mma::make_desc(ah + sa, a_lbo, a_sbo, a_mn), dAl = mma::make_desc(al + sa, a_lbo, a_sbo, a_mn);
-                const uint64_t dBh = mma::make_desc(bh + sb, b_lbo, b_sbo, b_mn), dBl = mma::make_desc(bl + sb, b_lbo, b_sbo, b_mn);
+            const uint32_t ah = mma::smem_addr(Ahi) >> 4, al = mma::smem_addr(Alo) >> 4, bh = mma::smem_addr(Bhi) >> 4, bl = mma::smem_addr(Blo) >> 4;
+            const int nks = kc >> 3;
+#pragma unroll 2
+            for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t dAh = a_tmpl | (uint64_t)((ah + ks * a_step) & 0x3FFFu), dAl = a_tmpl | (uint64_t)((al + ks * a_step) & 0x3FFFu);
+                const uint64_t dBh = b_tmpl | (uint64_t)((bh + ks * b_step) & 0x3FFFu), dBl = b_tmpl | (uint64_t)((bl + ks * b_step) & 0x3FFFu);
                 mma::mma_tf32(tbase + dcol, dAl, dBh, idesc, accum);
                 mma::mma_tf32(tbase + dcol, dAh, dBl, idesc, 1u);
                 mma::mma_tf32(tbase + dcol, dAh, dBh, idesc, 1u);
                 accum = 1u;
             }
-            mma::commit(S.bar + s);
+            mma::commit(S.done + s);
+            SG_MMA_T(t5);
+            SG_MMA_ACC(3, t4 - t3); SG_MMA_ACC(4, t5 - t4);
         }
-        P.pend[s] = true;
+        if (b_img) P.full_par ^= 1u << s;
+        P.done_pend |= 1u << s;
+        SG_MMA_ACC(0, t1 - t0); SG_MMA_ACC(1, t2 - t1); SG_MMA_ACC(2, t3 - t2); SG_MMA_ACC(5, 1);
+        // weight chunk c + NS - 1 goes to the stage chunk c - 1 used
+        if (b_img && c + NS - 1 < nchunks) {
+            const int cn = c + NS - 1;
+            int sn = s0 + cn % NS; if (sn >= NS) sn -= NS;
+            SG_MMA_T(t6);
+            P.wait_done(S.done, sn);
+            SG_MMA_T(t7);
+            SG_MMA_ACC(6, t7 - t6);
+            if (tid == 0) {
+                const int kn0 = cn * KC, kcn = K - kn0 < KC ? K - kn0 : KC;
+                float* Bn = S.stage(sn) + 2 * A.E * kcn;
+                const unsigned int bytes = (unsigned int)(kcn * B.E * 4);
+                mbar_expect_tx(S.full + sn, 2u * bytes);
+                tma_bulk_g2s(Bn, B.img + (size_t)kn0 * B.E, bytes, S.full + sn);
+                tma_bulk_g2s(Bn + B.E * kcn, B.img + B.img_lo + (size_t)kn0 * B.E, bytes, S.full + sn);
+            }
+        }
     }
-    P.wait(S.bar, 0);
-    P.wait(S.bar, 1);
+    P.cur = s0 + nchunks % NS; if (P.cur >= NS) P.cur -= NS;
+    SG_MMA_T(t8);
+#pragma unroll
+    for (int s = 0; s < kMmaMaxStages; ++s) if (s < NS) P.wait_done(S.done, s);
     mma::fence_after_sync();
+    SG_MMA_T(t9);
+    SG_MMA_ACC(7, t9 - t8);
 }
 
 // Epilogue walker: accumulator rows [0, Mi) x columns [0, N) from tmem column dcol; f(m, c0, v) gets 16 consecutive
@@ -298,22 +407,82 @@ __device__ __forceinline__ void mma_colsum(const float4* m4, int MRP, int MR, in
     __syncthreads();
 }
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1): ex2.approx + rcp.approx, absolute error ~1e-7 (the 1e-4 loss contract has room for it;
+// tanhf costs ~5x the instructions and these epilogues sit on the serial path of a job)
+__device__ __forceinline__ float mma_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+
+// weight-gradient epilogues: accumulator row = hidden unit u0 + m -------------------------------------------------------------
+// transposed head gradient: G[k*H + u] for k < NA
+__device__ __forceinline__ void mma_store_dwh(uint32_t tbase, uint32_t dcol, int Mi, int u0, float* __restrict__ gW, int H, int NA, bool acc) {
+    mma_epilogue(tbase, dcol, Mi, 32, [&](int m, int c0, const float (&v)[16]) {
+        const int u = u0 + m;
+        float old[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) old[j] = (acc && c0 + j < NA) ? __ldcg(gW + (size_t)(c0 + j) * H + u) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (c0 + j < NA) __stcg(gW + (size_t)(c0 + j) * H + u, v[j] + old[j]);
+    });
+}
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// G[(u0+m)*ld + c] for c < ncols, N accumulator columns.  acc: add to what an earlier job of this CTA stored -- one
+// fire-and-forget vector reduction per 16 bytes (the slot has a single writer, so the sum stays deterministic) instead of
+// a load-add-store round trip through L2
+__device__ __forceinline__ void mma_store_dw(uint32_t tbase, uint32_t dcol, int Mi, int N, int u0, float* __restrict__ gW, int ld, int ncols,
+                                             bool acc) {
+    const bool vec = (ld & 3) == 0;
+    mma_epilogue(tbase, dcol, Mi, N, [&](int m, int c0, const float (&v)[16]) {
+        float* p = gW + (size_t)(u0 + m) * ld + c0;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (c0 + 4 * j < ncols) {
+                    const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (acc) red_add4(p + 4 * j, o);
+                    else __stcg(reinterpret_cast<float4*>(p) + j, o);
+                }
+        } else {
+            float old[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = (acc && c0 + j < ncols) ? __ldcg(p + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (c0 + j < ncols) __stcg(p + j, v[j] + old[j]);
+        }
+    });
+}
+
+#ifdef SG_MMA_PROFILE
+#define SG_MMA_LAP() do { if (nstage < 16) tstage[nstage++] = clock64(); } while (0)
+#else
+#define SG_MMA_LAP()
+#endif
+
 // ---- one job ------------------------------------------------------------------------------------------------------------------
+// first: no earlier job of this CTA in this optimizer step (gradient accumulators start from zero)
 template <int MR>
 __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaPipe& P, uint32_t tbase, int step, int tile,
-                            int net, float* __restrict__ gout, bool acc) {
+                            int net, float* __restrict__ gout, bool first) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int O = a.O, H = a.H, A = a.A, MRP = d.MRP;
+    const int O = a.O, H = a.H, A = a.A, MRP = d.MRP, NS = d.NS;
     const int epoch = step / a.nmb, mb = step - epoch * a.nmb;
     const int32_t* idx = a.perm + (size_t)epoch * a.S + (size_t)mb * a.mbs;
     const int row0 = a.row_begin + tile * MR;
     const PolicyLayout& L = a.L;
-    const float* W1 = a.params + (net ? L.cw1 : L.aw1);
-    const float* W2 = a.params + (net ? L.cw2 : L.aw2);
-    const float* Wh = a.params + (net ? L.vw : L.mw);
     const int NA = net ? 1 : A;
     const int NA16 = round_up(NA, 16), NA8 = round_up(NA, 8);
-
+    const MmaImg g = make_mma_img(O, H);
+    const float* img = a.wimg + (size_t)(2 * net) * g.net_floats;
+    const int lo = g.net_floats;
+    const bool acc = !first;
+#ifdef SG_MMA_PROFILE
+    long long tstage[16];
+    int nstage = 0;
+    const bool prof = blockIdx.x == 0 && tid == 0 && step == 1;
+#endif
+    SG_MMA_LAP();
     // ---- sampler indices and row scalars (flat sample id = t*N+n, A2C/storage.py:169-185) -------------------------------
     if (tid < MR) {
         const int row = row0 + tid;
@@ -327,55 +496,80 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         S.VALID[tid] = ok ? 1.f : 0.f;
     }
     __syncthreads();
-    // ---- gather the observation rows into the X master: a warp covers 8 rows x 4 granules (64 contiguous bytes per row)
+    // ---- gather observation (and action) rows into the masters: a warp covers 8 rows x 4 granules (64 contiguous bytes
+    //      per row); all loads of a thread are issued before its stores
     {
         const int kq_l = lane & 3, r_l = lane >> 2;
-        const int kgroups = (d.xg + 3) >> 2;
-        const bool vec = (O & 3) == 0;
-        for (int it = warp; it < (MR / 8) * kgroups; it += kStepThreads / 32) {
-            const int rg = it / kgroups, kg = it - rg * kgroups;
-            const int r = 8 * rg + r_l, kq = 4 * kg + kq_l;
-            if (kq < d.xg) {
-                const int i = S.IDX[r];
-                const int k = 4 * kq;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i >= 0 && k < O) {
-                    const float* p = a.obs + (size_t)i * O + k;
-                    if (vec) v = *reinterpret_cast<const float4*>(p);
-                    else {
-                        v.x = p[0];
-                        if (k + 1 < O) v.y = p[1];
-                        if (k + 2 < O) v.z = p[2];
-                        if (k + 3 < O) v.w = p[3];
+        const int xgroups = (d.xg + 3) >> 2, agroups = net == 0 ? (d.ag + 3) >> 2 : 0;
+        const int per_rg = xgroups + agroups;
+        const bool vecx = (O & 3) == 0, veca = (A & 3) == 0;
+        constexpr int GB = 4;
+        const int nit = (MR / 8) * per_rg;
+        for (int it0 = warp; it0 < nit; it0 += GB * (kStepThreads / 32)) {
+            float4 v[GB];
+            float4* dstp[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                const int it = it0 + u * (kStepThreads / 32);
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                dstp[u] = nullptr;
+                if (it < nit) {
+                    const int rg = it / per_rg, kg = it - rg * per_rg;
+                    const int r = 8 * rg + r_l;
+                    const int i = S.IDX[r];
+                    const bool isx = kg < xgroups;
+                    const int kq = 4 * (isx ? kg : kg - xgroups) + kq_l;
+                    const int ncol = isx ? O : A, ngr = isx ? d.xg : d.ag;
+                    if (kq < ngr) {
+                        dstp[u] = (isx ? S.X : S.ACT) + kq * MRP + r;
+                        const int k = 4 * kq;
+                        if (i >= 0 && k < ncol) {
+                            const float* p = (isx ? a.obs : a.actions) + (size_t)i * ncol + k;
+                            if (isx ? vecx : veca) v[u] = *reinterpret_cast<const float4*>(p);
+                            else {
+                                v[u].x = p[0];
+                                if (k + 1 < ncol) v[u].y = p[1];
+                                if (k + 2 < ncol) v[u].z = p[2];
+                                if (k + 3 < ncol) v[u].w = p[3];
+                            }
+                        }
                     }
                 }
-                S.X[kq * MRP + r] = v;
             }
+#pragma unroll
+            for (int u = 0; u < GB; ++u)
+                if (dstp[u]) *dstp[u] = v[u];
         }
     }
     __syncthreads();
+    SG_MMA_LAP();   // 1: gather
 
     // ---- forward (A2C/model.py:255-264) ---------------------------------------------------------------------------------------
-    mma_gemm(S, P, MRP, tbase, 0, MR, H, d.Op8, op_master_k(S.X, MR), op_global_k(W1, H, O, H, O));
+    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, d.Op8, op_master_k(S.X, MR), op_image(img + g.w1k, lo, H, 0), 0u);
+    SG_MMA_LAP();   // 2: G1
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * j;
-            S.H1[(c >> 2) * MRP + r] = make_float4(tanhf(v[4 * j] + S.B1[c]), tanhf(v[4 * j + 1] + S.B1[c + 1]),
-                                                   tanhf(v[4 * j + 2] + S.B1[c + 2]), tanhf(v[4 * j + 3] + S.B1[c + 3]));
+            S.H1[(c >> 2) * MRP + r] = make_float4(mma_tanh(v[4 * j] + S.B1[c]), mma_tanh(v[4 * j + 1] + S.B1[c + 1]),
+                                                   mma_tanh(v[4 * j + 2] + S.B1[c + 2]), mma_tanh(v[4 * j + 3] + S.B1[c + 3]));
         }
     });
-    mma_gemm(S, P, MRP, tbase, 0, MR, H, H, op_master_k(S.H1, MR), op_global_k(W2, H, H, H, H));
+    SG_MMA_LAP();   // 3: E1
+    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, H, op_master_k(S.H1, MR), op_image(img + g.w2k, lo, H, 0), 0u);
+    SG_MMA_LAP();   // 4: G2
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * j;
-            S.H2[(c >> 2) * MRP + r] = make_float4(tanhf(v[4 * j] + S.B2[c]), tanhf(v[4 * j + 1] + S.B2[c + 1]),
-                                                   tanhf(v[4 * j + 2] + S.B2[c + 2]), tanhf(v[4 * j + 3] + S.B2[c + 3]));
+            S.H2[(c >> 2) * MRP + r] = make_float4(mma_tanh(v[4 * j] + S.B2[c]), mma_tanh(v[4 * j + 1] + S.B2[c + 1]),
+                                                   mma_tanh(v[4 * j + 2] + S.B2[c + 2]), mma_tanh(v[4 * j + 3] + S.B2[c + 3]));
         }
     });
+    SG_MMA_LAP();   // 5: E2
     // head: Gaussian mean (A2C/distributions.py:109-110) or critic_linear
-    mma_gemm(S, P, MRP, tbase, 0, MR, NA16, H, op_master_k(S.H2, MR), op_global_k(Wh, NA16, H, NA, H));
+    mma_gemm(S, P, NS, MRP, tbase, 0, MR, NA16, H, op_master_k(S.H2, MR), op_image(img + g.whk, lo, NA16, 0), 0u);
+    SG_MMA_LAP();   // 6: G3
 
     // ---- per-row losses and the gradient seeds (thread = row; warps 0-3) -------------------------------------------------------
     {
@@ -401,18 +595,23 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
             const bool ok = live && S.VALID[r] != 0.f;
             const float invB = 1.f / (float)a.mbs;
             if (net == 0) {
-                const int i = live ? S.IDX[r] : -1;
-                const float* act = a.actions + (size_t)(i >= 0 ? i : 0) * A;
-                // log-prob of the stored action, summed over the action dim (A2C/distributions.py:52-53); v[k] <- a - mu
-                float lp = 0.f;
+                // log-prob of the stored action, summed over the action dim (A2C/distributions.py:52-53); v[k] <- a - mu.
+                // The constant part sum_k(-log sigma_k - log sqrt(2 pi)) sits in LSG[31]; 1/(2 var), 1/var are per-step tables.
+                float lp = S.LSG[31];
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    if (k < A) {
-                        const float sigma = expf(S.LS[k]);
-                        const float var = sigma * sigma;
-                        const float dd = (ok ? act[k] : 0.f) - (v[k] + S.BH[k]);
-                        v[k] = dd;
-                        lp += -(dd * dd) / (2.f * var) - logf(sigma) - SG_LOG_SQRT_2PI;
+                for (int kq = 0; kq < 8; ++kq) {
+                    if (4 * kq < A) {
+                        const float4 av = live ? S.ACT[kq * MRP + r] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float ac[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = 4 * kq + j;
+                            if (k < A) {
+                                const float dd = ac[j] - (v[k] + S.BH[k]);
+                                v[k] = dd;
+                                lp = fmaf(-dd * dd, S.I2VAR[k], lp);
+                            }
+                        }
                     }
                 }
                 float coef = 0.f;
@@ -427,19 +626,20 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
                     const float gsel = s1 < s2 ? 1.f : (s2 < s1 ? inr : 0.5f + 0.5f * inr);
                     coef = -invB * gsel * adv * ratio;
                 }
+                // d logp / d mu = (a-mu)/var -> dHead; d logp / d logstd = (a-mu)^2/var - 1 -> scratch rows (summed over the tile's
+                // rows below by all warps)
+                float4* DL = reinterpret_cast<float4*>(S.stage0);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    float dmu = 0.f, dls = 0.f;
-                    if (k < A) {
-                        const float sigma = expf(S.LS[k]);
-                        const float var = sigma * sigma;
-                        const float dd = v[k];
-                        dmu = ok ? coef * dd / var : 0.f;                 // d logp / d mu     = (a-mu)/var
-                        dls = ok ? coef * (dd * dd / var - 1.f) : 0.f;    // d logp / d logstd = (a-mu)^2/var - 1
-                        dls = warp_sum(dls);
-                        if (lane == 0) S.RED[warp * kMmaRedStride + k] = dls;
+                for (int kq = 0; kq < 8; ++kq) {
+                    float dl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = 4 * kq + j;
+                        const float dd = v[k], iv = k < A ? S.IVAR[k] : 0.f;
+                        v[k] = (ok && k < A) ? coef * dd * iv : 0.f;
+                        dl[j] = (ok && k < A) ? coef * (dd * dd * iv - 1.f) : 0.f;
                     }
-                    v[k] = dmu;
+                    if (live && 4 * kq < A) DL[kq * MRP + r] = make_float4(dl[0], dl[1], dl[2], dl[3]);
                 }
             } else {
                 float dv = 0.f;
@@ -452,8 +652,8 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
                         const float l1 = e1 * e1, l2 = e2 * e2;
                         vl = 0.5f * fmaxf(l1, l2);
                         const float in2 = (diff >= -a.clip && diff <= a.clip) ? 1.f : 0.f;
-                        const float g = l1 > l2 ? e1 : (l2 > l1 ? in2 * e2 : 0.5f * (e1 + in2 * e2));
-                        dv = a.c_v * invB * g;
+                        const float gg = l1 > l2 ? e1 : (l2 > l1 ? in2 * e2 : 0.5f * (e1 + in2 * e2));
+                        dv = a.c_v * invB * gg;
                     } else {
                         const float e1 = ret - val;
                         vl = 0.5f * e1 * e1;
@@ -474,33 +674,26 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         }
         mma::fence_before_sync();
         __syncthreads();
-        if (tid < 34) {
+        if (tid >= 32 && tid < 34) {
             const float s = S.RED[tid] + S.RED[kMmaRedStride + tid] + S.RED[2 * kMmaRedStride + tid] + S.RED[3 * kMmaRedStride + tid];
-            if (tid < 32) { if (net == 0 && tid < A) S.GLS[tid] += s; }
-            else S.LOSS[tid - 32] += s;
+            S.LOSS[tid - 32] += s;
         }
-        mma_colsum(S.DH, MRP, MR, d.dg, S.GBH);
+        if (net == 0) mma_colsum(reinterpret_cast<const float4*>(S.stage0), MRP, MR, d.ag, S.GLS);
+        mma_colsum(S.DH, MRP, MR, net == 0 ? d.ag : 1, S.GBH);
+        mma::fence_async_smem();            // stage 0 was generic scratch; its next writer may be a TMA copy
     }
+    SG_MMA_LAP();   // 7: losses
 
     // ---- backward ------------------------------------------------------------------------------------------------------------------
+    const uint32_t accum = (d.tacc && !first) ? 1u : 0u;
     // head weight gradient, transposed: D(unit, a) = sum_rows H2(row, unit) dHead(row, a)
     for (int b = 0; b < d.nblk; ++b) {
-        mma_gemm(S, P, MRP, tbase, 0, d.Mb, 32, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H), op_master_mn(S.DH, 32, 0, 32));
-        float* gW = gout + (net ? L.vw : L.mw);
-        mma_epilogue(tbase, 0, d.Mb, 32, [&](int m, int c0, const float (&v)[16]) {
-            const int u = b * d.Mb + m;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int k = c0 + j;
-                if (k < NA) {
-                    float* p = gW + (size_t)k * H + u;
-                    __stcg(p, acc ? v[j] + __ldcg(p) : v[j]);
-                }
-            }
-        });
+        mma_gemm(S, P, NS, MRP, tbase, d.tacc ? d.c_dwh : 0, d.Mb, 32, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H), op_master_mn(S.DH, 32, 0, 32), accum);
+        if (!d.tacc) mma_store_dwh(tbase, 0, d.Mb, b * d.Mb, gout + (net ? L.vw : L.mw), H, NA, acc);
     }
+    SG_MMA_LAP();   // 8: G4 + E4
     // dZ2 = (dHead . Wh) * (1 - h2^2), in place over the H2 master
-    mma_gemm(S, P, MRP, tbase, 0, MR, H, NA8, op_master_k(S.DH, MR), op_global_mn(Wh, H, H, H, NA));
+    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, NA8, op_master_k(S.DH, MR), op_image(img + g.whm, lo, H, 1), 0u);
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -511,23 +704,20 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         }
     });
     mma_colsum(S.H2, MRP, MR, d.hg, S.GB2);
-    // dW2(n, k) = sum_rows dZ2(row, n) H1(row, k)
-    for (int b = 0; b < d.nblk; ++b) {
-        mma_gemm(S, P, MRP, tbase, 0, d.Mb, H, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H), op_master_mn(S.H1, H, 0, H));
-        float* gW = gout + (net ? L.cw2 : L.aw2);
-        mma_epilogue(tbase, 0, d.Mb, H, [&](int m, int c0, const float (&v)[16]) {
-            float* p = gW + (size_t)(b * d.Mb + m) * H + c0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                float4* p4 = reinterpret_cast<float4*>(p) + j;
-                if (acc) o = f4_add(o, __ldcg(p4));
-                __stcg(p4, o);
+    SG_MMA_LAP();   // 9: G5 + E5
+    // dW2(n, k) = sum_rows dZ2(row, n) H1(row, k); with two unit blocks the N extent is halved as well (stage capacity)
+    {
+        const int nsplit = d.nblk > 1 ? 2 : 1, Nh = H / nsplit;
+        for (int b = 0; b < d.nblk; ++b)
+            for (int h = 0; h < nsplit; ++h) {
+                mma_gemm(S, P, NS, MRP, tbase, d.tacc ? d.c_dw2 : 0, d.Mb, Nh, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H),
+                         op_master_mn(S.H1, Nh, h * Nh, H), accum);
+                if (!d.tacc) mma_store_dw(tbase, 0, d.Mb, Nh, b * d.Mb, gout + (net ? L.cw2 : L.aw2) + h * Nh, H, Nh, acc);
             }
-        });
     }
+    SG_MMA_LAP();   // 10: G6 + E6
     // dZ1 = (dZ2 . W2) * (1 - h1^2), in place over the H1 master
-    mma_gemm(S, P, MRP, tbase, 0, MR, H, H, op_master_k(S.H2, MR), op_global_mn(W2, H, H, H, H));
+    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, H, op_master_k(S.H2, MR), op_image(img + g.w2m, lo, H, 1), 0u);
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -538,30 +728,22 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         }
     });
     mma_colsum(S.H1, MRP, MR, d.hg, S.GB1);
+    SG_MMA_LAP();   // 11: G7 + E7
     // dW1(n, k) = sum_rows dZ1(row, n) X(row, k)
     for (int b = 0; b < d.nblk; ++b) {
-        mma_gemm(S, P, MRP, tbase, 0, d.Mb, d.Op32, MR, op_master_mn(S.H1, d.Mb, b * d.Mb, H), op_master_mn(S.X, d.Op32, 0, d.Op8));
-        float* gW = gout + (net ? L.cw1 : L.aw1);
-        const bool vec = (O & 3) == 0;
-        mma_epilogue(tbase, 0, d.Mb, d.Op32, [&](int m, int c0, const float (&v)[16]) {
-            float* p = gW + (size_t)(b * d.Mb + m) * O + c0;
-            if (vec) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (c0 + 4 * j < O) {
-                        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        float4* p4 = reinterpret_cast<float4*>(p) + j;
-                        if (acc) o = f4_add(o, __ldcg(p4));
-                        __stcg(p4, o);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (c0 + j < O) __stcg(p + j, acc ? v[j] + __ldcg(p + j) : v[j]);
-            }
-        });
+        mma_gemm(S, P, NS, MRP, tbase, d.tacc ? d.c_dw1 : 0, d.Mb, d.Op32, MR, op_master_mn(S.H1, d.Mb, b * d.Mb, H),
+                 op_master_mn(S.X, d.Op32, 0, d.Op8), accum);
+        if (!d.tacc) mma_store_dw(tbase, 0, d.Mb, d.Op32, b * d.Mb, gout + (net ? L.cw1 : L.aw1), O, O, acc);
     }
+    SG_MMA_LAP();   // 12: G8 + E8
+#ifdef SG_MMA_PROFILE
+    if (prof) {
+        printf("job tile %d net %d first %d cycles:", tile, net, (int)first);
+        for (int i = 1; i < nstage; ++i) printf(" %lld", tstage[i] - tstage[i - 1]);
+        printf("\n  gemm totals so far: chunks %lld | wait_done %lld fill %lld sync %lld | t0: wait_full %lld issue %lld | wait_prefetch %lld drain %lld\n",
+               P.prof[5], P.prof[0], P.prof[1], P.prof[2], P.prof[3], P.prof[4], P.prof[6], P.prof[7]);
+    }
+#endif
 }
 
 // ---- phase A of one optimizer step -------------------------------------------------------------------------------------------
@@ -581,16 +763,28 @@ __device__ void ppo_phaseA_mma(const PpoArgs& a, const MmaDims& d, MmaSmem& S, M
     }
     if (tid < 32) {
         S.BH[tid] = tid < NA ? ld_cg(a.params + (net ? L.vb : L.mb) + tid) : 0.f;
-        S.LS[tid] = tid < A ? ld_cg(a.params + L.ls + tid) : 0.f;
+        const float ls = tid < A ? ld_cg(a.params + L.ls + tid) : 0.f;
+        const float sigma = expf(ls), var = sigma * sigma;
+        S.LS[tid] = ls; S.IVAR[tid] = 1.f / var; S.I2VAR[tid] = 1.f / (2.f * var);
+        // LSG[31] = sum_k (-log sigma_k - log sqrt(2 pi)) in the order the per-element form adds them
+        float c = tid < A ? -logf(sigma) - SG_LOG_SQRT_2PI : 0.f;
+        c = warp_sum(c);
+        S.LSG[tid] = c;
         S.GBH[tid] = 0.f; S.GLS[tid] = 0.f;
         if (tid < 4) S.LOSS[tid] = 0.f;
     }
     __syncthreads();
     float* gout = a.gpart + (size_t)cta * a.P;
-    bool acc = false;
+    bool first = true;
     for (int job = cta; job < njobs; job += ncta) {
-        ppo_mma_job<MR>(a, d, S, P, tbase, step, job >> 1, net, gout, acc);
-        acc = true;
+        ppo_mma_job<MR>(a, d, S, P, tbase, step, job >> 1, net, gout, first);
+        first = false;
+    }
+    if (d.tacc) {
+        // the CTA's weight gradients of this step, accumulated in tensor memory over its jobs
+        mma_store_dwh(tbase, d.c_dwh, d.Mb, 0, gout + (net ? L.vw : L.mw), H, NA, false);
+        mma_store_dw(tbase, d.c_dw2, d.Mb, H, 0, gout + (net ? L.cw2 : L.aw2), H, H, false);
+        mma_store_dw(tbase, d.c_dw1, d.Mb, d.Op32, 0, gout + (net ? L.cw1 : L.aw1), a.O, a.O, false);
     }
     for (int i = tid; i < H; i += kStepThreads) {
         __stcg(gout + (net ? L.cb1 : L.ab1) + i, S.GB1[i]);
