@@ -36,6 +36,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_EXPERT = os.path.join(ROOT, "tests", "golden", "hopper_expert_sas_f32.npy")
+GOLDEN_EXPERT_LAIKA = os.path.join(ROOT, "tests", "golden", "laika_expert_sas_f32.npy")
 
 # name -> sizes (SURVEY.md section 8 per-config table).  cfg2 is the configuration the metric is quoted on.
 CONFIGS = {
@@ -43,9 +44,9 @@ CONFIGS = {
                  label="HopperCombinedEnv-v1 sizes num_processes=4 num_steps=128 hidden=64"),
     "cfg2": dict(T=2048, N=16, O=14, A=7, H=64, F=25, HD=100, expert="hopper", ep_len=88.0,
                  label="HopperCombinedEnv-v1 sizes num_processes=16 num_steps=2048 hidden=64 (BASELINE configs[1])"),
-    "cfg3": dict(T=2048, N=16, O=64, A=28, H=256, F=86, HD=100, expert=15678, ep_len=78.0,
+    "cfg3": dict(T=2048, N=16, O=64, A=28, H=256, F=86, HD=100, expert="laika", ep_len=78.0,
                  label="LaikagoCombinedEnv-v1 sizes num_processes=16 num_steps=2048 hidden=256"),
-    "cfg4": dict(T=2048, N=128, O=64, A=28, H=256, F=86, HD=100, expert=15678, ep_len=78.0,
+    "cfg4": dict(T=2048, N=128, O=64, A=28, H=256, F=86, HD=100, expert="laika", ep_len=78.0,
                  label="LaikagoCombinedEnv-v1 sizes num_processes=128 num_steps=2048 hidden=256"),
     "cfg5": dict(T=1024, N=4096, O=111, A=12, H=64, F=86, HD=100, expert=16384, ep_len=78.0,
                  label="synthetic rollout 1024x4096 obs_dim=111"),
@@ -72,6 +73,8 @@ Box.__name__ = "Box"
 def expert_rows(c, seed):
     if c["expert"] == "hopper":
         return torch.from_numpy(np.load(GOLDEN_EXPERT))          # real hopper_new11_deform_n200_3.pkl rows (17555,25)
+    if c["expert"] == "laika":
+        return torch.from_numpy(np.load(GOLDEN_EXPERT_LAIKA))    # real laika_70_deform_n200_0.pkl rows (15678,86)
     g = torch.Generator().manual_seed(7000 + seed)
     return torch.randn(int(c["expert"]), c["F"], generator=g)
 
@@ -142,7 +145,8 @@ class Workload(object):
         self.n_disc_batches = min(len(expert) // h["gail_batch"], self.S // h["gail_batch"])
         self.opt_steps = h["ppo_epoch"] * h["num_mini_batch"] + h["gail_epoch"] * self.n_disc_batches
         if dp:
-            sg_dist.attach(ppo=self.agent, disc=self.disc)
+            # "auto": shard an update only where that shortens its critical path (dist.DataParallel); SIMGAN_DP=always forces it
+            sg_dist.attach(ppo=self.agent, disc=self.disc, policy=os.environ.get("SIMGAN_DP", "auto"))
 
         host, noise = host_rollout(c, seed, expert)
         # policy-produced fields (one batched act() over obs[:-1], as HOT LOOP A would have)
@@ -165,8 +169,11 @@ class Workload(object):
         for k, v in self.host.items():
             getattr(r, k).copy_(v, non_blocking=True)
 
-    def update_phase(self, from_host):
-        """One outer-iteration update phase through the public classes; returns the 6 loss floats."""
+    def update_phase(self, from_host, dropin_relabel=False):
+        """One outer-iteration update phase through the public classes; returns the 6 loss floats.
+        ``dropin_relabel``: run the reward relabel exactly as the unmodified caller does (main_gail_dyn_ppo.py:275-297:
+        T x predict_reward_combined + host RunningMeanStd + clip, three host syncs per step) instead of the fused
+        ``relabel_rollout`` entry point."""
         h, r = HYPER, self.rollouts
         if from_host:
             self.upload()
@@ -176,11 +183,22 @@ class Workload(object):
             dl = self.disc.update_gail_dyn(self.loader, r)
         from simgan_b200.algo.gail import alive_bonus_offset
         r_sa = alive_bonus_offset(r.masks, self.c["T"], self.c["N"], h["gail_tar_length"])
-        self.disc.relabel_rollout(r, h["gamma"], -r_sa, self.ret_rms)
+        if dropin_relabel:
+            gail_rewards = []
+            for step in range(self.c["T"]):
+                r.rewards[step], returns = self.disc.predict_reward_combined(r.obs_feat[step + 1], h["gamma"], r.masks[step],
+                                                                             offset=-r_sa)
+                self.ret_rms.update(returns.view(-1).cpu().numpy())
+                rews = r.rewards[step].view(-1).cpu().numpy()
+                rews = np.clip(rews / np.sqrt(self.ret_rms.var + 1e-7), -10.0, 10.0)
+                r.rewards[step] = torch.Tensor(rews).view(-1, 1)
+                gail_rewards.append(torch.mean(returns).cpu().data)
+        else:
+            self.disc.relabel_rollout(r, h["gamma"], -r_sa, self.ret_rms)
         r.compute_returns(next_value, True, h["gamma"], h["gae_lambda"], True)
         pl = self.agent.update(r)
         r.after_update()
-        return tuple(dl) + tuple(pl)
+        return tuple(float(x) for x in dl) + tuple(pl)
 
 
 def fake_env_collection(w):
@@ -307,7 +325,7 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, from_host, with_timer):
+    def timed(n, from_host, with_timer, dropin_relabel=False):
         """Sum of per-step device times (ms) over n steps; L2 flushed between steps outside the events."""
         total = 0.0
         _lib.timer.enabled = with_timer
@@ -319,7 +337,7 @@ def run_cuda(args):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             s.record()
-            losses = w.update_phase(from_host)
+            losses = w.update_phase(from_host, dropin_relabel)
             e.record()
             torch.cuda.synchronize()
             total += s.elapsed_time(e)
@@ -340,12 +358,18 @@ def run_cuda(args):
     # ---- timed region 1: buffer resident in HBM --------------------------------------------------------
     cp, cf = sample_clocks_start() if rank == 0 else (None, None)
     l0 = lib.sg_launch_count()
-    ms_total, wall, kt, losses = timed(args.steps, False, True)
+    ms_total, wall, _, losses = timed(args.steps, False, False)            # per-kernel event timer OFF for the headline
     launches = lib.sg_launch_count() - l0
     clocks = sample_clocks_stop(cp, cf, local_rank) if rank == 0 else {}
     # ---- timed region 2: end to end from pinned host buffers ------------------------------------------
     w.update_phase(True)
     ms_e2e, _, _, _ = timed(args.steps, True, False)
+    # ---- separate pass with the per-kernel event timer on: kernel shares / durations for the roofline ----------------
+    n_kt = max(3, args.steps // 4)
+    ms_kt, _, kt, _ = timed(n_kt, False, True)
+    # ---- the update phase as an UNMODIFIED caller runs it (per-step predict_reward_combined relabel loop) ---------
+    n_di = max(2, min(args.steps, 5))
+    ms_dropin, _, _, _ = timed(n_di, True, False, dropin_relabel=True)
 
     if rank != 0:
         if world > 1:
@@ -364,48 +388,62 @@ def run_cuda(args):
     work = algorithmic_work(c, w.n_disc_batches)
     kernels = {}
     for name, arr in kt.items():
-        kernels[name] = dict(launches_per_step=len(arr) / args.steps, ms_per_launch=float(np.mean(arr)),
-                             ms_per_step=float(np.sum(arr)) / args.steps)
-    # dominant kernel = largest share of the step
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
-    roof = None
-    if dom is not None:
-        per_launch = {"ppo_update": (work["ppo_flops"], work["ppo_bytes"], HYPER["ppo_epoch"]),     # one launch per epoch
-                      "disc_update": (work["disc_flops"], work["disc_bytes"], HYPER["gail_epoch"]),
-                      "disc_relabel": (work["relabel_flops"], work["relabel_bytes"], 1),
-                      "compute_returns": (0, work["gae_bytes"], 1)}[dom]
-        fl, by, nl = per_launch
-        t_s = kernels[dom]["ms_per_launch"] * 1e-3
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr_path):
-            traffic = json.load(open(tr_path)).get(args.config, {}).get(dom)
-        if dom == "compute_returns":
+        kernels[name] = dict(launches_per_step=len(arr) / n_kt, ms_per_launch=float(np.mean(arr)),
+                             ms_per_step=float(np.sum(arr)) / n_kt)
+    ms_per_step_kt = ms_kt / n_kt
+    # ---- roofline of EVERY kernel; the dominant one (largest share of the step) is the record's ``roofline`` ---------
+    sm_mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    sms = int(lib.sg_device_sm_count()) or 148
+    fma_peak = sms * 128 * 2 * sm_mhz * 1e6 / 1e12
+    tf32_peak = tc_peak / 2.0                   # kind::tf32 issues at half the bf16 rate; 3xTF32 spends 3 MMAs per product
+    ppo_on_tensor_cores = bool(getattr(w.agent, "last_kernel", "") == "tensor")
+    per_launch = {"ppo_update": (work["ppo_flops"], work["ppo_bytes"], HYPER["ppo_epoch"], HYPER["num_mini_batch"]),
+                  "disc_update": (work["disc_flops"], work["disc_bytes"], HYPER["gail_epoch"], w.n_disc_batches),
+                  "disc_relabel": (work["relabel_flops"], work["relabel_bytes"], 1, 1),
+                  "compute_returns": (0, work["gae_bytes"], 1, 1)}
+    traffic_all = {}
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic_all = json.load(open(tr_path)).get(args.config, {})
+    roofs = {}
+    for name, kd in kernels.items():
+        if name not in per_launch:
+            continue
+        fl, by, nl, steps_in_launch = per_launch[name]
+        fl, by = fl / world, by / world             # data parallel: a rank processes 1/world of every minibatch
+        t_s = kd["ms_per_launch"] * 1e-3
+        if name == "compute_returns":
             ach = by / nl / t_s / 1e9
-            roof = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak, traffic=traffic)
+            r = dict(bound="hbm", achieved=ach, peak=hbm_peak, unit="GB/s", frac=ach / hbm_peak,
+                     engine="streaming scan (cp.async ring, one serial recurrence per env column)")
         else:
             ach = fl / nl / t_s / 1e12
-            roof = dict(bound="tensor", achieved=ach, peak=tc_peak, unit="TFLOP/s", frac=ach / tc_peak, traffic=traffic,
-                        hbm_achieved_gbs=by / nl / t_s / 1e9, hbm_peak_gbs=hbm_peak)
-        steps_in_launch = {"ppo_update": HYPER["num_mini_batch"], "disc_update": w.n_disc_batches,
-                           "disc_relabel": 1, "compute_returns": 1}[dom]
-        roof.update(kernel=dom, peak_source=peak_src, share_of_step=kernels[dom]["ms_per_step"] / ms_per_step,
-                    algorithmic_bytes_per_launch=by / nl, algorithmic_flops_per_launch=fl / nl,
-                    us_per_optimizer_step=1e3 * kernels[dom]["ms_per_launch"] / steps_in_launch,
-                    note="fp32 FMA kernel on a serial chain of optimizer steps (grid barriers between phases): "
-                         "latency-bound, neither roofline binds at this size")
-        # what does bind (SURVEY.md 8d caveat): the CUDA-core fp32 peak the arithmetic actually runs against, and the
-        # serial-step floor = grid barriers + weight refresh that every one of the dependent steps has to pay
-        sm_mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0)
-        sms = int(lib.sg_device_sm_count()) or 148
-        fma_peak = sms * 128 * 2 * sm_mhz * 1e6 / 1e12
-        if roof.get("unit") == "TFLOP/s":
-            roof.update(fp32_fma_peak_tflops=fma_peak, frac_of_fp32_fma_peak=roof["achieved"] / fma_peak)
+            on_tc = name == "ppo_update" and ppo_on_tensor_cores
+            r = dict(bound="tensor", achieved=ach, peak=tc_peak, unit="TFLOP/s", frac=ach / tc_peak,
+                     hbm_achieved_gbs=by / nl / t_s / 1e9, hbm_peak_gbs=hbm_peak, hbm_frac=by / nl / t_s / 1e9 / hbm_peak,
+                     engine=("tcgen05 kind::tf32, 3xTF32 operand splitting (3 MMAs per fp32 product), accumulators in TMEM"
+                             if on_tc else "fp32 FMA on CUDA cores (no tensor instruction issued), latency-bound serial chain"),
+                     fp32_fma_peak_tflops=fma_peak, frac_of_fp32_fma_peak=ach / fma_peak)
+            if on_tc:
+                r.update(tf32_3x_peak_tflops=tf32_peak / 3.0, frac_of_3xtf32_peak=ach / (tf32_peak / 3.0))
+        r.update(kernel=name, peak_source=peak_src, traffic=traffic_all.get(name),
+                 share_of_step=kd["ms_per_step"] / ms_per_step_kt,
+                 algorithmic_bytes_per_launch=by / nl, algorithmic_flops_per_launch=fl / nl,
+                 us_per_optimizer_step=1e3 * kd["ms_per_launch"] / steps_in_launch)
+        roofs[name] = r
+    dom = max(roofs, key=lambda k: kernels[k]["ms_per_step"]) if roofs else None
+    roof = None
+    if dom is not None:
+        roof = dict(roofs[dom])
+        roof["note"] = ("the bound key keeps the contract's vocabulary; what the arithmetic runs on is in `engine`. "
+                        "One outer iteration is a serial chain of dependent optimizer steps (grid barriers between phases): "
+                        "at cfg1-3 neither roofline binds, see serial_chain")
         try:
             if dom in ("disc_update", "ppo_update") and not c.get("split"):
                 ph = dict(zip(["image", "tile", "bar1", "reduce_adam", "bar2"], w.disc.phase_cycles())) if dom == "disc_update" else \
                     dict(zip(["image", "tile", "bar1", "reduce_ssq", "bar2", "clip_adam", "bar3"], w.agent.phase_cycles()))
                 sync = sum(v for k, v in ph.items() if k.startswith("bar") or k == "image")
+                steps_in_launch = per_launch[dom][3]
                 roof["serial_chain"] = dict(steps_per_launch=steps_in_launch,
                                             us_sync_and_refresh_per_step=sync / steps_in_launch / sm_mhz,
                                             us_tile_phase_per_step=ph["tile"] / steps_in_launch / sm_mhz)
@@ -416,13 +454,20 @@ def run_cuda(args):
         "unit": "optimizer steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic rollout (seeded N(0,1) obs, expert-resampled obs_feat) + "
-                                + ("real Hopper expert rows (tests/golden fixture)" if c["expert"] == "hopper" else "N(0,1) expert rows"),
+                                + ({"hopper": "real Hopper expert rows (hopper_new11_deform_n200_3.pkl, tests/golden fixture)",
+                                   "laika": "real Laikago expert rows (laika_70_deform_n200_0.pkl, tests/golden fixture)"}.get(
+                                       c["expert"], "N(0,1) expert rows")),
         "config": {"workload": c["label"], "name": args.config, "T": c["T"], "N": c["N"], "obs_dim": c["O"], "act_dim": c["A"],
                    "hidden": c["H"], "feat_dim": c["F"], "disc_hidden": c["HD"], "ppo_epoch": HYPER["ppo_epoch"],
                    "num_mini_batch": HYPER["num_mini_batch"], "gail_epoch": HYPER["gail_epoch"],
                    "gail_batch": HYPER["gail_batch"], "optimizer_steps_per_step": w.opt_steps,
                    "parallelism": "single GPU" if world == 1 else
-                   "minibatch data-parallel dp%d, 1 gradient exchange/step (%s)" % (world, w.agent.dp.transport if w.agent.dp else "-"),
+                   "dp%d (%s policy): PPO update %s, discriminator update %s; gradient exchange inside the step kernel over NVLink peer "
+                   "memory (%s transport)" % (world, w.agent.dp.policy,
+                                              "sharded by minibatch rows" if getattr(w.agent, "last_sharded", False) else
+                                              "replicated (its tiles already run concurrently on one GPU)",
+                                              "sharded" if w.disc.__dict__.get("last_sharded") else
+                                              "replicated (128 row triples = 128 tiles <= SMs)", w.agent.dp.transport),
                    "l2": "flushed between timed steps (256 MiB write)", "timing": "cuda events per step, max over ranks"},
         "iters_per_s": args.steps / (ms_total * 1e-3),
         "samples_per_s": HYPER["ppo_epoch"] * w.S * args.steps / (ms_total * 1e-3),
@@ -432,7 +477,12 @@ def run_cuda(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "env_steps": env_steps,
-        "kernels": kernels, "roofline": roof, "clocks": clocks,
+        "kernels": kernels, "roofline": roof, "roofline_all": roofs, "clocks": clocks,
+        "update_phase_dropin": {"value": w.opt_steps * n_di / (ms_dropin * 1e-3), "unit": "optimizer steps/s",
+                                "ms_per_step": ms_dropin / n_di, "steps_timed": n_di,
+                                "note": "same update phase from pinned host buffers, reward relabel through the UNMODIFIED caller loop "
+                                        "(main_gail_dyn_ppo.py:275-297: T x predict_reward_combined + host RunningMeanStd, 3 host syncs "
+                                        "per step); `e2e` uses the fused relabel_rollout entry point instead"},
         "losses_last_step": [float(x) for x in losses],
         "phase_cycles_last_launch": {"ppo": dict(zip(["image", "tile", "bar1", "reduce_ssq", "bar2", "clip_adam", "bar3"],
                                                      w.agent.phase_cycles())),
@@ -498,20 +548,88 @@ def reference_sample(c, seed, threads):
     return one, steps
 
 
+def reference_sample_real(c, seed, threads):
+    """The same bounded sample as ``reference_sample`` driven through the UNMODIFIED reference modules
+    (third_party/a2c_ppo_acktr/{model,storage,algo/ppo,algo/gail}.py imported through oracle/ref_shim.py).  Only possible
+    where a reference tree is mounted (the dev container; never the GPU box)."""
+    from oracle import ref_shim
+    from torch.utils.data import DataLoader, TensorDataset
+    ref = ref_shim.load()
+    h = HYPER
+    torch.set_num_threads(threads)
+    torch.manual_seed(seed)
+    T, N, O, A, H, F, HD = c["T"], c["N"], c["O"], c["A"], c["H"], c["F"], c["HD"]
+    space = ref_shim.BoxSpace(A)
+    if c.get("split"):
+        pol = ref.model_split.SplitPolicy((O,), space, base_kwargs={"hidden_size": H, "num_feet": A // 7})
+    else:
+        pol = ref.model.Policy((O,), space, base_kwargs={"recurrent": False, "hidden_size": H})
+    agent = ref.ppo.PPO(pol, h["clip_param"], 2, h["num_mini_batch"], h["value_loss_coef"], h["entropy_coef"], lr=h["lr"],
+                        eps=h["eps"], max_grad_norm=h["max_grad_norm"])
+    expert = expert_rows(c, seed)
+    loader = DataLoader(TensorDataset(expert), batch_size=h["gail_batch"], shuffle=True, drop_last=len(expert) > h["gail_batch"])
+    disc = ref.gail.Discriminator(F, HD, torch.device("cpu"))
+    rollouts = ref.storage.RolloutStorage(T, N, (O,), space, pol.recurrent_hidden_state_size, F)
+    host, _ = host_rollout(c, seed, expert)
+    for k, v in host.items():
+        getattr(rollouts, k).copy_(v)
+    with torch.no_grad():
+        value, action, logp, _ = pol.act(rollouts.obs[:-1].reshape(T * N, O), rollouts.recurrent_hidden_states[:-1].reshape(T * N, -1),
+                                         rollouts.masks[:-1].reshape(T * N, 1))
+    rollouts.value_preds[:-1].copy_(value.view(T, N, 1))
+    rollouts.actions.copy_(action.view(T, N, A))
+    rollouts.action_log_probs.copy_(logp.view(T, N, 1))
+    ret_rms = ref.rms.RunningMeanStd(shape=())
+    n_db = min(len(expert) // h["gail_batch"], T * N // h["gail_batch"])
+    steps = n_db + 2 * h["num_mini_batch"]
+
+    def one():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            next_value = pol.get_value(rollouts.obs[-1], rollouts.recurrent_hidden_states[-1], rollouts.masks[-1]).detach()
+        disc.update_gail_dyn(loader, rollouts)
+        t1 = time.perf_counter()
+        n_done = (1.0 - rollouts.masks).sum().cpu().numpy() + N / 2              # main_gail_dyn_ppo.py:258-271
+        d_sa = 1 - n_done / (n_done + (T * N) / h["gail_tar_length"])
+        r_sa = np.log(d_sa) - np.log(1 - d_sa)
+        for step in range(T):                                                    # main_gail_dyn_ppo.py:275-297
+            rollouts.rewards[step], returns = disc.predict_reward_combined(rollouts.obs_feat[step + 1], h["gamma"],
+                                                                           rollouts.masks[step], offset=-r_sa)
+            ret_rms.update(returns.view(-1).cpu().numpy())
+            rews = rollouts.rewards[step].view(-1).cpu().numpy()
+            rews = np.clip(rews / np.sqrt(ret_rms.var + 1e-7), -10.0, 10.0)
+            rollouts.rewards[step] = torch.Tensor(rews).view(-1, 1)
+        rollouts.compute_returns(next_value, True, h["gamma"], h["gae_lambda"], True)
+        t2 = time.perf_counter()
+        agent.update(rollouts)
+        t3 = time.perf_counter()
+        return (t1 - t0) + (t2 - t1) / 5.0 + (t3 - t2), dict(disc=t1 - t0, relabel_gae=t2 - t1, ppo=t3 - t2)
+
+    return one, steps
+
+
 def run_reference(args, quiet=False, budget_s=None):
     c = CONFIGS[args.config]
     ncores = os.cpu_count() or 1
+    kind = "port"
+    sampler = reference_sample
+    try:
+        from oracle import ref_shim
+        if ref_shim.available() and os.environ.get("SIMGAN_BENCH_PORT", "0") != "1":
+            kind, sampler = "reference", reference_sample_real
+    except Exception:
+        pass
     # the reference itself runs with one intra-op thread (main_gail_dyn_ppo.py:64); try all cores too and
     # keep whichever is faster for this workload
     best = None
     for threads in sorted({1, ncores}):
-        one, steps = reference_sample(c, args.seed, threads)
+        one, steps = sampler(c, args.seed, threads)
         one()                             # warm-up
         t = min(one()[0], one()[0])       # probe
         if best is None or t < best[0]:
             best = (t, threads)
     threads = best[1]
-    one, steps = reference_sample(c, args.seed, threads)
+    one, steps = sampler(c, args.seed, threads)
     n_warm = 1 if quiet else max(1, min(args.warmup, 3))
     n_steps = args.steps
     if budget_s is not None:
@@ -526,8 +644,10 @@ def run_reference(args, quiet=False, budget_s=None):
     value = steps * n_steps / tot
     sample = ("1/5 outer iteration per step (1 of 5 D epochs + relabel + GAE + 2 of 10 PPO epochs = %d optimizer steps; "
               "relabel+GAE time scaled by 1/5), %d steps timed, torch CPU eager, %d intra-op thread(s) "
-              "(faster of 1 and %d)" % (steps, n_steps, threads, ncores))
-    cpu = {"value": value, "unit": "optimizer steps/s", "cores": threads, "kind": "port", "sample": sample,
+              "(faster of 1 and %d); %s" % (steps, n_steps, threads, ncores,
+                                           "the reference's own modules imported through oracle/ref_shim.py" if kind == "reference"
+                                           else "oracle port (no reference tree on this box)"))
+    cpu = {"value": value, "unit": "optimizer steps/s", "cores": threads, "kind": kind, "sample": sample,
            "host_cores": ncores, "s_per_sample": tot / n_steps,
            "phase_s": {k: float(np.mean([p[k] for p in parts])) for k in parts[0]}}
     if quiet:

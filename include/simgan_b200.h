@@ -132,6 +132,9 @@ int64_t sg_ppo_workspace_bytes(const sg_ppo_config* cfg);
  * launch: int64 [n_ctas][8] with slots {param image, tile phase, barrier 1, reduce+ssq, barrier 2, clip+Adam,
  * barrier 3, -}; n_ctas = min(#tiles, #SMs). */
 int64_t sg_ppo_phase_cycles_offset(const sg_ppo_config* cfg);
+/* Diagnostics: 1 when sg_ppo_update will run this configuration on the tensor cores (mode 4, or mode 0 with a minibatch
+ * shard large enough to fill the SMs with 64/128-row jobs), 0 for the CUDA-core tiles, -1 on an invalid configuration. */
+int sg_ppo_uses_tensor_cores(const sg_ppo_config* cfg);
 
 /* PPO.update (A2C/algo/ppo.py:65-157) for cfg->ppo_epoch epochs.
  *   params/adam_m/adam_v : flat policy vectors (updated in place)

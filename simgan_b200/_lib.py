@@ -59,6 +59,7 @@ SIGNATURES = {
     "sg_rollout_feed": (C.c_int, [c_void] + [C.c_int] * 7 + [c_void] * 13),
     "sg_ppo_workspace_bytes": (C.c_int64, [C.POINTER(PpoConfig)]),
     "sg_ppo_phase_cycles_offset": (C.c_int64, [C.POINTER(PpoConfig)]),
+    "sg_ppo_uses_tensor_cores": (C.c_int, [C.POINTER(PpoConfig)]),
     "sg_ppo_update": (C.c_int, [C.POINTER(PpoConfig)] + [c_void] * 14 + [ALLREDUCE_FN, c_void, c_void]),
     "sg_split_layout": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "sg_split_forward": (C.c_int, [c_void, C.c_int, C.c_int, C.c_int, c_void, C.c_int, c_void, c_void, c_void, c_void,

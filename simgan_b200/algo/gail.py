@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _lib, _spec
+from .. import _lazy, _lib, _spec
 from ..running_mean_std import RunningMeanStd
 from .adam import FusedAdam
 
@@ -36,8 +36,19 @@ class Discriminator(nn.Module):
         self.ret_rms = RunningMeanStd(shape=())
         self.kernel_mode = 0
         self.dp = None
-        self.last_trace = None
+        self.lazy_losses = True          # update_gail_dyn returns LazyFloat scalars (no blocking read-back per call)
+        self.__dict__["_pending"] = None
         self.__dict__["_ws"] = None
+
+    @property
+    def last_trace(self):
+        """(n_steps, 3) per-step {loss, expert_loss, policy_loss} of the last update call (host tensor)."""
+        pend = self.__dict__.get("_pending")
+        return None if pend is None else pend.trace()
+
+    @last_trace.setter
+    def last_trace(self, value):
+        self.__dict__["_pending"] = None if value is None else _lazy.HostTrace(value)
 
     # ---- flat parameter buffer ---------------------------------------------------------------------------
     @property
@@ -79,7 +90,8 @@ class Discriminator(nn.Module):
         state.pop("_flat", None)
         state["_ws"] = None
         state["dp"] = None
-        state["last_trace"] = None
+        state["_pending"] = None
+        state.pop("last_trace", None)
         state.pop("_prof_view", None)
         state.pop("_rms_dev", None)
         state.pop("_predraw", None)
@@ -95,7 +107,9 @@ class Discriminator(nn.Module):
         d = self.__dict__
         d.setdefault("kernel_mode", 0)
         d.setdefault("dp", None)
-        d.setdefault("last_trace", None)
+        d.pop("last_trace", None)
+        d.setdefault("_pending", None)
+        d.setdefault("lazy_losses", True)
         d.setdefault("_ws", None)
         d.setdefault("returns", None)
         if "ret_rms" not in d:
@@ -213,12 +227,14 @@ class Discriminator(nn.Module):
         cfg.gp_lambda = 10.0
         cfg.beta1, cfg.beta2, cfg.adam_eps = g["betas"][0], g["betas"][1], g["eps"]
         cfg.first_adam_step = opt.step_count + 1
-        cfg.row_begin, cfg.row_end = (0, B) if self.dp is None else self.dp.shard(B)
-        p2p = self.dp is not None and self.dp.p2p_ok(B)
-        cfg.mode = self.kernel_mode if (self.dp is None or p2p) else 1
+        dp = self.dp if (self.dp is not None and self.dp.shards(B, 1)) else None        # "auto": replicate small batches
+        self.__dict__["last_sharded"] = dp is not None
+        cfg.row_begin, cfg.row_end = (0, B) if dp is None else dp.shard(B)
+        p2p = dp is not None and dp.p2p_ok(B)
+        cfg.mode = self.kernel_mode if (dp is None or p2p) else 1
         if cfg.mode == 1 and p2p:
             cfg.mode = 0
-        cfg.dp_ctx = self.dp.context("disc", flat.numel()) if p2p else None
+        cfg.dp_ctx = dp.context("disc", flat.numel()) if p2p else None
         lib = _lib.lib()
         need = lib.sg_disc_workspace_bytes(C.byref(cfg))
         if need < 0:
@@ -243,8 +259,8 @@ class Discriminator(nn.Module):
         sched = stage_dev[3 * nb:].view(torch.float32).view(2, n)
         trace = torch.empty(n, 3, device=dev)
         cb, user = _lib.NULL_ALLREDUCE, None
-        if self.dp is not None and not p2p:
-            cb = self.dp.make_callback(ws)
+        if dp is not None and not p2p:
+            cb = dp.make_callback(ws)
         tok = _lib.timer.start("disc_update")
         rc = lib.sg_disc_update(C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(expert),
                                 _lib.ptr(policy_feat), _lib.ptr(idx_dev[0]), _lib.ptr(idx_dev[1]), _lib.ptr(alpha_dev),
@@ -255,18 +271,18 @@ class Discriminator(nn.Module):
         opt.step_count += n
         self.__dict__["_prof_view"] = (ws, int(lib.sg_disc_phase_cycles_offset(C.byref(cfg))))
         if p2p:
-            self.dp.sum_trace_(trace, 3)      # all three loss columns are per-rank partial sums
+            dp.sum_trace_(trace, 3)           # all three loss columns are per-rank partial sums
+        # an earlier call whose trace has landed by now is checked here (non-finite losses raise), without waiting
+        prev = self.__dict__.get("_pending")
+        if prev is not None and prev.done():
+            prev.means()
+        pend = _lazy.PendingTrace(trace, 3, lambda msg: _lib.SgError("sg_disc_update: " + msg))
+        self.__dict__["_pending"] = pend
         _spec.host_idle()                     # the next consumer of the CPU generator draws while the GPU runs this epoch
-        tr = _lib.read_back(trace)
-        self.last_trace = tr
-        lt = le = lp = 0.0
-        for row in tr.tolist():
-            lt += row[0]
-            le += row[1]
-            lp += row[2]
-        if not (math.isfinite(lt) and math.isfinite(le) and math.isfinite(lp)):
-            raise _lib.SgError("sg_disc_update produced non-finite losses (grid barrier timeout or diverged update)")
-        return lt / n, le / n, lp / n
+        out = tuple(_lazy.LazyFloat(pend, c) for c in range(3))
+        if not self.lazy_losses:
+            out = tuple(float(x) for x in out)
+        return out
 
     def phase_cycles(self):
         """Diagnostics: per-phase SM-clock totals of CTA 0 of the last persistent launch

@@ -41,6 +41,7 @@ class PPO(object):
         self.kernel_mode = 0            # 0: automatic, 1: one launch per phase, 2/3: CUDA-core tiles, 4: tensor-core tiles
         self.dp = None                  # simgan_b200.dist.DataParallel or None
         self.last_trace = None          # (n_steps, 4) {value_loss, action_loss, entropy, grad_norm}
+        self.last_kernel = None         # "tensor" (tcgen05 tiles) or "cuda-core": which tile phase the last update ran
         self._ws = None
         self._stage = None
         self._perm_dev = None
@@ -124,15 +125,17 @@ class PPO(object):
         cfg.beta1, cfg.beta2, cfg.adam_eps = g["betas"][0], g["betas"][1], g["eps"]
         cfg.use_clipped_value_loss = int(bool(self.use_clipped_value_loss))
         cfg.first_adam_step = opt.step_count + 1
-        cfg.row_begin, cfg.row_end = (0, mbs) if self.dp is None else self.dp.shard(mbs)
-        p2p = self.dp is not None and self.dp.p2p_ok(mbs)
-        if is_split and self.dp is not None and not p2p:
+        dp = self.dp if (self.dp is not None and self.dp.shards(mbs, 8)) else None      # "auto": replicate small minibatches
+        self.last_sharded = dp is not None
+        cfg.row_begin, cfg.row_end = (0, mbs) if dp is None else dp.shard(mbs)
+        p2p = dp is not None and dp.p2p_ok(mbs)
+        if is_split and dp is not None and not p2p:
             raise NotImplementedError("SplitPolicy data-parallel updates need the p2p transport and a minibatch size "
                                       "divisible by the world size (there is no phased split kernel for the nccl callback)")
-        cfg.mode = self.kernel_mode if (self.dp is None or p2p) else 1
+        cfg.mode = self.kernel_mode if (dp is None or p2p) else 1
         if cfg.mode == 1 and p2p:
             cfg.mode = 0
-        cfg.dp_ctx = self.dp.context("ppo", flat.numel()) if p2p else None
+        cfg.dp_ctx = dp.context("ppo", flat.numel()) if p2p else None
 
         lib = _lib.lib()
         stream = _lib.current_stream()
@@ -158,8 +161,8 @@ class PPO(object):
             permutations = torch.as_tensor(permutations).to(torch.int32).reshape(self.ppo_epoch, S)
 
         cb, user = _lib.NULL_ALLREDUCE, None
-        if self.dp is not None and not p2p:
-            cb = self.dp.make_callback(ws)
+        if dp is not None and not p2p:
+            cb = dp.make_callback(ws)
         first = None
         if permutations is None:
             _spec.consumed(self)
@@ -185,9 +188,10 @@ class PPO(object):
         opt.step_count += n_steps
 
         self._prof_view = (ws, 0 if is_split else int(lib.sg_ppo_phase_cycles_offset(C.byref(cfg))))
+        self.last_kernel = "cuda-core" if is_split or lib.sg_ppo_uses_tensor_cores(C.byref(cfg)) != 1 else "tensor"
         if p2p:
             # value / action loss columns (and SplitPolicy's state-dependent entropy) are per-rank partial sums
-            self.dp.sum_trace_(trace, 3 if is_split else 2)
+            dp.sum_trace_(trace, 3 if is_split else 2)
         _spec.host_idle()           # the next consumer of the CPU generator draws while the last epoch runs
         tr = _lib.read_back(trace)  # the one host sync of the update
         if not bool(torch.isfinite(tr).all()):

@@ -32,7 +32,13 @@ def shard_bounds(n_rows, rank, world):
 
 
 class DataParallel(object):
-    def __init__(self, group=None, transport=None):
+    """``policy``: "always" shards every update; "auto" shards an update only when that removes work from its critical
+    path -- a minibatch whose tiles all run concurrently on ONE GPU (tiles <= SMs: the 1024-row PPO minibatches and the
+    128-triple discriminator batches of BASELINE configs[0-2]) gains nothing from being split and would only pay the
+    per-step exchange, so under "auto" such an update is computed redundantly by every rank (identical seeds, deterministic
+    kernels: the replicas stay bit-identical) and no gradient is exchanged."""
+
+    def __init__(self, group=None, transport=None, policy="always"):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = group
@@ -42,6 +48,8 @@ class DataParallel(object):
             transport = "p2p" if (torch.cuda.is_available() and dist.get_backend(group) == "nccl") else "nccl"
         assert transport in ("p2p", "nccl")
         self.transport = transport
+        assert policy in ("always", "auto")
+        self.policy = policy
         self.n_allreduce = 0
         self._cb = None
         self._ctx = {}           # key -> sg_dp context (one per optimizer)
@@ -83,6 +91,13 @@ class DataParallel(object):
         trace[:, :n_cols] = part
         return trace
 
+    def shards(self, n_rows, rows_per_tile):
+        """Whether an update over minibatches of ``n_rows`` rows (tiles of ``rows_per_tile``) is sharded under the policy."""
+        if self.policy == "always":
+            return True
+        sms = int(_lib.lib().sg_device_sm_count()) or 148
+        return n_rows > rows_per_tile * sms
+
     def close(self):
         lib = _lib.lib()
         for ctx in self._ctx.values():
@@ -122,11 +137,11 @@ class DataParallel(object):
         return self._cb
 
 
-def attach(ppo=None, disc=None, group=None, transport=None):
+def attach(ppo=None, disc=None, group=None, transport=None, policy="always"):
     """Enable data-parallel updates on a PPO and/or Discriminator object when world_size > 1."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return None
-    dp = DataParallel(group, transport)
+    dp = DataParallel(group, transport, policy)
     if ppo is not None:
         ppo.dp = dp
     if disc is not None:

@@ -175,6 +175,8 @@ def test_ppo_per_step_trace_vs_oracle(case, mode):
     """Every optimizer step's (value_loss, action_loss, entropy, grad_norm) against the oracle replaying the
     same recorded index stream; parameters after the whole update."""
     g = Golden(case)
+    if mode == 4 and g.H not in (64, 128, 256):
+        pytest.skip("the tensor-core tiles need hidden in {64,128,256}")
     pol, agent, rs, buf = _ppo_objects(g, mode)
     ora = orc.PPOOracle(g.policy(), g.hyper())
     trace = []
