@@ -328,6 +328,7 @@ def run_cuda(args):
     def timed(n, from_host, with_timer, dropin_relabel=False):
         """Sum of per-step device times (ms) over n steps; L2 flushed between steps outside the events."""
         total = 0.0
+        each = []
         _lib.timer.enabled = with_timer
         _lib.timer.records = []
         barrier()
@@ -340,7 +341,9 @@ def run_cuda(args):
             losses = w.update_phase(from_host, dropin_relabel)
             e.record()
             torch.cuda.synchronize()
-            total += s.elapsed_time(e)
+            each.append(s.elapsed_time(e))
+            total += each[-1]
+        timed.last_each = each
         barrier()
         wall = time.perf_counter() - t_wall
         _lib.timer.enabled = False
@@ -360,6 +363,7 @@ def run_cuda(args):
     l0 = lib.sg_launch_count()
     ms_total, wall, _, losses = timed(args.steps, False, False)            # per-kernel event timer OFF for the headline
     launches = lib.sg_launch_count() - l0
+    ms_each = [round(x, 3) for x in timed.last_each]
     clocks = sample_clocks_stop(cp, cf, local_rank) if rank == 0 else {}
     # ---- timed region 2: end to end from pinned host buffers ------------------------------------------
     w.update_phase(True)
@@ -488,6 +492,7 @@ def run_cuda(args):
                                                      w.agent.phase_cycles())),
                                      "disc": dict(zip(["image", "tile", "bar1", "reduce_adam", "bar2"], w.disc.phase_cycles()))},
         "host_wall_ms_per_step": 1e3 * wall / args.steps,
+        "ms_each_timed_step_rank0": ms_each,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = run_reference(args, quiet=True, budget_s=20.0)

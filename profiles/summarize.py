@@ -41,7 +41,7 @@ def launches(tag, path):
         a[1] += float(r["Metric Value"].replace(",", ""))
     tot = sum(a[1] for a in agg.values())
     out = ["# %s: kernel launch list (ncu --metrics gpu__time_duration.sum --clock-control none)" % tag, "",
-           "Command: `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (first 400 launches). Times are",
+           "Command: `%s` (first launches up to the -c limit). Times are" % CMD_LAUNCH,
            "cold-cache and serialised under the profiler: compare SHARES, not absolutes.", "",
            "| kernel | launches | total us | share | avg us |", "|---|---:|---:|---:|---:|"]
     for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -97,8 +97,7 @@ def full(tag, rep):
         name = r[hdr.index("Kernel Name")]
         short = "ppo_update" if "ppo" in name else "disc_update" if "disc" in name else name.split("(")[0]
         out = ["# %s: ncu --set full capture of `%s`" % (tag, name), "",
-               "Command: `ncu --set full --clock-control none --import-source on -k regex:\"disc_reg|ppo_persistent\" -s 4 -c 2 "
-               "python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (cfg2 workload).", "", "| metric | value | unit |", "|---|---:|---|"]
+               "Command: `%s` (%s workload)." % (CMD_FULL, CFG), "", "| metric | value | unit |", "|---|---:|---|"]
         vals = {}
         for m in RAW_METRICS:
             if m in hdr:
@@ -111,7 +110,7 @@ def full(tag, rep):
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd = num("dram__bytes_read.sum") * scale[units[hdr.index("dram__bytes_read.sum")]]
         wr = num("dram__bytes_write.sum") * scale[units[hdr.index("dram__bytes_write.sum")]]
-        traffic.setdefault("cfg2", {})[short] = rd + wr
+        traffic.setdefault(CFG, {})[short] = rd + wr
         out += ["", "DRAM traffic per launch: %.3f MB read + %.3f MB written = %.3f MB." % (rd / 1e6, wr / 1e6, (rd + wr) / 1e6)]
         per_line, tot = stall_groups(rep, name.split("<")[0].split("(")[0].replace("void ", "").strip())
         if tot["samples"]:
@@ -126,6 +125,11 @@ def full(tag, rep):
         open(os.path.join(HERE, "%s_ncu_%s.md" % (tag, short)), "w").write("\n".join(out) + "\n")
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 
+
+CFG = os.environ.get("SG_PROFILE_CFG", "cfg2")
+CMD_LAUNCH = os.environ.get("SG_PROFILE_CMD_LAUNCH", "python bench.py --steps 2 --warmup 3 --no-cpu-baseline")
+CMD_FULL = os.environ.get("SG_PROFILE_CMD_FULL", "ncu --set full --clock-control none --import-source on -k regex:\"disc_reg|ppo_persistent\" -s 4 -c 2 "
+                          "python bench.py --steps 1 --warmup 3 --no-cpu-baseline")
 
 if __name__ == "__main__":
     tag, launch_csv, rep = sys.argv[1:4]
