@@ -253,6 +253,8 @@ int sg_selftest_division(uint64_t seed, int blocks, int per_thread, double b_lo,
  * passes = 3: fp32 operands split hi + lo, hi*hi + hi*lo + lo*hi ("3xTF32"); passes = 1: plain TF32.
  * M in {64,128}, N a multiple of 16 in [16,256], K a multiple of 8.
  * An MN-major operand needs an MN extent that is a multiple of 32 (SWIZZLE_128B_BASE32B atoms).
+ * a_mn_major == 2: A is (M,K) row-major and is kept UNSPLIT in shared memory with a padded row pitch (the layout of the
+ * tiles' activation masters); the hi pass reads it in place, only the lo image is built (passes must be 3).
  * h_raw_strides (HOST, 8 ints {a_lbo, a_sbo, a_k_step, b_lbo, b_sbo, b_k_step} in bytes + {a_layout_type,
  * b_layout_type} descriptor bits [61,64), or NULL): descriptor probe -- A and B are then copied verbatim into shared
  * memory (M*K and N*K floats) and read through descriptors with these strides (passes must be 1). */

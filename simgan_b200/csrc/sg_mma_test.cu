@@ -9,6 +9,8 @@ namespace sg {
 struct MmaTestArgs {
     int M, N, K;
     int a_mn, b_mn;       // operand given MN-major ((K, M) / (K, N) row-major) instead of K-major ((M, K) / (N, K))
+    int a_direct;         // A (K-major) is kept as an UNSPLIT fp32 master [k/4][row] with a row pitch of M+1 granules; the hi
+                          // pass reads it in place (the tensor core drops the 13 low mantissa bits), only lo is an image
     int raw;              // probe: A / B are verbatim shared-memory images and the descriptor strides come from rs[]
     int rs[8];            // {a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step} in bytes, {a_layout_type, b_layout_type}
     int passes;           // 3 = 3xTF32 (hi*hi + hi*lo + lo*hi), 1 = plain TF32
@@ -50,7 +52,8 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(MmaTestArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int M = a.M, N = a.N, K = a.K;
     float4* Ahi = smem4;
-    float4* Alo = Ahi + (size_t)M * K / 4;
+    const int apitch = a.a_direct ? M + 1 : M;                      // granules between consecutive k-quads of A's hi operand
+    float4* Alo = Ahi + round_up((K / 4) * apitch, 64);             // images stay 1024-byte aligned
     float4* Bhi = Alo + (size_t)M * K / 4;
     float4* Blo = Bhi + (size_t)N * K / 4;
     uint32_t ncols = 32;
@@ -65,7 +68,19 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(MmaTestArgs a) {
         for (int g = tid; g < M * K / 4; g += 128) Ahi[g] = reinterpret_cast<const float4*>(a.A)[g];
         for (int g = tid; g < N * K / 4; g += 128) Bhi[g] = reinterpret_cast<const float4*>(a.B)[g];
     } else {
-        fill_operand(Ahi, Alo, a.A, M, K, a.a_mn, tid, 128);
+        if (a.a_direct) {
+            for (int g = tid; g < (K / 4) * M; g += 128) {
+                const int kb = g / M, e = g - kb * M;
+                const float4 x = *reinterpret_cast<const float4*>(a.A + (size_t)e * K + 4 * kb);
+                Ahi[kb * apitch + e] = x;
+                float4 h;
+                h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                Alo[g] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+            }
+        } else {
+            fill_operand(Ahi, Alo, a.A, M, K, a.a_mn, tid, 128);
+        }
         fill_operand(Bhi, Blo, a.B, N, K, a.b_mn, tid, 128);
     }
     mma::fence_async_smem();
@@ -85,9 +100,10 @@ __global__ void __launch_bounds__(128, 1) mma_selftest_kernel(MmaTestArgs a) {
                 a_lt = a.rs[6]; b_lt = a.rs[7];
             }
             const uint32_t ah = mma::smem_addr(Ahi), al = mma::smem_addr(Alo), bh = mma::smem_addr(Bhi), bl = mma::smem_addr(Blo);
+            const uint32_t ah_lbo = a.a_direct ? 16u * apitch : a_lbo, ah_step = a.a_direct ? 32u * apitch : a_step;
             uint32_t accum = 0;
             for (int ks = 0; ks < K / 8; ++ks) {
-                const uint64_t dAh = mma::make_desc(ah + ks * a_step, a_lbo, a_sbo, a_lt), dAl = mma::make_desc(al + ks * a_step, a_lbo, a_sbo, a_lt);
+                const uint64_t dAh = mma::make_desc(ah + ks * ah_step, ah_lbo, a_sbo, a_lt), dAl = mma::make_desc(al + ks * a_step, a_lbo, a_sbo, a_lt);
                 const uint64_t dBh = mma::make_desc(bh + ks * b_step, b_lbo, b_sbo, b_lt), dBl = mma::make_desc(bl + ks * b_step, b_lbo, b_sbo, b_lt);
                 if (a.passes == 3) {
                     mma::mma_tf32(tbase, dAl, dBh, idesc, accum); accum = 1;
@@ -136,12 +152,15 @@ int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int pas
     SG_REQUIRE(K >= 8 && K % 8 == 0, "sg_selftest_mma: K must be a positive multiple of 8");
     SG_REQUIRE(passes == 1 || passes == 3, "sg_selftest_mma: passes must be 1 or 3");
     SG_REQUIRE(A && B && D, "sg_selftest_mma: null pointer");
-    const size_t smem = (size_t)2 * (M + N) * K * sizeof(float);
+    const bool a_direct = a_mn_major == 2;
+    if (a_direct) a_mn_major = 0;
+    SG_REQUIRE(!a_direct || (!h_raw_strides && passes == 3), "sg_selftest_mma: the in-place hi operand is a 3-pass, non-raw variant");
+    const size_t smem = (size_t)2 * (M + N) * K * sizeof(float) + (a_direct ? (size_t)(K / 4 + 64) * 16 : 0);
     SG_REQUIRE(smem <= 200 * 1024, "sg_selftest_mma: operands need %zu bytes of shared memory", smem);
     SG_REQUIRE(!h_raw_strides || passes == 1, "sg_selftest_mma: raw images run a single pass");
     SG_REQUIRE(h_raw_strides || ((!a_mn_major || M % 32 == 0) && (!b_mn_major || N % 32 == 0)),
                "sg_selftest_mma: an MN-major operand needs an MN extent that is a multiple of 32");
-    MmaTestArgs a{M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, h_raw_strides ? 1 : 0, {0, 0, 0, 0, 0, 0, 0, 0}, passes, A, B, D};
+    MmaTestArgs a{M, N, K, a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, a_direct ? 1 : 0, h_raw_strides ? 1 : 0, {0, 0, 0, 0, 0, 0, 0, 0}, passes, A, B, D};
     if (h_raw_strides)
         for (int i = 0; i < 8; ++i) a.rs[i] = h_raw_strides[i];
     SG_CUDA(cudaFuncSetAttribute(mma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

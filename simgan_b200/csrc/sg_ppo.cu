@@ -52,7 +52,7 @@ struct PpoArgs {
     unsigned int* bar;
     long long* prof;      // per-phase clock64 totals of CTA 0 (sg_ppo_phase_cycles)
     float* wimg;          // hi / lo operand images of the weights (tensor-core tiles, sg_ppo_mma.cuh)
-    int mma_ns;           // stage buffers of the tensor-core tiles
+    int mma_ring;         // bytes of the stage ring of the tensor-core tiles
     int slots_by_net;     // partial-gradient slot c only holds net c & 1 (tensor-core tiles)
     int dp_on;            // fused peer-memory gradient exchange (sg_dp.cuh)
     DpView dp;
@@ -887,7 +887,7 @@ template <int MR>
 __global__ void __launch_bounds__(kStepThreads, 1) ppo_mma_kernel(PpoArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double red[kStepThreads / 32];
-    const MmaDims d = make_mma_dims(a.O, a.H, a.A, MR, a.mma_ns);
+    const MmaDims d = make_mma_dims(a.O, a.H, a.A, MR, a.mma_ring);
     MmaSmem S;
     S.carve(smem_raw, d);
     MmaPipe P;
@@ -897,7 +897,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) ppo_mma_kernel(PpoArgs a) {
         mma::tmem_relinquish();
     }
     if (threadIdx.x == 0)
-        for (int s = 0; s < kMmaMaxStages; ++s) { mbar_init(S.full + s, 1); mbar_init(S.done + s, 1); }
+        for (int s = 0; s < kMmaMaxStages; ++s) {
+            mbar_init(S.full + s, 1); mbar_init(S.done + s, 1); mbar_init(S.filled + s, kMmaFillThreads / 32);
+        }
     mma::fence_before_sync();
     __syncthreads();
     mma::fence_after_sync();
@@ -973,14 +975,17 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;     // opt-in limit minus stat
 // traffic of the per-CTA partial gradient
 static size_t ppo_tile_smem_floats_r(const sg_ppo_config* c, int rows);
 // tensor-core tiles: 128 rows per job when the masters fit shared memory, else 64; 0 = not available for these sizes
-static int ppo_mma_rows(const sg_ppo_config* c, int* stages = nullptr) {
+static int ppo_mma_rows(const sg_ppo_config* c, int* ring_bytes = nullptr) {
     if (!ppo_mma_supported(c->obs_dim, c->hidden, c->act_dim)) return 0;
-    for (int mr = 128; mr >= 64; mr -= 64)
-        for (int ns = kMmaMaxStages; ns >= 2; --ns)
-            if ((size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, mr, ns).total <= kMaxDynSmem) {
-                if (stages) *stages = ns;
-                return mr;
-            }
+    for (int mr = 128; mr >= 64; mr -= 64) {
+        // the stage ring takes what the masters leave of the CTA's shared memory
+        const size_t rest = (size_t)make_mma_dims(c->obs_dim, c->hidden, c->act_dim, mr, 0).total;
+        if (rest + kMmaMinRingBytes > kMaxDynSmem) continue;
+        size_t ring = (kMaxDynSmem - rest) & ~(size_t)1023;
+        if (ring > (size_t)kMmaMaxRingBytes) ring = kMmaMaxRingBytes;
+        if (ring_bytes) *ring_bytes = (int)ring;
+        return mr;
+    }
     return 0;
 }
 // mode 0 picks the tensor-core tiles once a minibatch (shard) keeps every SM busy with full 64/128-row jobs
@@ -1165,13 +1170,13 @@ int sg_ppo_update(const sg_ppo_config* cfg, float* params, float* adam_m, float*
 
     const int tile_rows = ppo_rows(cfg);
     a.wimg = (float*)(ws + w.wimg);
-    a.mma_ns = 2;
+    a.mma_ring = 0;
     a.slots_by_net = use_mma ? 1 : 0;
     if (use_mma) {
         SG_CUDA(cudaMemsetAsync(ws, 0, w.total, s));
-        ppo_mma_rows(cfg, &a.mma_ns);
+        ppo_mma_rows(cfg, &a.mma_ring);
         const void* fn = tile_rows == 128 ? (const void*)ppo_mma_kernel<128> : (const void*)ppo_mma_kernel<64>;
-        const size_t smem = (size_t)make_mma_dims(a.O, a.H, a.A, tile_rows, a.mma_ns).total;
+        const size_t smem = (size_t)make_mma_dims(a.O, a.H, a.A, tile_rows, a.mma_ring).total;
         SG_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         SG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kStepThreads, smem));

@@ -15,8 +15,14 @@
 //
 // Data flow
 //   activations  live once, in fp32, in shared-memory "masters" laid out [col/4][row][col%4] (16-byte granules, row
-//                pitch MR+1 granules); for every K-chunk the 256 threads build the hi / lo operand images of the chunk in a
-//                ring of stage buffers (K-major or MN-major, sg_mma.cuh);
+//                pitch MR+1 granules).  That IS the K-major operand layout, and the tensor core reads only the top 19 bits
+//                of an fp32 word, so a K-major activation operand's hi pass reads the master in place; per K-chunk the
+//                seven "filler" warps build only its lo image (x - trunc(x)) -- or, for the MN-major operands of the
+//                weight-gradient contractions, the hi and lo images -- in a ring of stage buffers (sg_mma.cuh);
+//   pipeline     warp 0 is the control warp: one thread issues the TMA copies of the weight chunks (ring depth ahead) and
+//                the MMAs; fillers and issuer meet only through mbarriers (filled[s]: image ready, full[s]: weight chunk
+//                landed, done[s]: the MMAs that read stage s completed), so filling chunk c+1.., the TMA of chunk c+2..
+//                and the MMAs of chunk c overlap; the CTA only joins again at the epilogue;
 //   weights      are kept as ready-made hi / lo operand images of the whole K extent in global memory (L2): the CTA that
 //                owns a slice of the parameter vector rewrites the image entries of its parameters right after their Adam
 //                update, so a K-chunk of a weight operand is two contiguous TMA bulk copies (cp.async.bulk -> mbarrier
@@ -35,9 +41,10 @@
 
 namespace sg {
 
-constexpr int kMmaStageBytes = 24 * 1024;      // one stage: hi + lo images of the A chunk and of the B chunk
 constexpr int kMmaRedStride = 36;
-constexpr int kMmaMaxStages = 3;
+constexpr int kMmaMaxStages = 6;
+constexpr int kMmaFillThreads = kStepThreads - 32;      // warps 1.. build operand images; warp 0 issues TMA + MMA
+constexpr int kMmaMinRingBytes = 40 * 1024, kMmaMaxRingBytes = 96 * 1024;
 
 struct MmaDims {
     int MR, MRP;            // rows per job; master row pitch in granules
@@ -45,7 +52,7 @@ struct MmaDims {
     int Op8, Op32;          // K extent of layer 1; N extent of the dW1 contraction
     int xg, hg, dg, ag;     // granule columns of the X / hidden / dHead / action masters
     int Mb, nblk;           // weight-gradient contractions: rows (hidden units) per MMA and number of such blocks
-    int NS;                 // stage buffers
+    int ring;               // bytes of the stage ring (carved per contraction into NS stages of one K-chunk each)
     int tacc;               // weight-gradient accumulators stay in tensor memory across the CTA's jobs
     int c_dwh, c_dw2, c_dw1;// their columns (tacc)
     int tmem_cols;
@@ -53,7 +60,7 @@ struct MmaDims {
     int o_stage, o_X, o_ACT, o_H1, o_H2, o_DH, o_small, total;
 };
 
-__host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR, int NS) {
+__host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR, int ring_bytes) {
     MmaDims d;
     d.MR = MR; d.MRP = MR + 1;
     d.O = O; d.H = H; d.A = A;
@@ -61,7 +68,7 @@ __host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR, in
     d.xg = d.Op8 / 4; d.hg = H / 4; d.dg = 8; d.ag = round_up(A, 4) / 4;
     d.Mb = H >= 128 ? 128 : 64;
     d.nblk = H / d.Mb;
-    d.NS = NS;
+    d.ring = ring_bytes;
     const int work = H > 32 ? H : 32;
     d.c_dwh = work; d.c_dw2 = work + 32; d.c_dw1 = work + 32 + H;
     d.tacc = (d.nblk == 1 && d.c_dw1 + d.Op32 <= 512) ? 1 : 0;
@@ -70,7 +77,7 @@ __host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR, in
     while (t < cols) t <<= 1;
     d.tmem_cols = t;
     int o = 0;
-    d.o_stage = o; o += NS * kMmaStageBytes;
+    d.o_stage = o; o += ring_bytes;
     d.o_X = o; o += d.xg * d.MRP * 16;
     d.o_ACT = o; o += d.ag * d.MRP * 16;
     d.o_H1 = o; o += d.hg * d.MRP * 16;
@@ -78,8 +85,8 @@ __host__ __device__ inline MmaDims make_mma_dims(int O, int H, int A, int MR, in
     d.o_DH = o; o += d.dg * d.MRP * 16;
     d.o_small = o;
     // B1 B2 GB1 GB2 (H each), BH LS SIG VAR LSG GBH GLS (32 each), 5 row-scalar arrays + IDX (MR each), LOSS (4),
-    // RED (8 warps x 36), 2*3 mbarriers + tmem slot (64 bytes)
-    o += (4 * H + 7 * 32 + 6 * MR + 4 + 8 * kMmaRedStride) * 4 + 64;
+    // RED (8 warps x 36), 3 x kMmaMaxStages mbarriers + tmem slot (192 bytes)
+    o += (4 * H + 7 * 32 + 6 * MR + 4 + 8 * kMmaRedStride) * 4 + 192;
     d.total = round_up(o, 16);
     return d;
 }
@@ -141,11 +148,10 @@ __device__ __forceinline__ void mma_img_refresh(float* __restrict__ wimg, const 
 
 struct MmaSmem {
     float* stage0;
-    __device__ __forceinline__ float* stage(int s) const { return stage0 + s * (kMmaStageBytes / 4); }
     float4 *X, *ACT, *H1, *H2, *DH;
     float *B1, *B2, *GB1, *GB2, *BH, *LS, *IVAR, *I2VAR, *LSG, *GBH, *GLS, *RET, *VP, *OLP, *ADV, *VALID, *LOSS, *RED;
     int* IDX;
-    unsigned long long *full, *done;
+    unsigned long long *full, *done, *filled;
     uint32_t* tmem_slot;
     __device__ void carve(unsigned char* base, const MmaDims& d) {
         stage0 = reinterpret_cast<float*>(base + d.o_stage);
@@ -176,7 +182,8 @@ struct MmaSmem {
         RED = f; f += 8 * kMmaRedStride;
         full = reinterpret_cast<unsigned long long*>(f);
         done = full + kMmaMaxStages;
-        tmem_slot = reinterpret_cast<uint32_t*>(done + kMmaMaxStages);
+        filled = done + kMmaMaxStages;
+        tmem_slot = reinterpret_cast<uint32_t*>(filled + kMmaMaxStages);
     }
 };
 
@@ -193,17 +200,17 @@ __device__ __forceinline__ MmaOperand op_master_k(const float4* m4, int E) { ret
 __device__ __forceinline__ MmaOperand op_master_mn(const float4* m4, int E, int e0, int ecols) { return MmaOperand{1, E, m4, e0, ecols, nullptr, 0}; }
 __device__ __forceinline__ MmaOperand op_image(const float* img, int lo, int E, int mn) { return MmaOperand{2 + mn, E, nullptr, 0, 0, img, lo}; }
 
-constexpr int kMmaMaxG = 3;       // granules per thread, operand and chunk: 24 KiB / 8 bytes per element / 4 / 256 threads
+constexpr int kMmaMaxG = 4;       // granules per filler thread, operand and chunk (a filled operand chunk has <= 896 granules)
 
-// per-thread, per-GEMM plan of a master operand: which master granule each of my (up to 3) stage granules comes from at
-// k0 = 0 and where it goes; both are independent of the chunk, so a chunk only adds an offset
+// per-thread, per-contraction plan of a master operand: which master granule each of my (up to 4) stage granules comes
+// from at k0 = 0 and where it goes; both are independent of the chunk, so a chunk only adds an offset
 struct MmaPlan {
     int src[kMmaMaxG], dst[kMmaMaxG];      // master granule index at k0 = 0 (-1: zero fill), stage float offset
 };
-__device__ __forceinline__ void mma_plan(const MmaOperand& op, int MRP, MmaPlan& pl) {
+__device__ __forceinline__ void mma_plan(const MmaOperand& op, int MRP, int ftid, MmaPlan& pl) {
 #pragma unroll
     for (int i = 0; i < kMmaMaxG; ++i) {
-        const int gi = threadIdx.x + i * kStepThreads;
+        const int gi = ftid + i * kMmaFillThreads;
         if (op.kind == 0) {
             const int kq = gi / op.E, e = gi - kq * op.E;
             pl.src[i] = kq * MRP + e;
@@ -220,158 +227,207 @@ __device__ __forceinline__ void mma_plan(const MmaOperand& op, int MRP, MmaPlan&
         }
     }
 }
-// chunk [k0, k0+kc) of a master operand -> hi / lo stage images.  hi = x with the 13 low mantissa bits cleared (what the
-// tensor core reads of an fp32 word anyway), lo = x - hi exactly (13 significant bits, of which the tensor core keeps 11):
-// x = hi + lo to 2^-21 relative, two instructions per element
-__device__ __forceinline__ void mma_fill(const MmaOperand& op, const MmaPlan& pl, int MRP, int k0, int kc, float* hi, float* lo) {
+// chunk [k0, k0+kc) of a master operand -> stage images.  hi = x with the 13 low mantissa bits cleared (what the tensor
+// core reads of an fp32 word anyway), lo = x - hi exactly (13 significant bits, of which the tensor core keeps 11):
+// x = hi + lo to 2^-21 relative, two instructions per element.  K-major operands (kind 0) get only the lo image: their hi
+// pass reads the master itself.
+__device__ __forceinline__ void mma_fill(const MmaOperand& op, const MmaPlan& pl, int MRP, int ftid, int k0, int kc, float* hi, float* lo) {
     const int ng = (kc * op.E) >> 2;
     const int delta = op.kind == 0 ? (k0 >> 2) * MRP : k0;
 #pragma unroll
     for (int i = 0; i < kMmaMaxG; ++i) {
-        if (i * kStepThreads >= ng) break;
-        const int gi = threadIdx.x + i * kStepThreads;
+        if (i * kMmaFillThreads >= ng) break;
+        const int gi = ftid + i * kMmaFillThreads;
         if (gi < ng) {
             const float4 x = pl.src[i] >= 0 ? op.m4[pl.src[i] + delta] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 h;
             h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
             h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-            *reinterpret_cast<float4*>(hi + pl.dst[i]) = h;
+            if (op.kind != 0) *reinterpret_cast<float4*>(hi + pl.dst[i]) = h;
             *reinterpret_cast<float4*>(lo + pl.dst[i]) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
     }
 }
 
 // ---- stage pipeline ------------------------------------------------------------------------------------------------------
-// Stage s is released by the completion of the MMAs that read it (tcgen05.commit -> done[s]); its weight chunk arrives by
-// TMA on full[s].  Every thread tracks the same phase bits (all control flow around them is uniform).
+// Three mbarriers per stage: filled[s] (one arrival per filler warp: the chunk's images are written and fenced), full[s]
+// (TMA transaction bytes of the chunk's weight images), done[s] (tcgen05.commit: the MMAs that read stage s completed, the
+// stage may be rewritten).  A contraction starts with every stage free (its predecessor drained), so chunk c uses stage
+// c % NS for the (c / NS)-th time and the parity of its phase on each barrier is base bit ^ (c / NS): every thread can
+// compute any chunk's parity without having waited on the earlier ones.  The base bits advance at the end of a contraction,
+// identically in all threads.
 struct MmaPipe {
-    unsigned int done_par, done_pend, full_par;      // bit s
-    int cur;                                         // stage of the next chunk
+    unsigned int done_base, fill_base, full_base;      // bit s
 #ifdef SG_MMA_PROFILE
-    long long prof[8];
+    int gid;                                            // contraction index within the job (profile rows)
 #endif
     __device__ __forceinline__ void init() {
-        done_par = done_pend = full_par = 0u; cur = 0;
+        done_base = fill_base = full_base = 0u;
 #ifdef SG_MMA_PROFILE
-        for (int i = 0; i < 8; ++i) prof[i] = 0;
+        gid = 0;
 #endif
-    }
-    __device__ __forceinline__ void wait_done(unsigned long long* done, int s) {
-        if ((done_pend >> s) & 1u) {
-            mbar_wait(done + s, (done_par >> s) & 1u);
-            done_par ^= 1u << s;
-            done_pend &= ~(1u << s);
-        }
     }
 };
-
 #ifdef SG_MMA_PROFILE
-#define SG_MMA_T(var) const long long var = clock64()
-#define SG_MMA_ACC(i, expr) P.prof[i] += (expr)
+// per contraction: {issuer: wait filled, wait full, issue, wait refill; filler (thread 32): wait done, fill; chunks, NS}
+__shared__ unsigned int sg_mma_prof[20][10];
+#define SG_MMA_CLK(v) const long long v = clock64()
+#define SG_MMA_ADD(col, expr) sg_mma_prof[P.gid][col] += (unsigned int)(expr)
 #else
-#define SG_MMA_T(var)
-#define SG_MMA_ACC(i, expr)
+#define SG_MMA_CLK(v)
+#define SG_MMA_ADD(col, expr)
 #endif
+// mbarrier wait of the tile pipeline: a protocol error must end the launch (trap -> the host sees a launch failure), not
+// hang the cooperative grid
+__device__ __forceinline__ void mma_wait(unsigned long long* bar, unsigned int parity) {
+    unsigned int done;
+    unsigned int spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 26)) __trap();
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // D[tmem columns dcol .. dcol+N) (Mi rows) (+)= A . B^T over K, 3xTF32.  A is a master operand; B a master operand or a
 // weight image.  All 256 threads call; returns with every MMA complete and visible to tcgen05.ld.
-__device__ __forceinline__ void mma_gemm(MmaSmem& S, MmaPipe& P, int NS, int MRP, uint32_t tbase, uint32_t dcol, int Mi, int N, int K,
+__device__ __forceinline__ void mma_gemm(MmaSmem& S, MmaPipe& P, int ring_bytes, int MRP, uint32_t tbase, uint32_t dcol, int Mi, int N, int K,
                                       MmaOperand A, MmaOperand B, uint32_t accum) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int a_mn = A.kind & 1, b_mn = B.kind & 1;
     const bool b_img = B.kind >= 2;
-    int KC = (kMmaStageBytes / ((A.E + B.E) * 8)) & ~7;
+    const bool a_dir = A.kind == 0;                                  // hi pass straight from the master
+    const int pk = A.E * (a_dir ? 4 : 8) + B.E * 8;                  // stage bytes per k
+    // chunk length: aim at 4 (weights by TMA: their L2 latency has to be covered) or 3 stages, within what the fillers'
+    // plan holds per chunk
+    int KC = (ring_bytes / ((b_img ? 4 : 3) * pk)) & ~7;
+    if (KC < 8) KC = 8;
+    { const int cap = (kMmaMaxG * kMmaFillThreads * 4 / A.E) & ~7; if (KC > cap) KC = cap; }
+    if (!b_img) { const int cap = (kMmaMaxG * kMmaFillThreads * 4 / B.E) & ~7; if (KC > cap) KC = cap; }
     if (KC > K) KC = K;
     const int nchunks = (K + KC - 1) / KC;
-    const uint32_t idesc = mma::make_idesc_tf32(Mi, N, a_mn, b_mn);
-    // descriptor templates (everything but the start address) and the per-MMA (K = 8) address step in 16-byte units
-    const uint64_t a_tmpl = mma::make_desc(0u, a_mn ? 512u : 16u * A.E, a_mn ? 16u * A.E : 128u, a_mn);
-    const uint64_t b_tmpl = mma::make_desc(0u, b_mn ? 512u : 16u * B.E, b_mn ? 16u * B.E : 128u, b_mn);
-    const uint32_t a_step = 2u * A.E, b_step = 2u * B.E;
-    MmaPlan pa, pb;
-    mma_plan(A, MRP, pa);
-    if (!b_img) mma_plan(B, MRP, pb);
-    const int s0 = P.cur;
-    // prologue: the first NS-1 weight chunks
-    if (b_img) {
-        const int npre = nchunks < NS - 1 ? nchunks : NS - 1;
-        for (int c = 0; c < npre; ++c) {
-            int s = s0 + c; if (s >= NS) s -= NS;
-            P.wait_done(S.done, s);
-            if (tid == 0) {
+    int NS = ring_bytes / (KC * pk);
+    if (NS > kMmaMaxStages) NS = kMmaMaxStages;
+    if (NS > nchunks) NS = nchunks;
+    const int stage_floats = (KC * pk) >> 2;
+    const int a_img_floats = a_dir ? 1 : 2;                          // x A.E x kc: floats of A's images in a stage
+    const unsigned int done_base = P.done_base, fill_base = P.fill_base, full_base = P.full_base;
+
+    SG_MMA_CLK(g0);
+    if (warp > 0) {
+        // ---- fillers (their first thread also requests the weight chunks: a stage is refilled by whoever sees it free, so
+        //      the MMA issuer never waits for a completion) ------------------------------------------------------------------
+        const int ftid = tid - 32;
+        auto issue_tma = [&](int cn) {
+            const int sn = cn % NS;
+            const int kn0 = cn * KC, kcn = K - kn0 < KC ? K - kn0 : KC;
+            float* Bn = S.stage0 + sn * stage_floats + a_img_floats * A.E * kcn;
+            const unsigned int bytes = (unsigned int)(kcn * B.E * 4);
+            mbar_expect_tx(S.full + sn, 2u * bytes);
+            tma_bulk_g2s(Bn, B.img + (size_t)kn0 * B.E, bytes, S.full + sn);
+            tma_bulk_g2s(Bn + B.E * kcn, B.img + B.img_lo + (size_t)kn0 * B.E, bytes, S.full + sn);
+        };
+        if (b_img && ftid == 0) {
+            fence_proxy_async();
+            for (int c = 0; c < NS; ++c) issue_tma(c);
+        }
+        MmaPlan pa, pb;
+        mma_plan(A, MRP, ftid, pa);
+        if (!b_img) mma_plan(B, MRP, ftid, pb);
+        int s = 0, u = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            const int k0 = c * KC, kc = K - k0 < KC ? K - k0 : KC;
+            SG_MMA_CLK(f0);
+            if (u > 0) {
+                mma_wait(S.done + s, ((done_base >> s) ^ (unsigned int)(u - 1)) & 1u);      // chunk c - NS has been read
+                if (b_img && ftid == 0) issue_tma(c);
+            }
+            SG_MMA_CLK(f1);
+            float* st = S.stage0 + s * stage_floats;
+            float* Alo = a_dir ? st : st + A.E * kc;
+            float* Bhi = Alo + A.E * kc;
+            mma_fill(A, pa, MRP, ftid, k0, kc, st, Alo);
+            if (!b_img) mma_fill(B, pb, MRP, ftid, k0, kc, Bhi, Bhi + B.E * kc);
+            mma::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(S.filled + s);
+#ifdef SG_MMA_PROFILE
+            if (tid == 32) { SG_MMA_CLK(f2); SG_MMA_ADD(4, f1 - f0); SG_MMA_ADD(5, f2 - f1); }
+#endif
+            if (++s == NS) { s = 0; ++u; }
+        }
+    } else {
+        // ---- control warp: one thread issues the weight copies and the MMAs --------------------------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = mma::make_idesc_tf32(Mi, N, a_mn, b_mn);
+            // descriptor templates (everything but the start address) and the per-MMA (K = 8) address step in 16-byte units
+            const uint64_t a_tmpl = mma::make_desc(0u, a_mn ? 512u : 16u * A.E, a_mn ? 16u * A.E : 128u, a_mn);
+            const uint64_t b_tmpl = mma::make_desc(0u, b_mn ? 512u : 16u * B.E, b_mn ? 16u * B.E : 128u, b_mn);
+            const uint64_t m_tmpl = mma::make_desc(0u, 16u * MRP, 128u, 0u);                  // the master as a K-major operand
+            const uint32_t a_step = 2u * A.E, b_step = 2u * B.E, m_step = 2u * MRP;
+            const uint32_t m_base = a_dir ? mma::smem_addr(A.m4) >> 4 : 0u;
+            int s = 0, u = 0;
+            SG_MMA_ADD(8, clock64() - g0);
+            for (int c = 0; c < nchunks; ++c) {
                 const int k0 = c * KC, kc = K - k0 < KC ? K - k0 : KC;
-                float* Bhi = S.stage(s) + 2 * A.E * kc;
-                const unsigned int bytes = (unsigned int)(kc * B.E * 4);
-                fence_proxy_async();
-                mbar_expect_tx(S.full + s, 2u * bytes);
-                tma_bulk_g2s(Bhi, B.img + (size_t)k0 * B.E, bytes, S.full + s);
-                tma_bulk_g2s(Bhi + B.E * kc, B.img + B.img_lo + (size_t)k0 * B.E, bytes, S.full + s);
-            }
-        }
-    }
-    for (int c = 0; c < nchunks; ++c) {
-        const int k0 = c * KC, kc = K - k0 < KC ? K - k0 : KC;
-        int s = s0 + c % NS; if (s >= NS) s -= NS;
-        SG_MMA_T(t0);
-        P.wait_done(S.done, s);
-        SG_MMA_T(t1);
-        float* Ahi = S.stage(s);
-        float* Alo = Ahi + A.E * kc;
-        float* Bhi = Alo + A.E * kc;
-        float* Blo = Bhi + B.E * kc;
-        mma_fill(A, pa, MRP, k0, kc, Ahi, Alo);
-        if (!b_img) mma_fill(B, pb, MRP, k0, kc, Bhi, Blo);
-        SG_MMA_T(t2);
-        mma::fence_async_smem();
-        __syncthreads();
-        SG_MMA_T(t3);
-        if (tid < 32 && mma::elect_one()) {
-            if (b_img) { mbar_wait(S.full + s, (P.full_par >> s) & 1u); }
-            SG_MMA_T(t4);
-            mma::fence_after_sync();
-            const uint32_t ah = mma::smem_addr(Ahi) >> 4, al = mma::smem_addr(Alo) >> 4, bh = mma::smem_addr(Bhi) >> 4, bl = mma::smem_addr(Blo) >> 4;
-            const int nks = kc >> 3;
+                SG_MMA_CLK(i0);
+                mma_wait(S.filled + s, ((fill_base >> s) ^ (unsigned int)u) & 1u);
+                SG_MMA_CLK(i1);
+                if (b_img) mma_wait(S.full + s, ((full_base >> s) ^ (unsigned int)u) & 1u);
+                SG_MMA_CLK(i2);
+                mma::fence_after_sync();
+                float* st = S.stage0 + s * stage_floats;
+                const uint32_t al = mma::smem_addr(a_dir ? st : st + A.E * kc) >> 4;
+                const uint32_t ah = a_dir ? m_base + (uint32_t)(k0 >> 2) * (uint32_t)MRP : mma::smem_addr(st) >> 4;
+                const uint32_t bh = mma::smem_addr(st + a_img_floats * A.E * kc) >> 4, bl = bh + (uint32_t)((B.E * kc) >> 2);
+                const uint64_t ah_tmpl = a_dir ? m_tmpl : a_tmpl;
+                const uint32_t ah_step = a_dir ? m_step : a_step;
+                const int nks = kc >> 3;
 #pragma unroll 2
-            for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t dAh = a_tmpl | (uint64_t)((ah + ks * a_step) & 0x3FFFu), dAl = a_tmpl | (uint64_t)((al + ks * a_step) & 0x3FFFu);
-                const uint64_t dBh = b_tmpl | (uint64_t)((bh + ks * b_step) & 0x3FFFu), dBl = b_tmpl | (uint64_t)((bl + ks * b_step) & 0x3FFFu);
-                mma::mma_tf32(tbase + dcol, dAl, dBh, idesc, accum);
-                mma::mma_tf32(tbase + dcol, dAh, dBl, idesc, 1u);
-                mma::mma_tf32(tbase + dcol, dAh, dBh, idesc, 1u);
-                accum = 1u;
+                for (int ks = 0; ks < nks; ++ks) {
+                    const uint64_t dAh = ah_tmpl | (uint64_t)((ah + ks * ah_step) & 0x3FFFu), dAl = a_tmpl | (uint64_t)((al + ks * a_step) & 0x3FFFu);
+                    const uint64_t dBh = b_tmpl | (uint64_t)((bh + ks * b_step) & 0x3FFFu), dBl = b_tmpl | (uint64_t)((bl + ks * b_step) & 0x3FFFu);
+                    mma::mma_tf32(tbase + dcol, dAl, dBh, idesc, accum);
+                    mma::mma_tf32(tbase + dcol, dAh, dBl, idesc, 1u);
+                    mma::mma_tf32(tbase + dcol, dAh, dBh, idesc, 1u);
+                    accum = 1u;
+                }
+                mma::commit(S.done + s);
+                SG_MMA_CLK(i3);
+#ifdef SG_MMA_PROFILE
+                SG_MMA_ADD(0, i1 - i0); SG_MMA_ADD(1, i2 - i1); SG_MMA_ADD(2, i3 - i2);
+#endif
+                if (++s == NS) { s = 0; ++u; }
             }
-            mma::commit(S.done + s);
-            SG_MMA_T(t5);
-            SG_MMA_ACC(3, t4 - t3); SG_MMA_ACC(4, t5 - t4);
+#ifdef SG_MMA_PROFILE
+            SG_MMA_ADD(6, nchunks); sg_mma_prof[P.gid][7] = (unsigned int)(NS * 1000 + KC);
+#endif
         }
-        if (b_img) P.full_par ^= 1u << s;
-        P.done_pend |= 1u << s;
-        SG_MMA_ACC(0, t1 - t0); SG_MMA_ACC(1, t2 - t1); SG_MMA_ACC(2, t3 - t2); SG_MMA_ACC(5, 1);
-        // weight chunk c + NS - 1 goes to the stage chunk c - 1 used
-        if (b_img && c + NS - 1 < nchunks) {
-            const int cn = c + NS - 1;
-            int sn = s0 + cn % NS; if (sn >= NS) sn -= NS;
-            SG_MMA_T(t6);
-            P.wait_done(S.done, sn);
-            SG_MMA_T(t7);
-            SG_MMA_ACC(6, t7 - t6);
-            if (tid == 0) {
-                const int kn0 = cn * KC, kcn = K - kn0 < KC ? K - kn0 : KC;
-                float* Bn = S.stage(sn) + 2 * A.E * kcn;
-                const unsigned int bytes = (unsigned int)(kcn * B.E * 4);
-                mbar_expect_tx(S.full + sn, 2u * bytes);
-                tma_bulk_g2s(Bn, B.img + (size_t)kn0 * B.E, bytes, S.full + sn);
-                tma_bulk_g2s(Bn + B.E * kcn, B.img + B.img_lo + (size_t)kn0 * B.E, bytes, S.full + sn);
-            }
-        }
+        __syncwarp();
     }
-    P.cur = s0 + nchunks % NS; if (P.cur >= NS) P.cur -= NS;
-    SG_MMA_T(t8);
-#pragma unroll
-    for (int s = 0; s < kMmaMaxStages; ++s) if (s < NS) P.wait_done(S.done, s);
-    mma::fence_after_sync();
-    SG_MMA_T(t9);
-    SG_MMA_ACC(7, t9 - t8);
+    // every MMA issued above has completed once the last chunk's commit has arrived
+    {
+        const int cl = nchunks - 1, sl = cl % NS, ul = cl / NS;
+        SG_MMA_CLK(d0);
+        mma_wait(S.done + sl, ((done_base >> sl) ^ (unsigned int)ul) & 1u);
+        mma::fence_after_sync();
+#ifdef SG_MMA_PROFILE
+        if (tid == 0) { SG_MMA_ADD(9, clock64() - d0); }
+#endif
+    }
+    // advance the phase bases by the number of times each stage was used (NS <= nchunks: every stage was)
+    for (int s = 0; s < NS; ++s) {
+        const unsigned int flip = (unsigned int)(((nchunks - 1 - s) / NS + 1) & 1) << s;
+        P.done_base ^= flip;
+        P.fill_base ^= flip;
+        if (b_img) P.full_base ^= flip;
+    }
+#ifdef SG_MMA_PROFILE
+    if (P.gid < 19) ++P.gid;
+#endif
 }
 
 // Epilogue walker: accumulator rows [0, Mi) x columns [0, N) from tmem column dcol; f(m, c0, v) gets 16 consecutive
@@ -389,6 +445,7 @@ __device__ __forceinline__ void mma_epilogue(uint32_t tbase, uint32_t dcol, int 
         if (live) f(m, c0, v);
     }
     mma::fence_before_sync();
+    mma::fence_async_smem();            // a master written here may be the next contraction's in-place hi operand
     __syncthreads();
 }
 
@@ -466,7 +523,7 @@ template <int MR>
 __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaPipe& P, uint32_t tbase, int step, int tile,
                             int net, float* __restrict__ gout, bool first) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int O = a.O, H = a.H, A = a.A, MRP = d.MRP, NS = d.NS;
+    const int O = a.O, H = a.H, A = a.A, MRP = d.MRP, RB = d.ring;
     const int epoch = step / a.nmb, mb = step - epoch * a.nmb;
     const int32_t* idx = a.perm + (size_t)epoch * a.S + (size_t)mb * a.mbs;
     const int row0 = a.row_begin + tile * MR;
@@ -481,6 +538,10 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     long long tstage[16];
     int nstage = 0;
     const bool prof = blockIdx.x == 0 && tid == 0 && step == 1;
+    P.gid = 0;
+    __syncthreads();
+    for (int i = tid; i < 20 * 10; i += kStepThreads) (&sg_mma_prof[0][0])[i] = 0u;
+    __syncthreads();
 #endif
     SG_MMA_LAP();
     // ---- sampler indices and row scalars (flat sample id = t*N+n, A2C/storage.py:169-185) -------------------------------
@@ -541,11 +602,12 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
                 if (dstp[u]) *dstp[u] = v[u];
         }
     }
+    mma::fence_async_smem();            // the X master is G1's in-place hi operand
     __syncthreads();
     SG_MMA_LAP();   // 1: gather
 
     // ---- forward (A2C/model.py:255-264) ---------------------------------------------------------------------------------------
-    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, d.Op8, op_master_k(S.X, MR), op_image(img + g.w1k, lo, H, 0), 0u);
+    mma_gemm(S, P, RB, MRP, tbase, 0, MR, H, d.Op8, op_master_k(S.X, MR), op_image(img + g.w1k, lo, H, 0), 0u);
     SG_MMA_LAP();   // 2: G1
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
@@ -556,7 +618,7 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         }
     });
     SG_MMA_LAP();   // 3: E1
-    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, H, op_master_k(S.H1, MR), op_image(img + g.w2k, lo, H, 0), 0u);
+    mma_gemm(S, P, RB, MRP, tbase, 0, MR, H, H, op_master_k(S.H1, MR), op_image(img + g.w2k, lo, H, 0), 0u);
     SG_MMA_LAP();   // 4: G2
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
@@ -568,7 +630,7 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     });
     SG_MMA_LAP();   // 5: E2
     // head: Gaussian mean (A2C/distributions.py:109-110) or critic_linear
-    mma_gemm(S, P, NS, MRP, tbase, 0, MR, NA16, H, op_master_k(S.H2, MR), op_image(img + g.whk, lo, NA16, 0), 0u);
+    mma_gemm(S, P, RB, MRP, tbase, 0, MR, NA16, H, op_master_k(S.H2, MR), op_image(img + g.whk, lo, NA16, 0), 0u);
     SG_MMA_LAP();   // 6: G3
 
     // ---- per-row losses and the gradient seeds (thread = row; warps 0-3) -------------------------------------------------------
@@ -688,12 +750,12 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     const uint32_t accum = (d.tacc && !first) ? 1u : 0u;
     // head weight gradient, transposed: D(unit, a) = sum_rows H2(row, unit) dHead(row, a)
     for (int b = 0; b < d.nblk; ++b) {
-        mma_gemm(S, P, NS, MRP, tbase, d.tacc ? d.c_dwh : 0, d.Mb, 32, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H), op_master_mn(S.DH, 32, 0, 32), accum);
+        mma_gemm(S, P, RB, MRP, tbase, d.tacc ? d.c_dwh : 0, d.Mb, 32, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H), op_master_mn(S.DH, 32, 0, 32), accum);
         if (!d.tacc) mma_store_dwh(tbase, 0, d.Mb, b * d.Mb, gout + (net ? L.vw : L.mw), H, NA, acc);
     }
     SG_MMA_LAP();   // 8: G4 + E4
     // dZ2 = (dHead . Wh) * (1 - h2^2), in place over the H2 master
-    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, NA8, op_master_k(S.DH, MR), op_image(img + g.whm, lo, H, 1), 0u);
+    mma_gemm(S, P, RB, MRP, tbase, 0, MR, H, NA8, op_master_k(S.DH, MR), op_image(img + g.whm, lo, H, 1), 0u);
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -710,14 +772,14 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         const int nsplit = d.nblk > 1 ? 2 : 1, Nh = H / nsplit;
         for (int b = 0; b < d.nblk; ++b)
             for (int h = 0; h < nsplit; ++h) {
-                mma_gemm(S, P, NS, MRP, tbase, d.tacc ? d.c_dw2 : 0, d.Mb, Nh, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H),
+                mma_gemm(S, P, RB, MRP, tbase, d.tacc ? d.c_dw2 : 0, d.Mb, Nh, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H),
                          op_master_mn(S.H1, Nh, h * Nh, H), accum);
                 if (!d.tacc) mma_store_dw(tbase, 0, d.Mb, Nh, b * d.Mb, gout + (net ? L.cw2 : L.aw2) + h * Nh, H, Nh, acc);
             }
     }
     SG_MMA_LAP();   // 10: G6 + E6
     // dZ1 = (dZ2 . W2) * (1 - h1^2), in place over the H1 master
-    mma_gemm(S, P, NS, MRP, tbase, 0, MR, H, H, op_master_k(S.H2, MR), op_image(img + g.w2m, lo, H, 1), 0u);
+    mma_gemm(S, P, RB, MRP, tbase, 0, MR, H, H, op_master_k(S.H2, MR), op_image(img + g.w2m, lo, H, 1), 0u);
     mma_epilogue(tbase, 0, MR, H, [&](int r, int c0, const float (&v)[16]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -731,7 +793,7 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     SG_MMA_LAP();   // 11: G7 + E7
     // dW1(n, k) = sum_rows dZ1(row, n) X(row, k)
     for (int b = 0; b < d.nblk; ++b) {
-        mma_gemm(S, P, NS, MRP, tbase, d.tacc ? d.c_dw1 : 0, d.Mb, d.Op32, MR, op_master_mn(S.H1, d.Mb, b * d.Mb, H),
+        mma_gemm(S, P, RB, MRP, tbase, d.tacc ? d.c_dw1 : 0, d.Mb, d.Op32, MR, op_master_mn(S.H1, d.Mb, b * d.Mb, H),
                  op_master_mn(S.X, d.Op32, 0, d.Op8), accum);
         if (!d.tacc) mma_store_dw(tbase, 0, d.Mb, d.Op32, b * d.Mb, gout + (net ? L.cw1 : L.aw1), O, O, acc);
     }
@@ -740,8 +802,11 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     if (prof) {
         printf("job tile %d net %d first %d cycles:", tile, net, (int)first);
         for (int i = 1; i < nstage; ++i) printf(" %lld", tstage[i] - tstage[i - 1]);
-        printf("\n  gemm totals so far: chunks %lld | wait_done %lld fill %lld sync %lld | t0: wait_full %lld issue %lld | wait_prefetch %lld drain %lld\n",
-               P.prof[5], P.prof[0], P.prof[1], P.prof[2], P.prof[3], P.prof[4], P.prof[6], P.prof[7]);
+        printf("\n");
+        for (int g = 0; g < P.gid; ++g)
+            printf("  gemm %2d: chunks %3u NS*1000+KC %5u | issuer: setup %5u wait_filled %6u wait_full %6u issue %6u drain %5u | filler: wait_done %6u fill %6u\n",
+                   g, sg_mma_prof[g][6], sg_mma_prof[g][7], sg_mma_prof[g][8], sg_mma_prof[g][0], sg_mma_prof[g][1], sg_mma_prof[g][2],
+                   sg_mma_prof[g][9], sg_mma_prof[g][4], sg_mma_prof[g][5]);
     }
 #endif
 }

@@ -16,7 +16,7 @@ def run(M, N, K, a_mn, b_mn, passes, seed=0):
     A = torch.randn(M, K, generator=g)
     B = torch.randn(N, K, generator=g)
     ref = A.double() @ B.double().t()
-    dA = (A.t().contiguous() if a_mn else A).cuda()
+    dA = (A.t().contiguous() if a_mn == 1 else A).cuda()
     dB = (B.t().contiguous() if b_mn else B).cuda()
     D = torch.zeros(M, N, device="cuda")
     lib = _lib.lib()
@@ -40,3 +40,12 @@ def test_3xtf32_matches_float64(M, N, K, a_mn, b_mn):
 def test_plain_tf32_is_tf32_grade(a_mn, b_mn):
     err = run(128, 128, 64, a_mn, b_mn, 1)
     assert 1e-5 < err < 5e-3, err
+
+
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (64, 256, 64), (128, 32, 128), (64, 128, 32)])
+def test_hi_operand_read_in_place_from_unsplit_master(M, N, K, b_mn):
+    """The activation masters double as the hi operand: the tensor core reads the top 19 bits of an fp32 word, so an
+    unsplit K-major master with a padded row pitch is a valid hi image; only lo = x - trunc(x) is built."""
+    err = run(M, N, K, 2, b_mn, 3)
+    assert err < 2e-6, err
