@@ -261,6 +261,23 @@ int sg_selftest_division(uint64_t seed, int blocks, int per_thread, double b_lo,
 int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int passes, const float* A, const float* B,
                     float* D, const int* h_raw_strides, void* stream);
 
+/* ---- host side of the minibatch sampler ---------------------------------------------------------------------------------------
+ * Replaces: the `torch.randperm(batch_size)` draws BatchSampler(SubsetRandomSampler(range(batch_size)), ...) makes once per PPO
+ * epoch (third_party/a2c_ppo_acktr/storage.py:158-162), when T*N is in the millions and the draw is longer than the epoch's
+ * kernel.  Same stream, bit for bit: ATen's randperm_cpu (n < 2^32/20) is a Fisher-Yates walk over one 32-bit mt19937 draw per
+ * element.  HOST pointers only; no CUDA call is made.
+ *
+ * sg_host_randperm_begin: start producing n_perms consecutive permutations of n elements into out (HOST, n_perms*n int32,
+ * e.g. pinned staging) from the engine state (mt_key: the 624 state words, mt_pos: index of the next word, 624 = "regenerate
+ * first" -- i.e. torch.get_rng_state()'s `state` and `next` fields).  One thread runs the engine, n_threads workers run the
+ * walks of different permutations concurrently.  Returns a handle, or NULL (sg_last_error).
+ * sg_host_randperm_wait: block until permutation e is complete in out[e*n .. (e+1)*n).
+ * sg_host_randperm_end: join, write the engine state after the last draw (what torch.set_rng_state must receive so that the
+ * generator is where n_perms torch.randperm(n) calls would have left it), free the handle. */
+void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int n_perms, int32_t* out, int n_threads);
+int sg_host_randperm_wait(void* handle, int e);
+int sg_host_randperm_end(void* handle, uint32_t* mt_key_out, int* mt_pos_out);
+
 #ifdef __cplusplus
 }
 #endif

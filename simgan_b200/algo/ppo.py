@@ -12,7 +12,7 @@ import ctypes as C
 
 import torch
 
-from .. import _lib, _spec
+from .. import _lib, _spec, host_sampler
 from .adam import FusedAdam
 
 
@@ -73,7 +73,7 @@ class PPO(object):
         S = self._last_S
         if S is None or _spec.still_valid(self._predraw, S):
             return
-        self._predraw = _spec.predraw(S, lambda: torch.randperm(S))
+        self._predraw = _spec.predraw(S, lambda: host_sampler.randperm_i32(S))
         self._schedule(self.ppo_epoch * self.num_mini_batch)      # pure host arithmetic; cached by its inputs
 
     def _schedule(self, n_steps):
@@ -169,11 +169,19 @@ class PPO(object):
             self._last_S = S
             first, self._predraw = _spec.take(self._predraw, S), None
         cfg.ppo_epoch = 1
+        stream, drawn0 = None, 0
+        if permutations is None:
+            # the remaining epochs' permutations are produced on helper threads while the epochs' kernels run
+            # (host_sampler.PermutationStream: the same mt19937 stream torch.randperm would consume)
+            if first is not None:
+                self._stage[0].copy_(first)
+                drawn0 = 1
+            stream = host_sampler.PermutationStream(S, self.ppo_epoch - drawn0, self._stage[drawn0:])
         for e in range(self.ppo_epoch):
             if permutations is not None:
                 self._stage[e].copy_(permutations[e])
-            else:
-                self._stage[e].copy_(first if (e == 0 and first is not None) else torch.randperm(S))
+            elif e >= drawn0:
+                stream.wait(e - drawn0)
             self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
             cfg.first_adam_step = opt.step_count + 1 + e * nmb
             tok = _lib.timer.start("ppo_update")
@@ -184,6 +192,8 @@ class PPO(object):
             rc = lib.sg_split_ppo_update(*args, stream) if is_split else lib.sg_ppo_update(*args, cb, user, stream)
             _lib.timer.stop(tok)
             _lib.check(rc, "sg_ppo_update")
+        if stream is not None:
+            stream.finish()             # the CPU default generator is now where ppo_epoch torch.randperm(S) calls leave it
         cfg.ppo_epoch = self.ppo_epoch
         opt.step_count += n_steps
 

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libsimgan_b200.so")
-SOURCES = ["sg_api.cu", "sg_rollout.cu", "sg_ppo.cu", "sg_disc.cu", "sg_dp.cu", "sg_split.cu", "sg_mma_test.cu"]
+SOURCES = ["sg_api.cu", "sg_rollout.cu", "sg_ppo.cu", "sg_disc.cu", "sg_dp.cu", "sg_split.cu", "sg_mma_test.cu", "sg_host.cu"]
 HEADERS = ["sg_common.cuh", "sg_policy.cuh", "sg_colgemm.cuh", "sg_disc_reg.cuh", "sg_dp.cuh", "sg_mma.cuh", "sg_ppo_mma.cuh", os.path.join("..", "..", "include", "simgan_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"] + os.environ.get("SG_NVCC_EXTRA", "").split()

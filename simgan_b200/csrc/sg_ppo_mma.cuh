@@ -517,6 +517,27 @@ __device__ __forceinline__ void mma_store_dw(uint32_t tbase, uint32_t dcol, int 
 #define SG_MMA_LAP()
 #endif
 
+// Pull the observation (and action) rows of a later job of this CTA towards L2 while the current one computes: the gather at
+// the head of a job is a burst of dependent, randomly placed HBM reads with nothing to overlap them with.
+template <int MR>
+__device__ __forceinline__ void ppo_mma_prefetch_rows(const PpoArgs& a, int step, int tile, int net) {
+    const int tid = threadIdx.x;
+    if (tid >= MR) return;
+    const int epoch = step / a.nmb, mb = step - epoch * a.nmb;
+    const int row = a.row_begin + tile * MR + tid;
+    if (row >= a.row_end) return;
+    const int i = (a.perm + (size_t)epoch * a.S + (size_t)mb * a.mbs)[row];
+    const char* p = reinterpret_cast<const char*>(a.obs + (size_t)i * a.O);
+    const int bytes = a.O * 4;
+    for (int off = 0; off < bytes; off += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + bytes - 4));
+    if (net == 0) {
+        const char* q = reinterpret_cast<const char*>(a.actions + (size_t)i * a.A);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q + a.A * 4 - 4));
+    }
+}
+
 // ---- one job ------------------------------------------------------------------------------------------------------------------
 // first: no earlier job of this CTA in this optimizer step (gradient accumulators start from zero)
 template <int MR>
@@ -769,7 +790,7 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     SG_MMA_LAP();   // 9: G5 + E5
     // dW2(n, k) = sum_rows dZ2(row, n) H1(row, k); with two unit blocks the N extent is halved as well (stage capacity)
     {
-        const int nsplit = d.nblk > 1 ? 2 : 1, Nh = H / nsplit;
+        const int nsplit = (d.nblk > 1 && 2 * 8 * 8 * (d.Mb + H) > d.ring) ? 2 : 1, Nh = H / nsplit;      // two stages of K = 8 must fit
         for (int b = 0; b < d.nblk; ++b)
             for (int h = 0; h < nsplit; ++h) {
                 mma_gemm(S, P, RB, MRP, tbase, d.tacc ? d.c_dw2 : 0, d.Mb, Nh, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H),
@@ -842,6 +863,8 @@ __device__ void ppo_phaseA_mma(const PpoArgs& a, const MmaDims& d, MmaSmem& S, M
     float* gout = a.gpart + (size_t)cta * a.P;
     bool first = true;
     for (int job = cta; job < njobs; job += ncta) {
+        if (job + ncta < njobs) ppo_mma_prefetch_rows<MR>(a, step, (job + ncta) >> 1, net);
+        else if (step + 1 < a.nsteps) ppo_mma_prefetch_rows<MR>(a, step + 1, cta >> 1, net);
         ppo_mma_job<MR>(a, d, S, P, tbase, step, job >> 1, net, gout, first);
         first = false;
     }

@@ -433,3 +433,46 @@ def test_predraw_swallows_errors_and_rewinds():
     got = _spec.take(slot, "k")
     torch.set_rng_state(before)
     assert torch.equal(got, torch.rand(2))
+
+
+# ---- host sampler: the torch.randperm stream of the CPU default generator, produced by csrc/sg_host.cu ----------------------
+@pytest.mark.parametrize("n,k", [(1 << 17, 3), (300001, 2), (1, 2), (5, 4)])
+def test_permutation_stream_equals_torch_randperm(n, k):
+    """Values AND generator state: feed_forward_generator's sampler draws (A2C/storage.py:158-162) must stay bit-exact."""
+    from simgan_b200 import host_sampler as hs
+    assert hs.usable()
+    torch.manual_seed(11)
+    torch.rand(3)                                   # some earlier consumer
+    start = torch.get_rng_state()
+    want = [torch.randperm(n) for _ in range(k)]
+    tail_want = torch.rand(5)                       # a later consumer sees the same stream
+    torch.set_rng_state(start)
+    out = torch.empty(k, n, dtype=torch.int32)
+    old_min, hs.MIN_ELEMENTS = hs.MIN_ELEMENTS, 1   # force the C stream for the tiny sizes too
+    try:
+        ps = hs.PermutationStream(n, k, out)
+        for e in range(k):
+            got = ps.wait(e)
+            assert torch.equal(got.long(), want[e])
+        ps.finish()
+    finally:
+        hs.MIN_ELEMENTS = old_min
+    assert torch.equal(torch.rand(5), tail_want)
+
+
+def test_permutation_stream_small_sizes_use_torch():
+    from simgan_b200 import host_sampler as hs
+    torch.manual_seed(3)
+    want = [torch.randperm(100) for _ in range(2)]
+    after = torch.get_rng_state()
+    torch.manual_seed(3)
+    out = torch.empty(2, 100, dtype=torch.int32)
+    ps = hs.PermutationStream(100, 2, out)
+    assert ps._h is None
+    ps.finish()
+    assert torch.equal(out[0].long(), want[0]) and torch.equal(out[1].long(), want[1])
+    assert torch.equal(torch.get_rng_state(), after)
+    torch.manual_seed(4)
+    a = hs.randperm_i32(1 << 17)
+    torch.manual_seed(4)
+    assert a.dtype == torch.int32 and torch.equal(a.long(), torch.randperm(1 << 17))
