@@ -273,7 +273,11 @@ int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int pas
  * walks of different permutations concurrently.  Returns a handle, or NULL (sg_last_error).
  * sg_host_randperm_wait: block until permutation e is complete in out[e*n .. (e+1)*n).
  * sg_host_randperm_end: join, write the engine state after the last draw (what torch.set_rng_state must receive so that the
- * generator is where n_perms torch.randperm(n) calls would have left it), free the handle. */
+ * generator is where n_perms torch.randperm(n) calls would have left it), free the handle.
+ * sg_host_randperm_prefix: synchronous; the first m elements of ONE torch.randperm(n) (what a zip() with a shorter loader
+ * consumes of it, third_party/a2c_ppo_acktr/algo/gail.py:159-166) while the engine still advances by all n-1 draws. */
+int sg_host_randperm_prefix(const uint32_t* mt_key, int mt_pos, int64_t n, int64_t m, int32_t* out, uint32_t* mt_key_out,
+                            int* mt_pos_out);
 void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int n_perms, int32_t* out, int n_threads);
 int sg_host_randperm_wait(void* handle, int e);
 int sg_host_randperm_end(void* handle, uint32_t* mt_key_out, int* mt_pos_out);

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .. import _lazy, _lib, _spec
+from .. import _lazy, _lib, _spec, host_sampler
 from ..running_mean_std import RunningMeanStd
 from .adam import FusedAdam
 
@@ -145,9 +145,9 @@ class Discriminator(nn.Module):
         gen = torch.Generator()
         gen.manual_seed(seed)
         e_perm = torch.randperm(n_expert, generator=gen)
-        p_perm = torch.randperm(n_rollout)
+        p_perm = host_sampler.randperm_prefix(n_rollout, n * batch_size)     # == torch.randperm(n_rollout)[:n*B], same consumption
         alpha = torch.rand(n * batch_size)          # == n consecutive torch.rand(B,1) draws (tests pin this)
-        return (e_perm[:n * batch_size].view(n, batch_size), p_perm[:n * batch_size].view(n, batch_size),
+        return (e_perm[:n * batch_size].view(n, batch_size), p_perm.view(n, batch_size),
                 alpha.view(n, batch_size))
 
     # ---- early index draws (simgan_b200/_spec.py) -----------------------------------------------------------------

@@ -169,19 +169,19 @@ class PPO(object):
             self._last_S = S
             first, self._predraw = _spec.take(self._predraw, S), None
         cfg.ppo_epoch = 1
-        stream, drawn0 = None, 0
+        pstream, drawn0 = None, 0
         if permutations is None:
             # the remaining epochs' permutations are produced on helper threads while the epochs' kernels run
             # (host_sampler.PermutationStream: the same mt19937 stream torch.randperm would consume)
             if first is not None:
                 self._stage[0].copy_(first)
                 drawn0 = 1
-            stream = host_sampler.PermutationStream(S, self.ppo_epoch - drawn0, self._stage[drawn0:])
+            pstream = host_sampler.PermutationStream(S, self.ppo_epoch - drawn0, self._stage[drawn0:])
         for e in range(self.ppo_epoch):
             if permutations is not None:
                 self._stage[e].copy_(permutations[e])
             elif e >= drawn0:
-                stream.wait(e - drawn0)
+                pstream.wait(e - drawn0)
             self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
             cfg.first_adam_step = opt.step_count + 1 + e * nmb
             tok = _lib.timer.start("ppo_update")
@@ -192,8 +192,8 @@ class PPO(object):
             rc = lib.sg_split_ppo_update(*args, stream) if is_split else lib.sg_ppo_update(*args, cb, user, stream)
             _lib.timer.stop(tok)
             _lib.check(rc, "sg_ppo_update")
-        if stream is not None:
-            stream.finish()             # the CPU default generator is now where ppo_epoch torch.randperm(S) calls leave it
+        if pstream is not None:
+            pstream.finish()             # the CPU default generator is now where ppo_epoch torch.randperm(S) calls leave it
         cfg.ppo_epoch = self.ppo_epoch
         opt.step_count += n_steps
 

@@ -50,6 +50,16 @@ struct Mt19937 {
         y ^= y >> 18;
         return y;
     }
+    // advance by count draws without producing them
+    void discard(int64_t count) {
+        while (count > 0) {
+            if (pos >= 624) regenerate();
+            int64_t take = 624 - pos;
+            if (take > count) take = count;
+            pos += (int)take;
+            count -= take;
+        }
+    }
     void fill(uint32_t* out, int64_t count) {
         int64_t i = 0;
         while (i < count) {
@@ -155,6 +165,33 @@ void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int 
     j->gen = std::thread([j] { j->generator(); });
     for (int t = 0; t < n_threads; ++t) j->workers.emplace_back([j] { j->worker(); });
     return j;
+}
+
+int sg_host_randperm_prefix(const uint32_t* mt_key, int mt_pos, int64_t n, int64_t m, int32_t* out, uint32_t* mt_key_out,
+                            int* mt_pos_out) {
+    SG_REQUIRE(mt_key && out && n >= 1 && m >= 0 && m <= n && mt_pos >= 0 && mt_pos <= 624 && n < (int64_t)(0xffffffffu / 20u),
+               "sg_host_randperm_prefix: bad arguments");
+    Mt19937 mt;
+    std::memcpy(mt.key, mt_key, sizeof(mt.key));
+    mt.pos = mt_pos;
+    // element i of the result is final after step i of the walk, and step i only reads positions >= i: the first m elements
+    // need the first min(m, n-1) steps; the remaining draws only move the engine
+    const int64_t steps = m < n - 1 ? m : n - 1;
+    std::vector<uint32_t> d((size_t)steps);
+    mt.fill(d.data(), steps);
+    mt.discard(n - 1 - steps);
+    std::vector<int32_t> r((size_t)n);
+    for (int64_t i = 0; i < n; ++i) r[i] = (int32_t)i;
+    for (int64_t i = 0; i < steps; ++i) {
+        const int64_t j = i + d[i] % (uint32_t)(n - i);
+        const int32_t sav = r[i];
+        r[i] = r[j];
+        r[j] = sav;
+    }
+    std::memcpy(out, r.data(), (size_t)m * sizeof(int32_t));
+    if (mt_key_out) std::memcpy(mt_key_out, mt.key, sizeof(mt.key));
+    if (mt_pos_out) *mt_pos_out = mt.pos;
+    return SG_OK;
 }
 
 int sg_host_randperm_wait(void* handle, int e) {

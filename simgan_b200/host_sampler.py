@@ -107,6 +107,23 @@ def randperm_i32(n):
     return out[0]
 
 
+def randperm_prefix(n, m):
+    """``torch.randperm(n)[:m]`` as int64 with the generator advanced by the whole draw: what ``zip(expert_loader,
+    feed_forward_generator)`` consumes of the rollout sampler's permutation when the expert loader is the shorter one
+    (third_party/a2c_ppo_acktr/algo/gail.py:159-166)."""
+    if n < MIN_ELEMENTS or not usable():
+        return torch.randperm(n)[:m]
+    state = torch.get_rng_state()
+    key, pos, _ = _unpack(state)
+    out = torch.empty(max(m, 1), dtype=torch.int32)
+    k2 = np.empty(624, dtype=np.uint32)
+    p2 = C.c_int(0)
+    _lib.check(_lib.lib().sg_host_randperm_prefix(key.ctypes.data, pos, n, m, out.data_ptr(), k2.ctypes.data, C.byref(p2)),
+               "sg_host_randperm_prefix")
+    torch.set_rng_state(_pack(state, k2, p2.value))
+    return out[:m].long()
+
+
 def usable():
     """One-time self-test: the C stream equals torch.randperm (values and generator state) on this torch build."""
     global _usable

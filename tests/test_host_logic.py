@@ -476,3 +476,15 @@ def test_permutation_stream_small_sizes_use_torch():
     a = hs.randperm_i32(1 << 17)
     torch.manual_seed(4)
     assert a.dtype == torch.int32 and torch.equal(a.long(), torch.randperm(1 << 17))
+
+
+@pytest.mark.parametrize("n,m", [(1 << 17, 16384), (200003, 200003), (1 << 17, 0), (150000, 1)])
+def test_randperm_prefix_equals_torch(n, m):
+    from simgan_b200 import host_sampler as hs
+    torch.manual_seed(21)
+    want = torch.randperm(n)[:m]
+    tail = torch.rand(4)
+    torch.manual_seed(21)
+    got = hs.randperm_prefix(n, m)
+    assert got.dtype == torch.int64 and torch.equal(got, want)
+    assert torch.equal(torch.rand(4), tail)
