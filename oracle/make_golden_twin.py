@@ -1,0 +1,79 @@
+"""Write tests/golden/twin_gail_dyn_ppo.npz: what the reference's REAL main() (oracle/run_reference_main.py) logs and
+checkpoints over three outer iterations on the fake vec-env -- the fixture tests/test_gpu_twin.py holds this package's
+CUDA run of the same loop against.  TEST INFRASTRUCTURE; dev container only (needs /root/reference).
+
+    python oracle/make_golden_twin.py
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from oracle import run_reference_main as rrm  # noqa: E402
+import fake_env  # noqa: E402
+
+EXPERT = os.path.join(ROOT, "tests", "golden", "mini_expert.pkl")
+# one place for the run's command line: the twin tests build their args namespace from the same dict
+TWIN_CFG = dict(seed=1, num_processes=4, num_steps=32, num_mini_batch=4, ppo_epoch=3, gail_epoch=2, gail_batch_size=16,
+                hidden_size=64, gail_traj_num=3, gail_downsample_frequency=1, gail_dis_hdim=100, num_env_steps=3 * 32 * 4,
+                save_interval=1, log_interval=1, env_seed=5, noise_seed=9)
+LOG_KEYS = ("j", "total_num_steps", "n_episodes", "mean_reward", "median_reward", "min_reward", "max_reward", "dist_entropy",
+            "value_loss", "action_loss", "recent_gail_r", "gail_loss", "gail_loss_e", "gail_loss_p")
+
+
+def argv(save_dir, cfg=TWIN_CFG):
+    return ["--env-name", "FakeCombinedEnv-v1", "--algo", "ppo", "--no-cuda", "--gail", "--gail-dyn",
+            "--seed", str(cfg["seed"]), "--num-processes", str(cfg["num_processes"]), "--num-steps", str(cfg["num_steps"]),
+            "--num-mini-batch", str(cfg["num_mini_batch"]), "--ppo-epoch", str(cfg["ppo_epoch"]),
+            "--gail-epoch", str(cfg["gail_epoch"]), "--gail-batch-size", str(cfg["gail_batch_size"]),
+            "--hidden-size", str(cfg["hidden_size"]), "--gail-traj-path", EXPERT, "--gail-traj-num", str(cfg["gail_traj_num"]),
+            "--gail-downsample-frequency", str(cfg["gail_downsample_frequency"]), "--gail-dis-hdim", str(cfg["gail_dis_hdim"]),
+            "--num-env-steps", str(cfg["num_env_steps"]), "--save-interval", str(cfg["save_interval"]),
+            "--log-interval", str(cfg["log_interval"]), "--save-dir", save_dir, "--log-dir", os.path.join(save_dir, "log")]
+
+
+def run_reference(save_dir, cfg=TWIN_CFG):
+    noise = fake_env.SamplingNoise(cfg["noise_seed"])
+    logs, save_path = rrm.run(argv(save_dir, cfg), lambda n, dev: fake_env.FakeVecEnv(n, dev, seed=cfg["env_seed"]), noise,
+                              save_dir)
+    return logs, save_path
+
+
+def checkpoint_params(save_path, j, bound):
+    """state_dicts of the policy and the discriminator the run saved after update j (whole-object pickles of the
+    reference's classes: loaded with its modules bound)."""
+    with bound:
+        pol, ob_rms = torch.load(os.path.join(save_path, "FakeCombinedEnv-v1_%d.pt" % j), weights_only=False)
+        disc = torch.load(os.path.join(save_path, "FakeCombinedEnv-v1_%d_D.pt" % j), weights_only=False)
+        assert ob_rms is None
+        return ({k: v.clone() for k, v in pol.state_dict().items()}, {k: v.clone() for k, v in disc.trunk.state_dict().items()})
+
+
+def main():
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        logs, save_path = run_reference(tmp)
+        n_upd = TWIN_CFG["num_env_steps"] // TWIN_CFG["num_steps"] // TWIN_CFG["num_processes"]
+        assert len(logs) == n_upd, (len(logs), n_upd)
+        out["logs"] = np.array([[d[k] for k in LOG_KEYS] for d in logs], dtype=np.float64)
+        for j in range(n_upd):
+            pol, disc = checkpoint_params(save_path, j, rrm.bound_reference())
+            for k, v in pol.items():
+                out["pol%d_%s" % (j, k)] = v.numpy()
+            for k, v in disc.items():
+                out["disc%d_%s" % (j, k)] = v.numpy()
+    path = os.path.join(ROOT, "tests", "golden", "twin_gail_dyn_ppo.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, "logs:\n", out["logs"])
+
+
+if __name__ == "__main__":
+    main()
