@@ -12,7 +12,7 @@ from .running_mean_std import RunningMeanStd  # noqa: F401
 from . import algo  # noqa: F401
 from .algo import PPO  # noqa: F401
 from .algo.gail import Discriminator  # noqa: F401
-from .feed import RolloutFeeder  # noqa: F401
+from .feed import RolloutFeeder, ReturnNormalizer  # noqa: F401
 from .expert_data import load_sas_wpast_from_pickle, select_and_merge_sas, expert_tensor  # noqa: F401
 
 __version__ = "0.1.0"

@@ -77,3 +77,30 @@ class RolloutFeeder(object):
         out = self._launch(s, deterministic)
         self.rs.step = (s + 1) % self.T
         return out
+
+
+class ReturnNormalizer(object):
+    """The reward scaling the reference's vec-env applies before the rollout buffer sees a reward
+    (``VecNormalize(envs, gamma=gamma, ob=False)``, third_party/a2c_ppo_acktr/envs.py:120-125;
+    third_party/a2c_ppo_acktr/baselines/common/vec_env/vec_normalize.py:50-58): a discounted running return per env,
+    its running variance (``RunningMeanStd(shape=())``), reward / sqrt(var + eps) clipped to +-cliprew, return reset
+    where an episode ended.  N numbers per env step on the host, NumPy float64 like the reference (the values are
+    bit-identical to the reference class given the same NumPy); it sits where the env outputs are packed for the feed
+    (``RolloutFeeder.step(..., reward=normalizer(reward, done))``) and is what the policy-refinement driver
+    (third_party/a2c_ppo_acktr/main.py) trains on.  ``ret_rms`` is exposed under the reference's name."""
+
+    def __init__(self, num_envs, gamma=0.99, cliprew=10.0, epsilon=1e-8):
+        from .running_mean_std import RunningMeanStd
+        self.ret_rms = RunningMeanStd(shape=())
+        self.ret = np.zeros(num_envs)
+        self.gamma, self.cliprew, self.epsilon = gamma, cliprew, epsilon
+
+    def __call__(self, rews, news):
+        self.ret = self.ret * self.gamma + rews
+        self.ret_rms.update(self.ret)
+        rews = np.clip(rews / np.sqrt(self.ret_rms.var + self.epsilon), -self.cliprew, self.cliprew)
+        self.ret[np.asarray(news, dtype=bool)] = 0.
+        return rews
+
+    def reset(self):
+        self.ret = np.zeros_like(self.ret)

@@ -24,7 +24,11 @@ class Box(_Space):          # the reference dispatches on ``action_space.__class
 
 
 class FakeVecEnv(object):
-    def __init__(self, num_processes, device, seed=0, obs_dim=11, act_dim=3, s_dim=11, a_dim=3, window=10, ep_len=9):
+    def __init__(self, num_processes, device, seed=0, obs_dim=11, act_dim=3, s_dim=11, a_dim=3, window=10, ep_len=9,
+                 reward_filter=None):
+        # reward_filter(rews, news) -> rews: the VecNormalize return scaling of envs.py:120-125, which sits between the raw
+        # envs and VecPyTorch in the reference's wrapper chain
+        self.reward_filter = reward_filter
         self.N, self.device, self.seed = int(num_processes), device, int(seed)
         self.O, self.A, self.s_dim, self.a_dim, self.W, self.ep_len = obs_dim, act_dim, s_dim, a_dim, window, ep_len
         self.observation_space = _Space((obs_dim,))
@@ -54,6 +58,8 @@ class FakeVecEnv(object):
         win = r.standard_normal((self.N, self.W, self.s_dim + self.a_dim)) * 0.5
         s_next = r.standard_normal((self.N, self.s_dim)) * 0.5
         done = np.array([(t + 3 * i) % self.ep_len == 0 for i in range(self.N)])
+        if self.reward_filter is not None:
+            reward = np.asarray(self.reward_filter(reward, done))
         infos = []
         for i in range(self.N):
             info = {"sas_window": [list(win[i, k, :self.s_dim]) for k in range(self.W)] +

@@ -165,3 +165,53 @@ def test_gail_dyn_ppo_driver_with_split_policy(tmp_path):
     assert type(pol_cpu).__name__ == "SplitPolicy"
     for a, b in zip(pol_cpu.state_dict().values(), actor_critic.state_dict().values()):
         assert torch.equal(a, b.cpu())
+
+
+def test_policy_refinement_driver_matches_the_reference_run(tmp_path):
+    """Second shipped command (train_hopper_deform.sh:7 -> third_party/a2c_ppo_acktr/main.py:69-88, 199-268): a warm-started
+    policy gets reset_critic + reset_variance, then PPO with --use-linear-lr-decay --clip-param 0.1 --ppo-epoch 2
+    --num-mini-batch 8 --lr 1.5e-4 --entropy-coef 0 on rewards scaled by the vec-env's return normaliser
+    (VecNormalize(envs, gamma), here simgan_b200.ReturnNormalizer).  Held against the REAL main.py run of the reference
+    (tests/golden/twin_policy_refinement.npz)."""
+    import simgan_b200 as sg
+    z = np.load(os.path.join(HERE, "golden", "twin_policy_refinement.npz"))
+    cfg = dict(seed=3, num_processes=4, num_steps=32, num_mini_batch=8, ppo_epoch=2, lr=1.5e-4, entropy_coef=0.0,
+               clip_param=0.1, hidden_size=64, num_env_steps=3 * 32 * 4, save_interval=1, log_interval=1,
+               warm_start_logstd=-1.0, use_linear_lr_decay=True, gamma=0.99)
+    # the warm-start checkpoint: the parameters the reference's GAIL run ended with, as a whole-object pickle of OUR class
+    warm = sg.Policy((11,), fake_env.Box((3,)), base_kwargs={"recurrent": False, "hidden_size": 64})
+    sd = warm.state_dict()
+    for k in sd:
+        sd[k] = torch.from_numpy(z["warm_" + k])
+    warm.load_state_dict(sd)
+    warm_path = str(tmp_path / "warm.pt")
+    torch.save([warm, None], warm_path)
+
+    compat.install()
+    try:
+        M = caller_namespace()
+        args = twin_main.default_args(cuda=True, warm_start=warm_path, save_dir=str(tmp_path), **cfg)
+        envs = fake_env.FakeVecEnv(4, torch.device("cuda:0"), seed=6, reward_filter=sg.ReturnNormalizer(4, gamma=0.99))
+        logs = []
+        with replay_sampling_noise(10):
+            actor_critic, agent, rollouts = twin_main.policy_refinement(args, envs, M, logs.append)
+    finally:
+        compat.uninstall()
+    keys = ("j", "total_num_steps", "n_episodes", "mean_reward", "median_reward", "min_reward", "max_reward", "dist_entropy",
+            "value_loss", "action_loss")
+    assert len(logs) == 3
+    assert [round(d["lr"], 12) for d in logs] == [round(1.5e-4 * (1 - j / 3.0), 12) for j in range(3)]      # utils.py:68-72
+    for row, d in zip(z["logs"], logs):
+        w = dict(zip(keys, row))
+        tol = 1e-4 if w["j"] == 0 else 2e-3
+        assert d["n_episodes"] == w["n_episodes"]
+        for k in ("dist_entropy", "value_loss"):
+            assert abs(d[k] - w[k]) <= tol * abs(w[k]), (w["j"], k, d[k], w[k])
+        assert abs(d["action_loss"] - w["action_loss"]) <= tol * max(abs(w["action_loss"]), 0.05), (w["j"], d["action_loss"])
+    worst = 0.0
+    for k, v in actor_critic.state_dict().items():
+        worst = max(worst, float((v.cpu() - torch.from_numpy(z["pol2_" + k])).abs().max()))
+    assert worst < 3e-3, worst
+    # the critic really was re-initialised (main.py:84) and the log-std reset (main.py:85-86) before training moved them
+    assert not np.allclose(z["warm_base.critic.0.weight"], z["pol0_base.critic.0.weight"], atol=1e-2)
+    assert abs(float(actor_critic.dist.logstd._bias.mean()) + 1.0) < 0.05

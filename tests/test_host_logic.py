@@ -488,3 +488,28 @@ def test_randperm_prefix_equals_torch(n, m):
     got = hs.randperm_prefix(n, m)
     assert got.dtype == torch.int64 and torch.equal(got, want)
     assert torch.equal(torch.rand(4), tail)
+
+
+def test_return_normalizer_restated():
+    """ReturnNormalizer vs a direct restatement of vec_normalize.py:50-58 (runs on the GPU box too, where the reference's
+    class is not available; tests/test_twin_vs_reference.py holds it against the real class)."""
+    n, gamma, eps, clip = 6, 0.99, 1e-8, 10.0
+    ours = sg.ReturnNormalizer(n, gamma=gamma)
+    ret = np.zeros(n)
+    mean, var, count = 0.0, 1.0, 1e-4
+    rs = np.random.RandomState(1)
+    for t in range(100):
+        rews = rs.standard_normal(n).astype(np.float32) * 3
+        news = rs.rand(n) < 0.15
+        ret = ret * gamma + rews
+        bm, bv, bc = np.mean(ret, axis=0), np.var(ret, axis=0), ret.shape[0]
+        delta = bm - mean
+        tot = count + bc
+        new_mean = mean + delta * bc / tot
+        m2 = var * count + bv * bc + np.square(delta) * count * bc / tot
+        mean, var, count = new_mean, m2 / tot, tot
+        want = np.clip(rews / np.sqrt(var + eps), -clip, clip)
+        ret[news] = 0.0
+        got = ours(rews, news)
+        assert np.array_equal(got, want), t
+    assert ours.ret_rms.count == count and ours.ret_rms.var == var

@@ -73,3 +73,59 @@ def test_real_main_equals_twin_and_golden(tmp_path):
         assert np.array_equal(z["pol2_" + k], v.numpy()), k
     for k, v in rd.items():
         assert np.array_equal(z["disc2_" + k], v.numpy()), k
+
+
+def test_real_main_py_equals_refinement_twin_and_golden(tmp_path):
+    """Same for the PPO-only refinement driver (third_party/a2c_ppo_acktr/main.py, second shipped command): warm start from
+    the checkpoint the GAIL run left, reset_critic + reset_variance, linear lr decay, VecNormalize'd rewards."""
+    from oracle import make_golden_twin as mg
+    from oracle import run_reference_main as rrm
+    import fake_env
+    import twin_main
+
+    _, gail_path = mg.run_reference(str(tmp_path / "gail"))
+    warm = os.path.join(gail_path, "FakeCombinedEnv-v1.pt")
+    cfg = mg.REFINE_CFG
+    real_logs, real_path = mg.run_reference_refinement(str(tmp_path / "real"), warm)
+
+    noise = fake_env.SamplingNoise(cfg["noise_seed"])
+    old_normal = torch.normal
+    twin_logs = []
+    args = twin_main.default_args(warm_start=warm, save_dir=str(tmp_path / "twin"),
+                                  **{k: v for k, v in cfg.items() if k not in ("env_seed", "noise_seed")})
+    envs = fake_env.FakeVecEnv(cfg["num_processes"], torch.device("cpu"), seed=cfg["env_seed"],
+                               reward_filter=rrm.reference_vec_normalize(cfg["num_processes"], cfg["gamma"]))
+    with rrm.bound_reference() as ref:
+        try:
+            torch.normal = lambda mean, std, **kw: mean + std * noise.next(mean.shape).to(mean.device)
+            twin_main.policy_refinement(args, envs, _reference_namespace(ref, rrm._safe_load_sas), twin_logs.append)
+        finally:
+            torch.normal = old_normal
+    assert len(twin_logs) == len(real_logs) == 3
+    for a, b in zip(twin_logs, real_logs):
+        for k in ("j", "n_episodes", "dist_entropy", "value_loss", "action_loss"):
+            assert a[k] == b[k], (k, a[k], b[k])
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "twin_policy_refinement.npz"))
+    assert np.array_equal(z["logs"], np.array([[d[k] for k in mg.REFINE_LOG_KEYS] for d in real_logs]))
+    for j in range(3):
+        rp = mg.policy_checkpoint(real_path, j, rrm.bound_reference())
+        tp = mg.policy_checkpoint(os.path.join(str(tmp_path / "twin"), "ppo"), j, rrm.bound_reference())
+        for k in rp:
+            assert torch.equal(rp[k], tp[k]), k
+            assert np.array_equal(z["pol%d_%s" % (j, k)], rp[k].numpy()), k
+
+
+def test_return_normalizer_equals_reference_vec_normalize():
+    """simgan_b200.feed.ReturnNormalizer against the reference's real VecNormalize(venv, gamma, ob=False) (envs.py:120-125,
+    vec_normalize.py:50-58): bit-identical rewards and running statistics over a stream with episode ends."""
+    from oracle import run_reference_main as rrm
+    import simgan_b200 as sg
+    ref_filter = rrm.reference_vec_normalize(5, 0.99)
+    ours = sg.ReturnNormalizer(5, gamma=0.99)
+    rs = np.random.RandomState(0)
+    for t in range(200):
+        rews = rs.standard_normal(5).astype(np.float32) * (1.0 + t % 7)
+        news = rs.rand(5) < 0.1
+        a = ref_filter(rews.copy(), news.copy())
+        b = ours(rews.copy(), news.copy())
+        assert a.dtype == b.dtype and np.array_equal(a, b), t
