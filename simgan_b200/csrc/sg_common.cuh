@@ -370,6 +370,7 @@ __device__ __forceinline__ void rowsum_store(float* __restrict__ g, const float*
 // barrier is written with st.cg and read with ld.cg (L2), so no L1 invalidation is needed.
 // A spin cap turns a lost barrier into an error flag instead of a hung GPU.
 // ------------------------------------------------------------------------------------------------
+constexpr long long kGridBarrierWaitNs = 90ll * 1000 * 1000 * 1000;      // 90 s (> the peer-exchange cap of sg_dp.cuh)
 struct GridBarrier {
     unsigned int* counter;
     unsigned int* error_flag;
@@ -382,16 +383,20 @@ struct GridBarrier {
             const unsigned int target = gen * nblocks;
             asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
             unsigned int seen;
-            long long spins = 0;
+            long long spins = 0, t_start = 0;
             // once any barrier has timed out every later one falls through: the kernel drains quickly and
-            // the host sees the poisoned trace
+            // the host sees the poisoned trace.  The cap is wall-clock (kGridBarrierWaitNs): with data parallelism a CTA
+            // may legitimately sit in the peer exchange for as long as the peer's host takes to launch its kernel
             bool dead = false;
             while (true) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
                 if (seen >= target) break;
                 if ((++spins & 1023) == 0) {
                     if (*(volatile unsigned int*)error_flag != 0u) dead = true;
-                    if (spins > (1ll << 22)) { atomicExch(error_flag, 1u); dead = true; }
+                    long long now;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                    if (t_start == 0) t_start = now;
+                    else if (now - t_start > kGridBarrierWaitNs) { atomicExch(error_flag, 1u); dead = true; }
                     if (dead) break;
                 }
             }

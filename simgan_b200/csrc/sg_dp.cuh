@@ -39,6 +39,8 @@ __device__ __forceinline__ uint4* dp_slot(const DpView& d, int owner, int parity
 // peers and leave the rank-ordered total in `grad` (and in scr (float*), when non-null, for narrow slices).
 // `stepid` strictly increases across steps and calls (and is never 0).  All NT threads of the CTA must call.
 // Ends with a CTA barrier.
+constexpr long long kDpWaitNs = 60ll * 1000 * 1000 * 1000;      // 60 s
+
 template <int NT>
 __device__ __forceinline__ void dp_exchange_slice(const DpView& d, float* __restrict__ grad, int p0, int p1, int slice,
                                                   unsigned int stepid, float* scr) {
@@ -69,14 +71,19 @@ __device__ __forceinline__ void dp_exchange_slice(const DpView& d, float* __rest
             } else {
                 const uint4* src = dp_slot(d, d.rank, parity, r) + (size_t)(p0 >> 1) + 2 * j;
                 uint4 lo, hi;
-                long long spins = 0;
+                // a peer may start its launch late (its host draws / uploads at its own pace): wait by the wall clock, not by a
+                // spin count, and only give up (error flag -> the trace is poisoned, the host raises) after kDpWaitNs
+                long long spins = 0, t_start = 0;
                 while (true) {
                     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "l"(src) : "memory");
                     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "l"(src + 1) : "memory");
                     if (lo.y == stepid && lo.w == stepid && hi.y == stepid && hi.w == stepid) break;
                     if ((++spins & 1023) == 0) {
                         if (*(volatile unsigned int*)d.error_flag != 0u) break;
-                        if (spins > (1ll << 24)) { atomicExch(d.error_flag, 1u); break; }
+                        long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t_start == 0) t_start = now;
+                        else if (now - t_start > kDpWaitNs) { atomicExch(d.error_flag, 1u); break; }
                     }
                 }
                 v = make_float4(__uint_as_float(lo.x), __uint_as_float(lo.z), __uint_as_float(hi.x), __uint_as_float(hi.z));

@@ -20,6 +20,20 @@ def _free_port():
     return port
 
 
+def _spawn(fn, args_of_port, nprocs):
+    """mp.spawn with a fresh rendezvous port; a port that got taken between the probe and the bind (EADDRINUSE) is retried."""
+    last = None
+    for _ in range(4):
+        try:
+            mp.spawn(fn, args=args_of_port(_free_port()), nprocs=nprocs, join=True)
+            return
+        except Exception as e:      # noqa: BLE001
+            if "EADDRINUSE" not in str(e) and "address already in use" not in str(e):
+                raise
+            last = e
+    raise last
+
+
 def _run_case(g, dp_on, dev, transport=None):
     import gpu_util as gu
     import simgan_b200 as sg
@@ -93,7 +107,7 @@ def test_data_parallel_matches_single_gpu(case, transport, tmp_path):
         pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
     world = min(n, int(os.environ.get("SG_DP_WORLD", "2")))
     out = str(tmp_path / "ok")
-    mp.spawn(_worker, args=(world, _free_port(), case, out, transport), nprocs=world, join=True)
+    _spawn(_worker, lambda port: (world, port, case, out, transport), world)
     assert os.path.exists(out)
 
 
