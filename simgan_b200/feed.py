@@ -17,9 +17,14 @@ from . import _lib
 class RolloutFeeder(object):
     def __init__(self, actor_critic, rollouts):
         self.ac, self.rs = actor_critic, rollouts
-        if type(actor_critic).__name__ != "Policy":
-            raise NotImplementedError("RolloutFeeder drives sg_rollout_feed, which reads the Policy (MLPBase + DiagGaussian) "
-                                      "parameter layout; use act() + insert() with %s" % type(actor_critic).__name__)
+        kind = type(actor_critic).__name__
+        if kind not in ("Policy", "SplitPolicy"):
+            raise NotImplementedError("RolloutFeeder knows the Policy (MLPBase + DiagGaussian) and SplitPolicy parameter "
+                                      "layouts; use act() + insert() with %s" % kind)
+        # Policy: insert + act fused in sg_rollout_feed.  SplitPolicy (model_split.py:39-95, what the shipped scripts train):
+        # the same staged block and the same two async copies, the insert as one sg_copy_blocks launch and the act as
+        # sg_split_forward writing straight into the buffer slots.
+        self.split = kind == "SplitPolicy"
         if not rollouts.obs.is_cuda:
             raise _lib.SgError("RolloutFeeder needs the rollout buffer on a CUDA device; there is no CPU fallback")
         self.dev = rollouts.obs.device
@@ -38,13 +43,46 @@ class RolloutFeeder(object):
         self.h_bad = h[o:o + N]
         self.action_dev = torch.empty(N, self.A, dtype=torch.float32, device=self.dev)
         self.action_host = torch.empty(N, self.A, dtype=torch.float32).pin_memory()
+        self._scratch_logp = torch.empty(N, 1, dtype=torch.float32, device=self.dev)
         self.done_event = torch.cuda.Event()
+
+    def _launch_split(self, step, noise):
+        import ctypes as C
+        rs, ac, lib = self.rs, self.ac, _lib.lib()
+        N, O, F, T = self.N, self.O, self.F, self.T
+        slot = step + 1
+        stream = _lib.current_stream()
+        if step >= 0:
+            st = self.stage_dev
+            srcs = [st[:N * O], st[N * O:N * (O + F)], st[N * (O + F):N * (O + F) + N], st[N * (O + F) + N:N * (O + F) + 2 * N],
+                    st[N * (O + F) + 2 * N:]]
+            dsts = [rs.obs[slot], rs.obs_feat[slot], rs.rewards[step], rs.masks[slot], rs.bad_masks[slot]]
+            keep = [(a, b) for a, b in zip(srcs, dsts) if a.numel() > 0]
+            n = len(keep)
+            src_p = (C.c_void_p * n)(*[_lib.ptr(a) for a, _ in keep])
+            dst_p = (C.c_void_p * n)(*[_lib.ptr(b) for _, b in keep])
+            cnt = (C.c_int * n)(*[a.numel() for a, _ in keep])
+            _lib.check(lib.sg_copy_blocks(src_p, dst_p, cnt, n, stream), "sg_copy_blocks")
+        last = slot >= T                                    # value of obs[T] doubles as next_value; no action slot there
+        logp = self._scratch_logp if last else rs.action_log_probs[slot]
+        rc = lib.sg_split_forward(_lib.ptr(ac.flat_params()), O, ac.hidden_size, ac.num_feet, _lib.ptr(rs.obs[slot]), N,
+                                  _lib.ptr(noise), None, _lib.ptr(rs.value_preds[slot]), _lib.ptr(self.action_dev),
+                                  _lib.ptr(logp), None, stream)
+        _lib.check(rc, "sg_split_forward")
+        if not last:
+            rs.actions[slot].copy_(self.action_dev)
 
     @_lib.on_device(lambda self, *a, **k: self.dev)
     def _launch(self, step, deterministic):
         rs, ac = self.rs, self.ac
         flat = ac.flat_params()
         noise = None if deterministic else torch.randn(self.N, self.A, device=self.dev, dtype=torch.float32)
+        if self.split:
+            self._launch_split(step, noise)
+            self.action_host.copy_(self.action_dev, non_blocking=True)
+            self.done_event.record()
+            self.done_event.synchronize()
+            return self.action_host.numpy()
         rc = _lib.lib().sg_rollout_feed(
             _lib.ptr(flat), self.O, ac.hidden_size, self.A, self.F, self.N, self.T, step,
             _lib.ptr(self.stage_dev) if step >= 0 else None, _lib.ptr(noise), _lib.ptr(rs.obs), _lib.ptr(rs.obs_feat),

@@ -100,3 +100,60 @@ def test_split_ppo_shared_memory_w2_copy_is_bit_identical(case):
         agent.update(_storage(g), permutations=g.t("ppo_perm"))
         outs.append((agent.last_trace.clone(), sp.flat_params().cpu().clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("case", SPLIT_CASES)
+def test_rollout_feeder_with_split_policy(case):
+    """RolloutFeeder driving the policy the shipped scripts train (model_split.py:39-95): against the drop-in calls
+    (SplitPolicy.act + RolloutStorage.insert, the same CUDA-generator stream) every buffer is bit-identical, and what the
+    step copies is bit-exact against the ORACLE's buffer_insert (A2C/storage.py:70-84)."""
+    import simgan_b200 as sg
+    g = SplitGolden(case)
+    sp = _make(g)
+    T, N, O, A, F = 6, 5, g.O, g.A, 9
+    rng = np.random.RandomState(4)
+    obs0 = rng.randn(N, O).astype(np.float32)
+    env = [(rng.randn(N, O).astype(np.float32), rng.randn(N).astype(np.float32), rng.rand(N) < 0.3, rng.rand(N) < 0.1,
+            rng.randn(N, F)) for _ in range(T)]
+
+    def fresh():
+        rs = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, F)
+        rs.to(DEV)
+        rs.obs[0].copy_(torch.from_numpy(obs0))
+        return rs
+    # drop-in calls (main_gail_dyn_ppo.py:209-236) + the oracle's insert on the host
+    rs_a = fresh()
+    buf = orc.new_buffer(T, N, O, A, F)
+    buf["obs"][0].copy_(torch.from_numpy(obs0))
+    torch.cuda.manual_seed(8)
+    step_o = 0
+    acts_a = []
+    for t in range(T):
+        with torch.no_grad():
+            value, action, logp, hxs = sp.act(rs_a.obs[rs_a.step], rs_a.recurrent_hidden_states[rs_a.step], rs_a.masks[rs_a.step])
+        acts_a.append(action.cpu())
+        obs, rew, done, bad, feat = env[t]
+        masks = torch.tensor([[0.0] if d else [1.0] for d in done])
+        bad_masks = torch.tensor([[0.0] if b else [1.0] for b in bad])
+        rs_a.insert(torch.from_numpy(obs).to(DEV), hxs, action, logp, value, torch.from_numpy(rew).unsqueeze(1), masks, bad_masks,
+                    torch.Tensor(feat))
+        step_o = orc.buffer_insert(buf, step_o, torch.from_numpy(obs), torch.zeros(N, 1), action.cpu(), logp.cpu(), value.cpu(),
+                                   torch.from_numpy(rew).unsqueeze(1), masks, bad_masks, torch.Tensor(feat))
+    # the feeder
+    rs_b = fresh()
+    torch.cuda.manual_seed(8)
+    feeder = sg.RolloutFeeder(sp, rs_b)
+    acts_b = [torch.from_numpy(feeder.begin().copy())]
+    for t in range(T):
+        obs, rew, done, bad, feat = env[t]
+        acts_b.append(torch.from_numpy(feeder.step(obs, rew, done, bad, feat).copy()))
+    for a, b in zip(acts_a, acts_b):
+        assert torch.equal(a, b)
+    for k in ("obs", "obs_feat", "recurrent_hidden_states", "rewards", "actions", "action_log_probs", "masks", "bad_masks"):
+        assert torch.equal(getattr(rs_a, k), getattr(rs_b, k)), k
+        assert torch.equal(getattr(rs_b, k).cpu(), buf[k]), k
+    assert torch.equal(rs_a.value_preds[:-1], rs_b.value_preds[:-1])
+    with torch.no_grad():
+        nv = sp.get_value(rs_a.obs[-1], None, None)
+    assert torch.equal(rs_b.value_preds[-1], nv)             # slot T already holds next_value
+    assert rs_b.step == rs_a.step == step_o == 0
