@@ -379,7 +379,7 @@ def run_cuda(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    env_steps = fake_env_collection(w) if (world == 1 and not c.get("split")) else None      # feed kernel: Policy layout only
+    env_steps = fake_env_collection(w) if world == 1 else None
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):

@@ -130,8 +130,11 @@ class PPO(object):
         cfg.row_begin, cfg.row_end = (0, mbs) if dp is None else dp.shard(mbs)
         p2p = dp is not None and dp.p2p_ok(mbs)
         if is_split and dp is not None and not p2p:
-            raise NotImplementedError("SplitPolicy data-parallel updates need the p2p transport and a minibatch size "
-                                      "divisible by the world size (there is no phased split kernel for the nccl callback)")
+            # SplitPolicy has no phased kernel for the nccl callback: where the in-kernel exchange cannot run (nccl transport, or
+            # a minibatch the world size does not divide) every rank computes the whole minibatch instead -- identical seeds
+            # and deterministic kernels keep the replicas bit-identical, exactly as under the "auto" policy
+            dp, self.last_sharded = None, False
+            cfg.row_begin, cfg.row_end = 0, mbs
         cfg.mode = self.kernel_mode if (dp is None or p2p) else 1
         if cfg.mode == 1 and p2p:
             cfg.mode = 0

@@ -484,31 +484,58 @@ __device__ __forceinline__ void mma_store_dwh(uint32_t tbase, uint32_t dcol, int
 __device__ __forceinline__ void red_add4(float* p, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-// G[(u0+m)*ld + c] for c < ncols, N accumulator columns.  acc: add to what an earlier job of this CTA stored -- one
-// fire-and-forget vector reduction per 16 bytes (the slot has a single writer, so the sum stays deterministic) instead of
-// a load-add-store round trip through L2
-__device__ __forceinline__ void mma_store_dw(uint32_t tbase, uint32_t dcol, int Mi, int N, int u0, float* __restrict__ gW, int ld, int ncols,
-                                             bool acc) {
+// G[(u0+m)*ld + c] for c < ncols, N accumulator columns (N % 32 == 0).  The accumulator comes out of tensor memory one ROW per
+// thread, but a row of G is what is contiguous in memory: written straight from there, every warp store would touch 32
+// different lines.  Each warp therefore turns its 32 x 32 block around in a private staging tile of the (idle) stage ring
+// (row pitch 36 floats: conflict-free for the float4 writes and for the float4 / scalar reads) and writes whole 128-byte row
+// segments.  acc: add to what an earlier job of this CTA stored -- fire-and-forget reductions (the slot has a single writer,
+// so the sum stays deterministic) instead of a load-add-store round trip through L2.  Ends with a CTA barrier.
+constexpr int kMmaStorePitch = 36;
+__device__ __forceinline__ void mma_store_dw(float* __restrict__ ring, uint32_t tbase, uint32_t dcol, int Mi, int N, int u0,
+                                             float* __restrict__ gW, int ld, int ncols, bool acc) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2;
+    const int nrows = Mi == 128 ? 32 : 16;              // accumulator rows held by this warp's lanes (M = 64: lanes 0-15)
+    const int rbase = nrows * q;
+    float* st = ring + warp * (32 * kMmaStorePitch);
     const bool vec = (ld & 3) == 0;
-    mma_epilogue(tbase, dcol, Mi, N, [&](int m, int c0, const float (&v)[16]) {
-        float* p = gW + (size_t)(u0 + m) * ld + c0;
-        if (vec) {
+    for (int c0 = 32 * half; c0 < N; c0 += 64) {
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            float v[16];
+            mma::tmem_ld16(tbase + ((uint32_t)(32 * q) << 16) + dcol + (uint32_t)(c0 + 16 * h2), v);
+            mma::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (c0 + 4 * j < ncols) {
-                    const float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    if (acc) red_add4(p + 4 * j, o);
-                    else __stcg(reinterpret_cast<float4*>(p) + j, o);
-                }
-        } else {
-            float old[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) old[j] = (acc && c0 + j < ncols) ? __ldcg(p + j) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (c0 + j < ncols) __stcg(p + j, v[j] + old[j]);
+                *reinterpret_cast<float4*>(st + lane * kMmaStorePitch + 16 * h2 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-    });
+        __syncwarp();
+        if (vec) {
+            const int cq = lane & 7, c = c0 + 4 * cq;
+            if (c < ncols) {
+                for (int r = lane >> 3; r < nrows; r += 4) {
+                    const float4 o = *reinterpret_cast<const float4*>(st + r * kMmaStorePitch + 4 * cq);
+                    float* p = gW + (size_t)(u0 + rbase + r) * ld + c;
+                    if (acc) red_add4(p, o);
+                    else __stcg(reinterpret_cast<float4*>(p), o);
+                }
+            }
+        } else {
+            const int c = c0 + lane;
+            if (c < ncols) {
+                for (int r = 0; r < nrows; ++r) {
+                    const float o = st[r * kMmaStorePitch + lane];
+                    float* p = gW + (size_t)(u0 + rbase + r) * ld + c;
+                    if (acc) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(o) : "memory");
+                    else __stcg(p, o);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    mma::fence_before_sync();
+    mma::fence_async_smem();            // the staging tiles were generic writes into the stage ring
+    __syncthreads();
 }
 
 #ifdef SG_MMA_PROFILE
@@ -795,7 +822,7 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
             for (int h = 0; h < nsplit; ++h) {
                 mma_gemm(S, P, RB, MRP, tbase, d.tacc ? d.c_dw2 : 0, d.Mb, Nh, MR, op_master_mn(S.H2, d.Mb, b * d.Mb, H),
                          op_master_mn(S.H1, Nh, h * Nh, H), accum);
-                if (!d.tacc) mma_store_dw(tbase, 0, d.Mb, Nh, b * d.Mb, gout + (net ? L.cw2 : L.aw2) + h * Nh, H, Nh, acc);
+                if (!d.tacc) mma_store_dw(S.stage0, tbase, 0, d.Mb, Nh, b * d.Mb, gout + (net ? L.cw2 : L.aw2) + h * Nh, H, Nh, acc);
             }
     }
     SG_MMA_LAP();   // 10: G6 + E6
@@ -816,7 +843,7 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
     for (int b = 0; b < d.nblk; ++b) {
         mma_gemm(S, P, RB, MRP, tbase, d.tacc ? d.c_dw1 : 0, d.Mb, d.Op32, MR, op_master_mn(S.H1, d.Mb, b * d.Mb, H),
                  op_master_mn(S.X, d.Op32, 0, d.Op8), accum);
-        if (!d.tacc) mma_store_dw(tbase, 0, d.Mb, d.Op32, b * d.Mb, gout + (net ? L.cw1 : L.aw1), O, O, acc);
+        if (!d.tacc) mma_store_dw(S.stage0, tbase, 0, d.Mb, d.Op32, b * d.Mb, gout + (net ? L.cw1 : L.aw1), O, O, acc);
     }
     SG_MMA_LAP();   // 12: G8 + E8
 #ifdef SG_MMA_PROFILE
@@ -871,8 +898,8 @@ __device__ void ppo_phaseA_mma(const PpoArgs& a, const MmaDims& d, MmaSmem& S, M
     if (d.tacc) {
         // the CTA's weight gradients of this step, accumulated in tensor memory over its jobs
         mma_store_dwh(tbase, d.c_dwh, d.Mb, 0, gout + (net ? L.vw : L.mw), H, NA, false);
-        mma_store_dw(tbase, d.c_dw2, d.Mb, H, 0, gout + (net ? L.cw2 : L.aw2), H, H, false);
-        mma_store_dw(tbase, d.c_dw1, d.Mb, d.Op32, 0, gout + (net ? L.cw1 : L.aw1), a.O, a.O, false);
+        mma_store_dw(S.stage0, tbase, d.c_dw2, d.Mb, H, 0, gout + (net ? L.cw2 : L.aw2), H, H, false);
+        mma_store_dw(S.stage0, tbase, d.c_dw1, d.Mb, d.Op32, 0, gout + (net ? L.cw1 : L.aw1), a.O, a.O, false);
     }
     for (int i = tid; i < H; i += kStepThreads) {
         __stcg(gout + (net ? L.cb1 : L.ab1) + i, S.GB1[i]);
