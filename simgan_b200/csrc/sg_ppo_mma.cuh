@@ -216,8 +216,11 @@ __device__ __forceinline__ void mma_plan(const MmaOperand& op, int MRP, int ftid
             pl.src[i] = kq * MRP + e;
             pl.dst[i] = gi << 2;
         } else {
-            // MN-major: lanes walk (kk = 4 k-rows, eq8 = 8 quads of one 32-element block): conflict-free stores of whole atoms
-            const int kk = gi & 3, eq8 = (gi >> 2) & 7, t = gi >> 5;
+            // MN-major: a warp covers one atom (4 k-rows x 32 elements); the 8 lanes of a quarter-warp share the k-row and take
+            // the 8 element quads: their master granules (c/4)*MRP + k are 8 different 16-byte bank groups (MRP is odd) and so
+            // are their swizzled destinations -- conflict-free on both sides (lanes walking k fastest gave 2-way conflicts on
+            // the loads)
+            const int kk = (gi >> 3) & 3, eq8 = gi & 7, t = gi >> 5;
             const int EB = op.E >> 5;
             const int kb = t / EB, eb = t - kb * EB;
             const int k = 4 * kb + kk, e = 32 * eb + 4 * eq8;
