@@ -40,11 +40,16 @@ def argv(save_dir, cfg=TWIN_CFG):
             "--log-interval", str(cfg["log_interval"]), "--save-dir", save_dir, "--log-dir", os.path.join(save_dir, "log")]
 
 
-def run_reference(save_dir, cfg=TWIN_CFG):
+def run_reference(save_dir, cfg=TWIN_CFG, extra_argv=(), act_dim=3):
     noise = fake_env.SamplingNoise(cfg["noise_seed"])
-    logs, save_path = rrm.run(argv(save_dir, cfg), lambda n, dev: fake_env.FakeVecEnv(n, dev, seed=cfg["env_seed"]), noise,
-                              save_dir)
+    logs, save_path = rrm.run(argv(save_dir, cfg) + list(extra_argv),
+                              lambda n, dev: fake_env.FakeVecEnv(n, dev, seed=cfg["env_seed"], act_dim=act_dim), noise, save_dir)
     return logs, save_path
+
+
+# what train_hopper_deform.sh:5 trains: --use-split-pi (model_split.py), one foot (7 action dims), hidden 100 here
+SPLIT_ARGV = ("--use-split-pi", "--num-feet", "1")
+SPLIT_CFG = dict(TWIN_CFG, hidden_size=100)
 
 
 def checkpoint_params(save_path, j, bound):
@@ -106,6 +111,19 @@ def main():
                 rout["pol%d_%s" % (j, k)] = v.numpy()
         for k, v in checkpoint_params(save_path, 2, rrm.bound_reference())[0].items():
             rout["warm_" + k] = v.numpy()
+        # ---- the GAIL driver with SplitPolicy ------------------------------------------------------------------------------
+        stmp = os.path.join(tmp, "split")
+        slogs, spath = run_reference(stmp, SPLIT_CFG, SPLIT_ARGV, act_dim=7)
+        assert len(slogs) == 3
+        sout = {"logs": np.array([[d[k] for k in LOG_KEYS] for d in slogs], dtype=np.float64)}
+        spol, sdisc = checkpoint_params(spath, 2, rrm.bound_reference())
+        for k, v in spol.items():
+            sout["pol2_" + k] = v.numpy()
+        for k, v in sdisc.items():
+            sout["disc2_" + k] = v.numpy()
+        spath_npz = os.path.join(ROOT, "tests", "golden", "twin_gail_dyn_ppo_split.npz")
+        np.savez_compressed(spath_npz, **sout)
+        print("wrote", spath_npz, "logs:\n", sout["logs"])
         rpath_npz = os.path.join(ROOT, "tests", "golden", "twin_policy_refinement.npz")
         np.savez_compressed(rpath_npz, **rout)
         print("wrote", rpath_npz, "logs:\n", rout["logs"])

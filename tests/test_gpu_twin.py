@@ -150,12 +150,23 @@ def test_gail_dyn_ppo_driver_matches_the_reference_run(tmp_path):
 
 
 def test_gail_dyn_ppo_driver_with_split_policy(tmp_path):
-    """The policy every shipped script trains (train_hopper_deform.sh:5: --use-split-pi --num-feet 1, hidden 100)."""
+    """The policy every shipped script trains (train_hopper_deform.sh:5: --use-split-pi --num-feet 1; hidden 100 here), held
+    against the reference's REAL main() run with --use-split-pi (tests/golden/twin_gail_dyn_ppo_split.npz)."""
+    z = np.load(os.path.join(HERE, "golden", "twin_gail_dyn_ppo_split.npz"))
     args, envs, logs, (actor_critic, discr, agent, rollouts), _ = _run_twin(tmp_path, act_dim=7, use_split_pi=True,
                                                                              num_feet=1, hidden_size=100)
     assert type(actor_critic).__name__ == "SplitPolicy" and len(logs) == 3
-    for d in logs:
-        assert all(np.isfinite(d[k]) for k in ("dist_entropy", "value_loss", "action_loss", "gail_loss"))
+    for row, d in zip(z["logs"], logs):
+        w = dict(zip(LOG_KEYS, row))
+        assert d["n_episodes"] == w["n_episodes"]
+        tol = 1e-4 if w["j"] == 0 else 2e-3
+        for k in ("dist_entropy", "value_loss", "gail_loss", "gail_loss_e", "gail_loss_p", "recent_gail_r"):
+            assert abs(d[k] - w[k]) <= tol * max(abs(w[k]), 1e-3), (w["j"], k, d[k], w[k])
+        assert abs(d["action_loss"] - w["action_loss"]) <= tol * max(abs(w["action_loss"]), 0.05), (w["j"], d["action_loss"])
+    worst = 0.0
+    for k, v in actor_critic.state_dict().items():
+        worst = max(worst, float((v.cpu() - torch.from_numpy(z["pol2_" + k])).abs().max()))
+    assert worst < 5e-3, worst
     compat.install()
     try:
         pol_cpu, _ = torch.load(os.path.join(str(tmp_path), "ppo", "FakeCombinedEnv-v1.pt"), map_location="cpu",

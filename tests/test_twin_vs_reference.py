@@ -129,3 +129,10 @@ def test_return_normalizer_equals_reference_vec_normalize():
         a = ref_filter(rews.copy(), news.copy())
         b = ours(rews.copy(), news.copy())
         assert a.dtype == b.dtype and np.array_equal(a, b), t
+
+
+def test_split_policy_golden_is_what_the_real_main_produces(tmp_path):
+    from oracle import make_golden_twin as mg
+    logs, _ = mg.run_reference(str(tmp_path / "split"), mg.SPLIT_CFG, mg.SPLIT_ARGV, act_dim=7)
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "twin_gail_dyn_ppo_split.npz"))
+    assert np.array_equal(z["logs"], np.array([[d[k] for k in mg.LOG_KEYS] for d in logs]))
