@@ -25,30 +25,40 @@
 
 namespace sg {
 
+// mt19937 state transition and tempering, written so that the host compiler vectorises them: within a pass, word k reads the
+// OLD words k+1 and k+397 (first 227 words) or the NEW word k-227 (the rest) -- the dependence distance is far beyond any vector
+// width.  Two copies: baseline x86-64 and, picked at run time, AVX2 (8 words per instruction).
+#define SG_MT_TWIST(dst, a, b, far) do { const uint32_t y_ = ((a) & 0x80000000u) | ((b) & 0x7fffffffu); \
+                                         (dst) = (far) ^ (y_ >> 1) ^ ((uint32_t)(-(int32_t)(y_ & 1u)) & 0x9908b0dfu); } while (0)
+#define SG_MT_REGENERATE_BODY                                                            \
+    for (int k = 0; k < 624 - 397; ++k) SG_MT_TWIST(key[k], key[k], key[k + 1], key[k + 397]);        \
+    for (int k = 624 - 397; k < 623; ++k) SG_MT_TWIST(key[k], key[k], key[k + 1], key[k + 397 - 624]); \
+    SG_MT_TWIST(key[623], key[623], key[0], key[396]);
+#define SG_MT_TEMPER_BODY                                                                \
+    for (int64_t j = 0; j < count; ++j) {                                                \
+        uint32_t y = in[j];                                                              \
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18; \
+        out[j] = y;                                                                      \
+    }
+static void mt_regenerate_base(uint32_t* __restrict__ key) { SG_MT_REGENERATE_BODY }
+static void mt_temper_base(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int64_t count) { SG_MT_TEMPER_BODY }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2"))) static void mt_regenerate_avx2(uint32_t* __restrict__ key) { SG_MT_REGENERATE_BODY }
+__attribute__((target("avx2"))) static void mt_temper_avx2(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int64_t count) { SG_MT_TEMPER_BODY }
+static bool mt_have_avx2() { static const bool v = __builtin_cpu_supports("avx2"); return v; }
+#else
+static void mt_regenerate_avx2(uint32_t* key) { mt_regenerate_base(key); }
+static void mt_temper_avx2(uint32_t* out, const uint32_t* in, int64_t count) { mt_temper_base(out, in, count); }
+static bool mt_have_avx2() { return false; }
+#endif
+
 struct Mt19937 {
     uint32_t key[624];
     int pos;                       // next word to temper; 624 = regenerate first
     void regenerate() {
-        constexpr uint32_t kUpper = 0x80000000u, kLower = 0x7fffffffu, kMatrix = 0x9908b0dfu;
-        int k = 0;
-        for (; k < 624 - 397; ++k) {
-            const uint32_t y = (key[k] & kUpper) | (key[k + 1] & kLower);
-            key[k] = key[k + 397] ^ (y >> 1) ^ ((y & 1u) ? kMatrix : 0u);
-        }
-        for (; k < 623; ++k) {
-            const uint32_t y = (key[k] & kUpper) | (key[k + 1] & kLower);
-            key[k] = key[k + 397 - 624] ^ (y >> 1) ^ ((y & 1u) ? kMatrix : 0u);
-        }
-        const uint32_t y = (key[623] & kUpper) | (key[0] & kLower);
-        key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? kMatrix : 0u);
+        if (mt_have_avx2()) mt_regenerate_avx2(key);
+        else mt_regenerate_base(key);
         pos = 0;
-    }
-    static inline uint32_t temper(uint32_t y) {
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        return y;
     }
     // advance by count draws without producing them
     void discard(int64_t count) {
@@ -66,7 +76,8 @@ struct Mt19937 {
             if (pos >= 624) regenerate();
             int64_t take = 624 - pos;
             if (take > count - i) take = count - i;
-            for (int64_t j = 0; j < take; ++j) out[i + j] = temper(key[pos + j]);
+            if (mt_have_avx2()) mt_temper_avx2(out + i, key + pos, take);
+            else mt_temper_base(out + i, key + pos, take);
             pos += (int)take;
             i += take;
         }
@@ -180,15 +191,49 @@ int sg_host_randperm_prefix(const uint32_t* mt_key, int mt_pos, int64_t n, int64
     std::vector<uint32_t> d((size_t)steps);
     mt.fill(d.data(), steps);
     mt.discard(n - 1 - steps);
-    std::vector<int32_t> r((size_t)n);
-    for (int64_t i = 0; i < n; ++i) r[i] = (int32_t)i;
+    if (steps > n / 8) {
+        // a long prefix: the plain dense walk
+        std::vector<int32_t> r((size_t)n);
+        for (int64_t i = 0; i < n; ++i) r[i] = (int32_t)i;
+        for (int64_t i = 0; i < steps; ++i) {
+            const int64_t j = i + d[i] % (uint32_t)(n - i);
+            const int32_t sav = r[i];
+            r[i] = r[j];
+            r[j] = sav;
+        }
+        std::memcpy(out, r.data(), (size_t)m * sizeof(int32_t));
+        if (mt_key_out) std::memcpy(mt_key_out, mt.key, sizeof(mt.key));
+        if (mt_pos_out) *mt_pos_out = mt.pos;
+        return SG_OK;
+    }
+    // the walk only ever touches positions i < steps and the `steps` partners i + z: positions below m live in `head`, the
+    // others in a small open-addressing table (absent = still the identity), so nothing of size n is allocated
+    std::vector<int32_t> head((size_t)m);
+    for (int64_t i = 0; i < m; ++i) head[i] = (int32_t)i;
+    size_t cap = 64;
+    while (cap < (size_t)steps * 2 + 2) cap <<= 1;
+    std::vector<int64_t> tkey(cap, -1);
+    std::vector<int32_t> tval(cap);
+    auto slot = [&](int64_t pos) -> size_t {
+        size_t h = ((uint64_t)pos * 0x9E3779B97F4A7C15ull) >> 20 & (cap - 1);
+        while (tkey[h] != -1 && tkey[h] != pos) h = (h + 1) & (cap - 1);
+        return h;
+    };
     for (int64_t i = 0; i < steps; ++i) {
         const int64_t j = i + d[i] % (uint32_t)(n - i);
-        const int32_t sav = r[i];
-        r[i] = r[j];
-        r[j] = sav;
+        if (j < m) {
+            const int32_t sav = head[i];
+            head[i] = head[j];
+            head[j] = sav;
+        } else {
+            const size_t h = slot(j);
+            const int32_t vj = tkey[h] == j ? tval[h] : (int32_t)j;
+            tkey[h] = j;
+            tval[h] = head[i];
+            head[i] = vj;
+        }
     }
-    std::memcpy(out, r.data(), (size_t)m * sizeof(int32_t));
+    std::memcpy(out, head.data(), (size_t)m * sizeof(int32_t));
     if (mt_key_out) std::memcpy(mt_key_out, mt.key, sizeof(mt.key));
     if (mt_pos_out) *mt_pos_out = mt.pos;
     return SG_OK;
