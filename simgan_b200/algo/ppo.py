@@ -18,6 +18,12 @@ from .adam import FusedAdam
 
 class PPO(object):
     MMA_MODE = 4        # kernel_mode: tcgen05 3xTF32 tensor-core tiles (sg_ppo_config.mode 4)
+    # From this many rows per minibatch on, the rows of every minibatch are visited in ascending sample order.  The sampler's
+    # partition of the rollout into minibatches (which samples, which minibatch: A2C/storage.py:158-185) is untouched; only the
+    # order in which a minibatch's rows are summed changes (every loss is a batch mean), like the tiling itself already does.
+    # A 128-row tile then reads rows that lie within a few MB of each other instead of 128 random places of a multi-GB
+    # buffer: the gather at the head of a tile was bound by address-translation misses, not by bytes.
+    SORT_ROWS_FROM = 1 << 14
 
     def __init__(self, actor_critic, clip_param, ppo_epoch, num_mini_batch, value_loss_coef, entropy_coef,
                  symmetry_coef=0, lr=None, eps=None, max_grad_norm=None, use_clipped_value_loss=True,
@@ -186,6 +192,9 @@ class PPO(object):
             elif e >= drawn0:
                 pstream.wait(e - drawn0)
             self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
+            if mbs >= self.SORT_ROWS_FROM:
+                rows = self._perm_dev[e][:nmb * mbs].view(nmb, mbs)
+                rows.copy_(torch.sort(rows, dim=1).values)
             cfg.first_adam_step = opt.step_count + 1 + e * nmb
             tok = _lib.timer.start("ppo_update")
             args = (C.byref(cfg), _lib.ptr(flat), _lib.ptr(m), _lib.ptr(v), _lib.ptr(rollouts.obs),

@@ -568,6 +568,13 @@ __device__ __forceinline__ void ppo_mma_prefetch_rows(const PpoArgs& a, int step
     }
 }
 
+// a plain global load the compiler cannot speculate above its guard (asm volatile)
+__device__ __forceinline__ float ld_guarded_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // ---- one job ------------------------------------------------------------------------------------------------------------------
 // first: no earlier job of this CTA in this optimizer step (gradient accumulators start from zero)
 template <int MR>
@@ -608,49 +615,59 @@ __device__ void ppo_mma_job(const PpoArgs& a, const MmaDims& d, MmaSmem& S, MmaP
         S.VALID[tid] = ok ? 1.f : 0.f;
     }
     __syncthreads();
-    // ---- gather observation (and action) rows into the masters: a warp covers 8 rows x 4 granules (64 contiguous bytes
-    //      per row); all loads of a thread are issued before its stores
+    // ---- gather observation (and action) rows into the masters.  A warp takes whole rows: its lanes read consecutive floats of
+    //      one sampled row (whole 128-byte lines whatever obs_dim is) and scatter them into the [col/4][row][col%4] master --
+    //      with the odd row pitch the 32 scalar stores of an instruction fall into 32 different banks.  The head of a job is a
+    //      burst of dependent, randomly placed HBM reads with nothing to overlap them with: what counts is how many rows are
+    //      in flight per warp (measured at obs_dim 111, 128 rows: 4 rows 11.5k cycles, 8 rows 7.5k; 4-byte cp.async copies of
+    //      everything at once 10k -- their issue rate binds; touch loads / a bulk L2 prefetch of the next job's rows: no gain).
     {
-        const int kq_l = lane & 3, r_l = lane >> 2;
-        const int xgroups = (d.xg + 3) >> 2, agroups = net == 0 ? (d.ag + 3) >> 2 : 0;
-        const int per_rg = xgroups + agroups;
-        const bool vecx = (O & 3) == 0, veca = (A & 3) == 0;
-        constexpr int GB = 4;
-        const int nit = (MR / 8) * per_rg;
-        for (int it0 = warp; it0 < nit; it0 += GB * (kStepThreads / 32)) {
-            float4 v[GB];
-            float4* dstp[GB];
+        float* Xf = reinterpret_cast<float*>(S.X);
+        const int ncx = d.Op8;                                  // master columns incl. zero padding
+        constexpr int GB = 8, NW = kStepThreads / 32;
+        for (int cb = 0; cb < ncx; cb += 128) {
+            for (int r0 = warp; r0 < MR; r0 += GB * NW) {
+                float v[GB][4];
 #pragma unroll
-            for (int u = 0; u < GB; ++u) {
-                const int it = it0 + u * (kStepThreads / 32);
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                dstp[u] = nullptr;
-                if (it < nit) {
-                    const int rg = it / per_rg, kg = it - rg * per_rg;
-                    const int r = 8 * rg + r_l;
-                    const int i = S.IDX[r];
-                    const bool isx = kg < xgroups;
-                    const int kq = 4 * (isx ? kg : kg - xgroups) + kq_l;
-                    const int ncol = isx ? O : A, ngr = isx ? d.xg : d.ag;
-                    if (kq < ngr) {
-                        dstp[u] = (isx ? S.X : S.ACT) + kq * MRP + r;
-                        const int k = 4 * kq;
-                        if (i >= 0 && k < ncol) {
-                            const float* p = (isx ? a.obs : a.actions) + (size_t)i * ncol + k;
-                            if (isx ? vecx : veca) v[u] = *reinterpret_cast<const float4*>(p);
-                            else {
-                                v[u].x = p[0];
-                                if (k + 1 < ncol) v[u].y = p[1];
-                                if (k + 2 < ncol) v[u].z = p[2];
-                                if (k + 3 < ncol) v[u].w = p[3];
-                            }
-                        }
+                for (int u = 0; u < GB; ++u) {
+                    const int r = r0 + u * NW;
+                    const int i = r < MR ? S.IDX[r] : -1;
+                    const float* src = a.obs + (size_t)(i < 0 ? 0 : i) * O + cb + lane;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        v[u][j] = 0.f;
+                        if (i >= 0 && cb + lane + 32 * j < O) v[u][j] = ld_guarded_f32(src + 32 * j);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    const int r = r0 + u * NW;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = cb + lane + 32 * j;
+                        if (r < MR && c < ncx) Xf[(((c >> 2) * MRP + r) << 2) + (c & 3)] = v[u][j];
                     }
                 }
             }
+        }
+        if (net == 0) {
+            float* Af = reinterpret_cast<float*>(S.ACT);
+            const int nca = 4 * d.ag;                           // <= 32
+            for (int r0 = warp; r0 < MR; r0 += GB * NW) {
+                float v[GB];
 #pragma unroll
-            for (int u = 0; u < GB; ++u)
-                if (dstp[u]) *dstp[u] = v[u];
+                for (int u = 0; u < GB; ++u) {
+                    const int r = r0 + u * NW;
+                    const int i = r < MR ? S.IDX[r] : -1;
+                    v[u] = 0.f;
+                    if (i >= 0 && lane < A) v[u] = ld_guarded_f32(a.actions + (size_t)i * A + lane);
+                }
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    const int r = r0 + u * NW;
+                    if (r < MR && lane < nca) Af[(((lane >> 2) * MRP + r) << 2) + (lane & 3)] = v[u];
+                }
+            }
         }
     }
     mma::fence_async_smem();            // the X master is G1's in-place hi operand
