@@ -270,7 +270,10 @@ int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int pas
  * sg_host_randperm_begin: start producing n_perms consecutive permutations of n elements into out (HOST, n_perms*n int32,
  * e.g. pinned staging) from the engine state (mt_key: the 624 state words, mt_pos: index of the next word, 624 = "regenerate
  * first" -- i.e. torch.get_rng_state()'s `state` and `next` fields).  One thread runs the engine, n_threads workers run the
- * walks of different permutations concurrently.  Returns a handle, or NULL (sg_last_error).
+ * walks of different permutations concurrently.  owned_mask: bit e set = permutation e is built here; for a clear bit the
+ * engine only advances past its draws and out[e] is left untouched (the ranks of one node split the walks of an update's
+ * permutations and exchange the results; every rank still ends with the same engine state).  n_perms <= 64.
+ * Returns a handle, or NULL (sg_last_error).
  * sg_host_randperm_wait: block until permutation e is complete in out[e*n .. (e+1)*n).
  * sg_host_randperm_end: join, write the engine state after the last draw (what torch.set_rng_state must receive so that the
  * generator is where n_perms torch.randperm(n) calls would have left it), free the handle.
@@ -278,7 +281,8 @@ int sg_selftest_mma(int M, int N, int K, int a_mn_major, int b_mn_major, int pas
  * consumes of it, third_party/a2c_ppo_acktr/algo/gail.py:159-166) while the engine still advances by all n-1 draws. */
 int sg_host_randperm_prefix(const uint32_t* mt_key, int mt_pos, int64_t n, int64_t m, int32_t* out, uint32_t* mt_key_out,
                             int* mt_pos_out);
-void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int n_perms, int32_t* out, int n_threads);
+void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int n_perms, int32_t* out, int n_threads,
+                             uint64_t owned_mask);
 int sg_host_randperm_wait(void* handle, int e);
 int sg_host_randperm_end(void* handle, uint32_t* mt_key_out, int* mt_pos_out);
 

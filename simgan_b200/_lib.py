@@ -81,7 +81,7 @@ SIGNATURES = {
                                   C.c_double, c_void, C.c_int, c_void, c_void, c_void, c_void]),
     "sg_selftest_division": (C.c_int, [C.c_uint64, C.c_int, C.c_int, C.c_double, C.c_double, c_void, c_void]),
     "sg_selftest_mma": (C.c_int, [C.c_int] * 6 + [c_void] * 3 + [C.POINTER(C.c_int), c_void]),
-    "sg_host_randperm_begin": (C.c_void_p, [c_void, C.c_int, C.c_int64, C.c_int, c_void, C.c_int]),
+    "sg_host_randperm_begin": (C.c_void_p, [c_void, C.c_int, C.c_int64, C.c_int, c_void, C.c_int, C.c_uint64]),
     "sg_host_randperm_prefix": (C.c_int, [c_void, C.c_int, C.c_int64, C.c_int64, c_void, c_void, C.POINTER(C.c_int)]),
     "sg_host_randperm_wait": (C.c_int, [c_void, C.c_int]),
     "sg_host_randperm_end": (C.c_int, [c_void, c_void, C.POINTER(C.c_int)]),

@@ -79,8 +79,19 @@ class PPO(object):
         S = self._last_S
         if S is None or _spec.still_valid(self._predraw, S):
             return
+        if self._shares_permutations(S) and self.dp.rank != 0:
+            return          # rank 0 builds (and broadcasts) the first permutation; see update()
         self._predraw = _spec.predraw(S, lambda: host_sampler.randperm_i32(S))
         self._schedule(self.ppo_epoch * self.num_mini_batch)      # pure host arithmetic; cached by its inputs
+
+    def _shares_permutations(self, S):
+        """Sharded data-parallel updates over a large rollout: every rank would walk the SAME ppo_epoch permutations of S
+        elements (identical seeds) -- tens of ms of host time each, more than an epoch's kernel once the minibatch is split
+        over several GPUs.  The ranks split the walks instead (permutation e is built by rank e % world and broadcast on the
+        device); every rank still runs the mt19937 engine through all draws, so the generators stay identical."""
+        dp = self.dp
+        return (dp is not None and dp.world > 1 and getattr(self, "last_sharded", False) and dp.transport == "p2p"
+                and S >= host_sampler.MIN_ELEMENTS and host_sampler.usable())
 
     def _schedule(self, n_steps):
         """Adam step-size scalars of the next n_steps (FusedAdam.schedule), cached by everything they depend on."""
@@ -179,19 +190,29 @@ class PPO(object):
             first, self._predraw = _spec.take(self._predraw, S), None
         cfg.ppo_epoch = 1
         pstream, drawn0 = None, 0
+        share = permutations is None and dp is not None and self._shares_permutations(S)
         if permutations is None:
             # the remaining epochs' permutations are produced on helper threads while the epochs' kernels run
             # (host_sampler.PermutationStream: the same mt19937 stream torch.randperm would consume)
             if first is not None:
                 self._stage[0].copy_(first)
                 drawn0 = 1
-            pstream = host_sampler.PermutationStream(S, self.ppo_epoch - drawn0, self._stage[drawn0:])
+            owned = [e % dp.world == dp.rank for e in range(drawn0, self.ppo_epoch)] if share else None
+            pstream = host_sampler.PermutationStream(S, self.ppo_epoch - drawn0, self._stage[drawn0:], owned=owned)
         for e in range(self.ppo_epoch):
             if permutations is not None:
                 self._stage[e].copy_(permutations[e])
             elif e >= drawn0:
                 pstream.wait(e - drawn0)
-            self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
+            if share:
+                import torch.distributed as dist
+                owner = e % dp.world
+                if owner == dp.rank:
+                    self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
+                dist.broadcast(self._perm_dev[e], src=dist.get_global_rank(dp.group, owner) if dp.group is not None else owner,
+                               group=dp.group)
+            else:
+                self._perm_dev[e].copy_(self._stage[e], non_blocking=True)
             if mbs >= self.SORT_ROWS_FROM:
                 rows = self._perm_dev[e][:nmb * mbs].view(nmb, mbs)
                 rows.copy_(torch.sort(rows, dim=1).values)

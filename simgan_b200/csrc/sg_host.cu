@@ -111,6 +111,7 @@ struct RandpermJob {
     int64_t n = 0;
     int n_perms = 0;
     int32_t* out = nullptr;
+    uint64_t owned = ~0ull;                   // bit e: permutation e is built here (others only move the engine)
     std::vector<std::vector<uint32_t>> draws;
     std::vector<int> drawn, done;             // guarded by m
     int next = 0;                             // next permutation a worker takes (guarded by m)
@@ -121,12 +122,19 @@ struct RandpermJob {
 
     void generator() {
         for (int e = 0; e < n_perms; ++e) {
-            std::vector<uint32_t> d((size_t)(n > 1 ? n - 1 : 0));
-            mt.fill(d.data(), (int64_t)d.size());
+            std::vector<uint32_t> d;
+            const bool mine = (owned >> e) & 1ull;
+            if (mine) {
+                d.resize((size_t)(n > 1 ? n - 1 : 0));
+                mt.fill(d.data(), (int64_t)d.size());
+            } else {
+                mt.discard(n > 1 ? n - 1 : 0);
+            }
             {
                 std::lock_guard<std::mutex> lk(m);
                 draws[e] = std::move(d);
                 drawn[e] = 1;
+                if (!mine) done[e] = 1;
             }
             cv.notify_all();
         }
@@ -140,6 +148,7 @@ struct RandpermJob {
                 if (next >= n_perms) return;
                 e = next++;
                 cv.wait(lk, [&] { return drawn[e] != 0; });
+                if (!((owned >> e) & 1ull)) continue;
                 d = std::move(draws[e]);
             }
             fisher_yates(out + (size_t)e * n, d.data(), n);
@@ -159,15 +168,16 @@ using namespace sg;
 extern "C" {
 #pragma GCC visibility push(default)
 
-void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int n_perms, int32_t* out, int n_threads) {
-    if (!mt_key || !out || n < 1 || n_perms < 1 || mt_pos < 0 || mt_pos > 624 || n >= (int64_t)(0xffffffffu / 20u)) {
-        set_error("sg_host_randperm_begin: bad arguments (n must be in [1, 2^32/20): above that ATen switches algorithm)");
+void* sg_host_randperm_begin(const uint32_t* mt_key, int mt_pos, int64_t n, int n_perms, int32_t* out, int n_threads,
+                             uint64_t owned_mask) {
+    if (!mt_key || !out || n < 1 || n_perms < 1 || n_perms > 64 || mt_pos < 0 || mt_pos > 624 || n >= (int64_t)(0xffffffffu / 20u)) {
+        set_error("sg_host_randperm_begin: bad arguments (n in [1, 2^32/20): above that ATen switches algorithm; at most 64 permutations per stream)");
         return nullptr;
     }
     RandpermJob* j = new RandpermJob();
     std::memcpy(j->mt.key, mt_key, sizeof(j->mt.key));
     j->mt.pos = mt_pos;
-    j->n = n; j->n_perms = n_perms; j->out = out;
+    j->n = n; j->n_perms = n_perms; j->out = out; j->owned = owned_mask;
     j->draws.resize(n_perms);
     j->drawn.assign(n_perms, 0);
     j->done.assign(n_perms, 0);

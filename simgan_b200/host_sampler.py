@@ -53,16 +53,22 @@ def _pack(state, key, pos):
 class PermutationStream(object):
     """``n_perms`` consecutive ``torch.randperm(n)`` results written into ``out`` (int32, (n_perms, n), host)."""
 
-    def __init__(self, n, n_perms, out):
+    def __init__(self, n, n_perms, out, owned=None):
+        """``owned``: optional sequence of n_perms bools -- only those permutations are built into ``out`` (the engine still
+        advances past the others: the ranks of one node split the walks and exchange the results); C stream only."""
         assert out.dtype == torch.int32 and out.is_contiguous() and tuple(out.shape) == (n_perms, n) and not out.is_cuda
         self.n, self.n_perms, self.out = n, n_perms, out
+        mask = (1 << 64) - 1
+        if owned is not None:
+            assert len(owned) == n_perms <= 64 and n >= MIN_ELEMENTS and usable()
+            mask = sum(1 << e for e, o in enumerate(owned) if o)
         self._h = None
         self._state = None
         self._done = 0
         if n_perms > 0 and n >= MIN_ELEMENTS and usable():
             self._state = torch.get_rng_state()
             key, pos, _ = _unpack(self._state)
-            h = _lib.lib().sg_host_randperm_begin(key.ctypes.data, pos, n, n_perms, out.data_ptr(), _threads())
+            h = _lib.lib().sg_host_randperm_begin(key.ctypes.data, pos, n, n_perms, out.data_ptr(), _threads(), mask)
             if not h:
                 _lib.check(1, "sg_host_randperm_begin")
             self._h = h
@@ -142,7 +148,7 @@ def usable():
                     torch.set_rng_state(start)
                     key, pos, seeded = _unpack(start)
                     out = torch.empty(3, n, dtype=torch.int32)
-                    h = _lib.lib().sg_host_randperm_begin(key.ctypes.data, pos, n, 3, out.data_ptr(), 2)
+                    h = _lib.lib().sg_host_randperm_begin(key.ctypes.data, pos, n, 3, out.data_ptr(), 2, (1 << 64) - 1)
                     if not h or not seeded:
                         ok = False
                         break

@@ -174,3 +174,67 @@ def test_split_policy_data_parallel_matches_single_gpu(tmp_path):
         out = str(tmp_path / ("ok_" + case))
         mp.spawn(_split_worker, args=(world, _free_port(), case, out), nprocs=world, join=True)
         assert os.path.exists(out)
+
+
+# ---- large rollout: the ranks split the permutation walks of an update and broadcast them (PPO._shares_permutations) -----------
+def _big_case(dev, dp_on):
+    import simgan_b200 as sg
+    from simgan_b200 import dist as sg_dist
+    from oracle.ref_shim import BoxSpace
+    T, N, O, A, H = 64, 2048, 16, 4, 64              # S = 131072 = host_sampler.MIN_ELEMENTS, 4 minibatches of 32768 rows
+    torch.manual_seed(5)
+    pol = sg.Policy((O,), BoxSpace(A), base_kwargs={"recurrent": False, "hidden_size": H})
+    pol.to(dev)
+    rs = sg.RolloutStorage(T, N, (O,), BoxSpace(A), 1, 3)
+    g = torch.Generator().manual_seed(9)
+    rs.obs.copy_(torch.randn(rs.obs.shape, generator=g))
+    rs.actions.copy_(torch.randn(rs.actions.shape, generator=g))
+    rs.value_preds.copy_(torch.randn(rs.value_preds.shape, generator=g))
+    rs.returns.copy_(torch.randn(rs.returns.shape, generator=g))
+    rs.action_log_probs.fill_(-float(A))
+    rs.to(dev)
+    agent = sg.PPO(pol, 0.2, 3, 4, 0.5, 0.01, lr=3e-4, eps=1e-5, max_grad_norm=0.5)
+    if dp_on:
+        sg_dist.attach(ppo=agent, policy="auto")
+    torch.manual_seed(77)
+    outs = [agent.update(rs) for _ in range(2)]      # second call: rank 0 takes its early draw, the others do not have one
+    torch.cuda.synchronize()
+    return np.array(outs), agent.last_trace.clone(), agent._perm_dev.cpu().clone(), torch.get_rng_state(), agent
+
+
+def _big_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.cuda.set_device(rank)
+    dev = "cuda:%d" % rank
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        torch.set_num_threads(1)
+        res = _big_case(dev, True)
+        assert res[4].last_sharded and res[4]._shares_permutations(64 * 2048)
+        # every rank holds the same permutations and the same generator state
+        ref = res[2].to(dev).clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref.cpu(), res[2]), "permutations differ between ranks"
+        st = res[3].to(dev).clone()
+        dist.broadcast(st, 0)
+        assert torch.equal(st.cpu(), res[3]), "generator states differ between ranks"
+        dist.barrier()
+        if rank == 0:
+            one = _big_case(dev, False)
+            assert torch.equal(one[2], res[2]) and torch.equal(one[3], res[3])          # same index streams as one GPU
+            assert np.all(np.abs(res[0] - one[0]) <= 1e-4 * np.maximum(np.abs(one[0]), 0.05)), (res[0], one[0])
+            open(out, "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_large_rollout_ranks_split_the_permutation_walks(tmp_path):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    out = str(tmp_path / "ok_big")
+    _spawn(_big_worker, lambda port: (2, port, out), 2)
+    assert os.path.exists(out)

@@ -513,3 +513,22 @@ def test_return_normalizer_restated():
         got = ours(rews, news)
         assert np.array_equal(got, want), t
     assert ours.ret_rms.count == count and ours.ret_rms.var == var
+
+
+def test_permutation_stream_owned_subset():
+    """The ranks of one node split the walks of an update's permutations: a rank builds only the ones it owns, yet its
+    generator ends where all the draws leave it."""
+    from simgan_b200 import host_sampler as hs
+    n = 1 << 17
+    torch.manual_seed(7)
+    want = [torch.randperm(n) for _ in range(5)]
+    after = torch.get_rng_state()
+    torch.manual_seed(7)
+    out = torch.full((5, n), -1, dtype=torch.int32)
+    ps = hs.PermutationStream(n, 5, out, owned=[True, False, True, False, False])
+    for e in range(5):
+        ps.wait(e)
+    ps.finish()
+    assert torch.equal(out[0].long(), want[0]) and torch.equal(out[2].long(), want[2])
+    assert bool((out[1] == -1).all()) and bool((out[3] == -1).all()) and bool((out[4] == -1).all())
+    assert torch.equal(torch.get_rng_state(), after)
