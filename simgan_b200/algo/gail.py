@@ -95,7 +95,7 @@ class Discriminator(nn.Module):
         state.pop("_prof_view", None)
         state.pop("_rms_dev", None)
         state.pop("_predraw", None)
-        for k in ("_stage", "_stage_cur", "_side_upload", "_copy_stream", "_last_key", "_relabel_ws"):
+        for k in ("_stage", "_stage_cur", "_side_upload", "_copy_stream", "_last_key", "_relabel_ws", "_relabel_raw"):
             state.pop(k, None)
         return state
 
@@ -399,6 +399,8 @@ class Discriminator(nn.Module):
             self.eval()
             return torch.sigmoid(self.trunk(torch.cat([state, action], dim=1)))
 
+    SHARD_RELABEL_FROM = 1 << 20        # rows (T*N) from which a data-parallel relabel splits its D forward over the ranks
+
     @_lib.on_device(lambda self, *a, **k: self.trunk[0].weight.device)
     def relabel_rollout(self, rollouts, gamma, offset, ret_rms, sync=True):
         """The caller's whole relabel loop (main_gail_dyn_ppo.py:275-297) in one device pass:
@@ -424,10 +426,35 @@ class Discriminator(nn.Module):
                                device=dev)
         mean_returns = torch.empty(T, device=dev)
         tok = _lib.timer.start("disc_relabel")
-        rc = lib.sg_disc_relabel(_lib.ptr(flat), self.feat_dim, self.hidden_dim, _lib.ptr(rollouts.obs_feat),
-                                 _lib.ptr(rollouts.masks), _lib.ptr(rollouts.rewards), T, N, float(gamma), float(offset),
-                                 _lib.ptr(self.returns), int(has), _lib.ptr(rms_dev), _lib.ptr(mean_returns),
-                                 _lib.ptr(ws), _lib.current_stream())
+        dp = self.dp
+        rows = T * N
+        if dp is not None and dp.world > 1 and rows >= self.SHARD_RELABEL_FROM:
+            # data parallel over a large rollout: the D forward over the T*N rows (all of the relabel's arithmetic weight) is
+            # split by rows over the ranks and all-gathered; a row's reward does not depend on the split, and the serial,
+            # bit-exact part (running-return scan, moments, RunningMeanStd chain, normalise + clip) then runs on every rank
+            # from the same raw rewards -- the replicas stay bit-identical
+            import torch.distributed as dist
+            chunk = (rows + dp.world - 1) // dp.world
+            raw = self.__dict__.get("_relabel_raw")
+            if raw is None or raw.numel() != chunk * dp.world or raw.device != dev:
+                raw = torch.empty(chunk * dp.world, device=dev)
+                self.__dict__["_relabel_raw"] = raw
+            b, e = dp.rank * chunk, min(rows, (dp.rank + 1) * chunk)
+            feat = rollouts.obs_feat[1:].reshape(rows, self.feat_dim)          # reward_t reads obs_feat[t+1] (:278)
+            if e > b:
+                rc = lib.sg_disc_predict_reward(_lib.ptr(flat), self.feat_dim, self.hidden_dim, _lib.ptr(feat[b:e]), e - b,
+                                                float(gamma), None, float(offset), 0, _lib.ptr(raw[b:e]), None,
+                                                _lib.current_stream())
+                _lib.check(rc, "sg_disc_predict_reward")
+            dist.all_gather_into_tensor(raw, raw[dp.rank * chunk:(dp.rank + 1) * chunk], group=dp.group)
+            rc = lib.sg_relabel_normalize(_lib.ptr(raw), _lib.ptr(rollouts.masks), _lib.ptr(rollouts.rewards), T, N,
+                                          float(gamma), _lib.ptr(self.returns), int(has), _lib.ptr(rms_dev),
+                                          _lib.ptr(mean_returns), _lib.ptr(ws), _lib.current_stream())
+        else:
+            rc = lib.sg_disc_relabel(_lib.ptr(flat), self.feat_dim, self.hidden_dim, _lib.ptr(rollouts.obs_feat),
+                                     _lib.ptr(rollouts.masks), _lib.ptr(rollouts.rewards), T, N, float(gamma), float(offset),
+                                     _lib.ptr(self.returns), int(has), _lib.ptr(rms_dev), _lib.ptr(mean_returns),
+                                     _lib.ptr(ws), _lib.current_stream())
         _lib.timer.stop(tok)
         _lib.check(rc, "sg_disc_relabel")
         self.__dict__["_rms_dev"] = rms_dev

@@ -238,3 +238,60 @@ def test_large_rollout_ranks_split_the_permutation_walks(tmp_path):
     out = str(tmp_path / "ok_big")
     _spawn(_big_worker, lambda port: (2, port, out), 2)
     assert os.path.exists(out)
+
+
+# ---- large rollout: the relabel's D forward is split by rows over the ranks (Discriminator.SHARD_RELABEL_FROM) ---------------
+def _relabel_case(dev, dp_on):
+    import simgan_b200 as sg
+    from simgan_b200 import dist as sg_dist
+    from oracle.ref_shim import BoxSpace
+    T, N, F = 512, 2048 + 3, 25                      # T*N just above 2^20, not divisible by the world size
+    torch.manual_seed(3)
+    d = sg.Discriminator(F, 100, torch.device(dev))
+    rs = sg.RolloutStorage(T, N, (4,), BoxSpace(2), 1, F)
+    g = torch.Generator().manual_seed(4)
+    rs.obs_feat.copy_(torch.randn(rs.obs_feat.shape, generator=g))
+    rs.masks.copy_((torch.rand(rs.masks.shape, generator=g) > 0.02).float())
+    rs.to(dev)
+    if dp_on:
+        sg_dist.attach(disc=d, policy="auto")
+    rms = sg.RunningMeanStd(shape=())
+    outs = []
+    for _ in range(2):                               # the second pass starts from carried returns / statistics
+        mr = d.relabel_rollout(rs, 0.99, -0.3, rms)
+        outs.append((rs.rewards.cpu().clone(), d.returns.cpu().clone(), mr.cpu().clone(), float(rms.mean), float(rms.var), rms.count))
+    return outs
+
+
+def _relabel_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.cuda.set_device(rank)
+    dev = "cuda:%d" % rank
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    try:
+        torch.set_num_threads(1)
+        res = _relabel_case(dev, True)
+        ref = res[1][0].to(dev).clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(ref.cpu(), res[1][0]), "ranks diverged"
+        dist.barrier()
+        if rank == 0:
+            one = _relabel_case(dev, False)
+            for a, b in zip(res, one):
+                assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])      # bit-identical
+                assert a[3:] == b[3:]
+            open(out, "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_large_rollout_relabel_forward_is_split_over_the_ranks(tmp_path):
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    out = str(tmp_path / "ok_relabel")
+    _spawn(_relabel_worker, lambda port: (2, port, out), 2)
+    assert os.path.exists(out)
