@@ -68,7 +68,12 @@ class PermutationStream(object):
         if n_perms > 0 and n >= MIN_ELEMENTS and usable():
             self._state = torch.get_rng_state()
             key, pos, _ = _unpack(self._state)
-            h = _lib.lib().sg_host_randperm_begin(key.ctypes.data, pos, n, n_perms, out.data_ptr(), _threads(), mask)
+            threads = _threads()
+            if owned is not None:
+                # a rank that owns two walks of the update runs them side by side: the second one is needed only a few
+                # kernels after the first (the walks are memory-latency bound, so this pays even on a busy node)
+                threads = max(threads, min(2, sum(1 for o in owned if o)))
+            h = _lib.lib().sg_host_randperm_begin(key.ctypes.data, pos, n, n_perms, out.data_ptr(), threads, mask)
             if not h:
                 _lib.check(1, "sg_host_randperm_begin")
             self._h = h
