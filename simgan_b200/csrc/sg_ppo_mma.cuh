@@ -10,7 +10,8 @@
 //   G4 dWh^T = H2^T dHead   G5 dH2 = dHead Wh   G6 dW2 = dZ2^T H1   G7 dH1 = dZ2 W2   G8 dW1 = dZ1^T X
 // each formed as D(tmem) = A.B^T by ONE thread issuing tcgen05.mma over K-chunks of shared-memory operand images.
 //
-// fp32 accuracy on TF32 tensor cores: every operand is split a = hi + lo (hi = RN_tf32(a), lo = RN_tf32(a - hi)) and a
+// fp32 accuracy on TF32 tensor cores: every operand is split a = hi + lo (activations: hi = the top 19 bits of the word, which
+// is what the tensor core reads of it anyway, lo = a - hi exactly; weight images: hi = RN_tf32(a), lo = RN_tf32(a - hi)) and a
 // product is three MMAs lo*hi + hi*lo + hi*hi ("3xTF32", ~2^-21 relative), which keeps the 1e-4 loss contract.
 //
 // Data flow
@@ -19,14 +20,16 @@
 //                of an fp32 word, so a K-major activation operand's hi pass reads the master in place; per K-chunk the
 //                seven "filler" warps build only its lo image (x - trunc(x)) -- or, for the MN-major operands of the
 //                weight-gradient contractions, the hi and lo images -- in a ring of stage buffers (sg_mma.cuh);
-//   pipeline     warp 0 is the control warp: one thread issues the TMA copies of the weight chunks (ring depth ahead) and
-//                the MMAs; fillers and issuer meet only through mbarriers (filled[s]: image ready, full[s]: weight chunk
-//                landed, done[s]: the MMAs that read stage s completed), so filling chunk c+1.., the TMA of chunk c+2..
-//                and the MMAs of chunk c overlap; the CTA only joins again at the epilogue;
+//   pipeline     warp 0 is the control warp: one thread issues the MMAs; the first filler thread requests the weight chunks (a
+//                stage is refilled by whoever sees it free, so the issuer never waits for a completion); fillers and issuer
+//                meet only through mbarriers (filled[s]: image ready, full[s]: weight chunk landed, done[s]: the MMAs that
+//                read stage s completed), so filling chunk c+1.., the TMA of chunk c+2.. and the MMAs of chunk c overlap;
+//                the CTA only joins again at the epilogue;
 //   weights      are kept as ready-made hi / lo operand images of the whole K extent in global memory (L2): the CTA that
 //                owns a slice of the parameter vector rewrites the image entries of its parameters right after their Adam
 //                update, so a K-chunk of a weight operand is two contiguous TMA bulk copies (cp.async.bulk -> mbarrier
-//                transaction bytes) issued one to two chunks ahead -- no register staging, no split arithmetic;
+//                transaction bytes) issued as many chunks ahead as the ring has stages -- no register staging, no split
+//                arithmetic;
 //   accumulators live in tensor memory; epilogues read them with tcgen05.ld (thread = row, or = hidden unit for the weight
 //                gradients), apply bias / tanh / tanh' and write the next master or the CTA's partial gradient.  When the
 //                three weight-gradient accumulators fit beside the working accumulator (hidden <= 128) they stay in
