@@ -77,3 +77,36 @@ def test_data_parallel_host_logic_world2(tmp_path):
 def test_attach_is_a_noop_without_process_group():
     from simgan_b200 import dist as sg_dist
     assert sg_dist.attach() is None
+
+
+def _walk_worker(rank, world, port, out_dir):
+    """The ranks of a node split the walks of an update's permutations (PPO._shares_permutations): rank e % world builds
+    permutation e, broadcasts it, and every rank ends with the generator where ppo_epoch torch.randperm calls leave it."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from simgan_b200 import host_sampler as hs
+        n, k = 1 << 17, 5
+        torch.manual_seed(31)
+        want = [torch.randperm(n) for _ in range(k)]
+        tail = torch.rand(3)
+        torch.manual_seed(31)
+        stage = torch.full((k, n), -1, dtype=torch.int32)
+        ps = hs.PermutationStream(n, k, stage, owned=[e % world == rank for e in range(k)])
+        for e in range(k):
+            ps.wait(e)
+            dist.broadcast(stage[e], e % world)
+            assert torch.equal(stage[e].long(), want[e]), e
+        ps.finish()
+        assert torch.equal(torch.rand(3), tail)
+        open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranks_split_the_permutation_walks_world2(tmp_path):
+    world = 2
+    mp.spawn(_walk_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
